@@ -1,0 +1,178 @@
+/* fmri_b200.h — C ABI of libfmri_b200.so: the sm_100a kernels behind the VAE/GAN / WAE/GAN training step of
+ * MariaPdg/thesis-fmri-reconstruction (models/vae_gan.py + the update logic of train/train_{vgan,wae}_stage*.py).
+ *
+ * The reference has no FFI of its own: every op below is reached in the reference through torch.nn / ATen.
+ * Each entry point cites the reference call site whose arithmetic it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - extern "C"; plain pointers and sizes; no torch types.
+ *  - return 0 on success, a negative fmri_status on error; fmri_last_error() gives a thread-local message.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call allocates device memory,
+ *    synchronises the device, or touches host memory after returning. Workspaces are caller-owned.
+ *  - activations are channels-last ("NHWC", [N,H,W,C] dense) in `dtype` (FMRI_BF16 -> tcgen05/TMEM/TMA tensor path,
+ *    FMRI_F32 -> exact CUDA-core path). Master weights, gradients of weights, statistics and losses are fp32
+ *    (statistic accumulators fp64). Weight tensors keep the reference layouts
+ *    (Conv2d [Cout,Cin,5,5], ConvTranspose2d [Cin,Cout,5,5], Linear [out,in]).
+ *  - all convolutions are 5x5, padding 2 (configs/models_config.py:3-5).
+ */
+#ifndef FMRI_B200_H
+#define FMRI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMRI_ABI_VERSION 1
+
+typedef enum { FMRI_OK = 0, FMRI_ERR_ARG = -1, FMRI_ERR_UNSUPPORTED = -2, FMRI_ERR_CUDA = -3, FMRI_ERR_WORKSPACE = -4 } fmri_status;
+typedef enum { FMRI_F32 = 0, FMRI_BF16 = 1 } fmri_dtype;
+typedef enum { FMRI_ACT_NONE = 0, FMRI_ACT_RELU = 1, FMRI_ACT_TANH = 2, FMRI_ACT_SIGMOID = 3 } fmri_act;
+
+int fmri_version(void);
+const char* fmri_last_error(void);
+/* 1 when the running device is sm_100 and the tensor path can be used, 0 otherwise (no GPU: 0, no error). */
+int fmri_tensor_path_available(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 5x5 convolutions on C>=32 channels — tcgen05 implicit GEMM (bf16) or direct CUDA-core conv (fp32).
+ * Geometry is that of the FORWARD op: input [N,H,W,Cin] -> output [N,OH,OW,Cout],
+ *   Conv2d:          OH = (H-1)/stride + 1                      (vae_gan.py:18-20, :118, :145)
+ *   ConvTranspose2d: OH = 2H-1+output_pad, stride 2             (vae_gan.py:46-53)
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int N, H, W, Cin, Cout;
+    int stride;      /* 1 or 2 */
+    int transposed;  /* 0 Conv2d, 1 ConvTranspose2d */
+    int output_pad;  /* ConvTranspose2d only */
+    int dtype;       /* fmri_dtype of activations and activation gradients */
+} fmri_conv_desc;
+
+void fmri_conv_out_hw(const fmri_conv_desc* d, int* OH, int* OW);
+/* bf16 tap-major weight packs consumed by the tensor path: pack_f [25][Cout][Cin] (fprop), pack_d [25][Cin][Cout]
+ * (dgrad). Each 25*Cin*Cout bf16. Refreshed after every optimizer step. Either pointer may be NULL. */
+int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, void* pack_f, void* pack_d, void* stream);
+/* y = act(conv(x, w) + bias); optionally accumulates per-output-channel sum / sum-of-squares of the stored y into
+ * fp64 stat_sum/stat_sq[Cout] (BatchNorm batch statistics, vae_gan.py:21). `w` fp32 master weights (used by the fp32
+ * path), `pack_f` bf16 pack (used by the bf16 path). */
+int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const float* w, const void* pack_f, const float* bias,
+                    int act, void* y, double* stat_sum, double* stat_sq, void* stream);
+/* dx = conv data-gradient of dy (replaces aten::convolution_backward input-grad) */
+int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const float* w, const void* pack_d, void* dx,
+                    void* stream);
+/* dw (+)= conv weight-gradient, reference layout fp32. Workspace: fmri_conv_wgrad_workspace() bytes. */
+size_t fmri_conv_wgrad_workspace(const fmri_conv_desc* d);
+int fmri_conv_wgrad(const fmri_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Edge convolutions with a 3-channel image side kept in the module-boundary format (NCHW fp32):
+ *   "in"  : Conv2d(3, C)  image -> C-channel NHWC activation   (Encoder.conv[0] vae_gan.py:74, Discriminator.conv[0] :145)
+ *   "out" : Conv2d(C, 3)  C-channel NHWC activation -> image   (Decoder.conv[3] vae_gan.py:118-121, +bias +tanh)
+ * C in {32, 64}. Up to three image sources are read back-to-back on the batch axis (the discriminator's torch.cat,
+ * vae_gan.py:165) — pass the same pointer / NULL for unused ones and n_per_src = N for a single source.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int N, H, W;  /* image-side grid for "in" (input image), C-side grid equals image grid for "out" (stride 1) */
+    int C;        /* channel count of the wide side */
+    int stride;   /* "in" only: 1 or 2 */
+    int dtype;    /* dtype of the C-channel activation */
+} fmri_edge_desc;
+int fmri_edge_in_fprop(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2, int n_per_src,
+                       const float* w, const float* bias, int act, void* y, void* ws, size_t ws_bytes, void* stream);
+/* dimg[N,3,H,W] = data gradient wrt the concatenated image batch */
+int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const float* w, float* dimg, void* ws, size_t ws_bytes,
+                       void* stream);
+int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2, int n_per_src,
+                       const void* dy, float* dw, int accumulate, void* ws, size_t ws_bytes, void* stream);
+int fmri_edge_out_fprop(const fmri_edge_desc* d, const void* x, const float* w, const float* bias, int act, float* img,
+                        void* ws, size_t ws_bytes, void* stream);
+int fmri_edge_out_dgrad(const fmri_edge_desc* d, const float* dimg, const float* w, void* dx, void* ws, size_t ws_bytes,
+                        void* stream);
+int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const float* dimg, float* dw, int accumulate, void* ws,
+                        size_t ws_bytes, void* stream);
+size_t fmri_edge_workspace(const fmri_edge_desc* d); /* 75*C floats, enough for every edge call */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Linear layers (nn.Linear: vae_gan.py:79,84-85,107,156,160,199,206-207,510-519)
+ *   fprop: y[M,N] = act(x[M,K] w[N,K]^T + bias)      dgrad: dx[M,K] = dy[M,N] w[N,K]      wgrad: dw[N,K] (+)= dy^T x
+ * Row pitches (elements) are explicit so K can be padded to the 16-byte TMA pitch (K = 3620 fMRI voxels -> 3624).
+ * bf16 path operands: x / dy bf16; `wp` = bf16 copy of w with pitch ldw (fprop), `wpt` = bf16 copy of w^T [K,N]
+ * with pitch ldwt (dgrad). fp32 path: x / dy fp32 and the fp32 master `w` (pitch K) is used directly.
+ * y_dtype may be FMRI_F32 even on the bf16 path (latent heads, split-K accumulation).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int M, N, K;
+    int dtype;
+} fmri_linear_desc;
+int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* w, void* wp, int ldw, void* wpt, int ldwt,
+                             void* stream);
+int fmri_linear_fprop(const fmri_linear_desc* d, const void* x, int ldx, const float* w, const void* wp, int ldw,
+                      const float* bias, int act, void* y, int ldy, int y_dtype, void* stream);
+int fmri_linear_dgrad(const fmri_linear_desc* d, const void* dy, int lddy, const float* w, const void* wpt, int ldwt,
+                      void* dx, int lddx, int dx_dtype, void* stream);
+int fmri_linear_wgrad(const fmri_linear_desc* d, const void* x, int ldx, const void* dy, int lddy, float* dw,
+                      int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm (train: batch statistics; momentum semantics of torch, momentum=0.9 in the reference) + ReLU on a
+ * channels-last [rows, C] matrix. vae_gan.py:21,27-34,54,58-59,80-82,108-109,158-159,200-201
+ * --------------------------------------------------------------------------------------------------------- */
+int fmri_colstats(const void* x, int dtype, long long rows, int C, double* sum, double* sq, void* stream);
+int fmri_bn_finalize(const double* sum, const double* sq, long long rows, int C, float eps, float momentum, float* mean,
+                     float* invstd, float* running_mean, float* running_var, void* stream);
+int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, const float* mean,
+                  const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
+/* dx, dgamma (+)=, dbeta (+)= ; train=0 treats mean/invstd as constants (eval-mode BN). ws: 2*C doubles. */
+int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
+                     const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, int train,
+                     float* dgamma, float* dbeta, int accumulate, double* ws, void* stream);
+int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream);
+int fmri_colsum(const void* x, int dtype, long long rows, int C, float* out /* += */, void* stream);
+
+/* layout / dtype converters: NCHW <-> NHWC (any of f32/bf16 on either side; flatten order of vae_gan.py:89,127,180),
+ * and a 2-D cast with row pitch */
+int fmri_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+                      void* stream);
+int fmri_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+                      int accumulate, void* stream);
+int fmri_cast2d(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows, int cols,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Losses. vae_gan.py:266-269 (reparameterize), :302-320 (VaeGan.loss), train_wae_stage1.py:281-282,301-303
+ * --------------------------------------------------------------------------------------------------------- */
+int fmri_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, float* z /*nullable*/,
+                        float* kl /*nullable*/, int B, int Z, void* stream);
+int fmri_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* gz /*nullable*/,
+                        const float* gkl /*nullable*/, float* dmu, float* dlogvar, int B, int Z, void* stream);
+/* out[b] = scale * sum_j (a[b,j]-b[b,j])^2   (feature-matching MSE scale=.5 over 16384 features; NLE / WAE recon) */
+int fmri_rowsqdiff_fwd(const void* a, const void* b, int dtype, float* out, long long rows, long long F, float scale,
+                       void* stream);
+int fmri_rowsqdiff_bwd(const void* a, const void* b, int dtype, const float* g, void* da, void* db, long long rows,
+                       long long F, float scale, void* stream);
+/* p = sigmoid(x w + b) for Linear(F,1)+sigmoid heads (vae_gan.py:160,183 / :519-520) */
+int fmri_head_sigmoid_fwd(const void* x, int dtype, const float* w, const float* bias, float* p, int rows, int F,
+                          void* stream);
+int fmri_head_sigmoid_bwd(const void* x, int dtype, const float* w, const float* p, const float* gp, void* dx,
+                          float* dw /* += */, float* db /* += */, int rows, int F, void* stream);
+/* bce[i] = -scale*log(p+1e-3) (positive) or -scale*log(1-p+1e-3) */
+int fmri_bce_fwd(const float* p, float* out, int n, int positive, float scale, void* stream);
+int fmri_bce_bwd(const float* p, const float* g, float* dp, int n, int positive, float scale, int accumulate,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimizers over fp32 master weights (one launch per parameter bucket).
+ * train_vgan_stage1.py:275-283 (RMSprop alpha=.9 eps=1e-8), train_wae_stage1.py:221-224 (Adam betas=(.5,.999)),
+ * clamp>0 folds the `p.grad.data.clamp_(-1,1)` of train_vgan_stage2.py:391,406.
+ * --------------------------------------------------------------------------------------------------------- */
+int fmri_multi_tensor_rmsprop(int n, float* const* p, const float* const* g, float* const* sq, const int64_t* numel,
+                              float lr, float alpha, float eps, float clamp, void* stream);
+int fmri_multi_tensor_adam(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                           const int64_t* numel, float lr, float beta1, float beta2, float eps, int step, float clamp,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMRI_B200_H */

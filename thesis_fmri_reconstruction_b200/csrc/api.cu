@@ -1,0 +1,1177 @@
+// Host side of libfmri_b200.so: argument checking, tile planning, TMA tensor-map construction and kernel launches
+// behind the C ABI declared in include/fmri_b200.h. No torch, no cuDNN/cuBLAS, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "../../include/fmri_b200.h"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+
+using namespace fmri;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(FMRI_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCH_OK()                                                                                    \
+    do {                                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                                           \
+        if (e_ != cudaSuccess) return fail(FMRI_ERR_CUDA, "launch %s:%d: %s", __FILE__, __LINE__,      \
+                                           cudaGetErrorString(e_));                                    \
+    } while (0)
+
+extern "C" int fmri_version(void) { return FMRI_ABI_VERSION; }
+extern "C" const char* fmri_last_error(void) { return g_err; }
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int grid1d(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, cap));
+}
+
+extern "C" int fmri_tensor_path_available(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// bf16 tensor map of rank 2..4. dims/box innermost first; strides in ELEMENTS for dims 1..rank-1.
+static int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_el,
+                    const int* box, int inner_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(FMRI_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = (cuuint64_t)dims[i];
+        bx[i] = (cuuint32_t)box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_el[i] * 2;
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                     : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FMRI_ERR_CUDA,
+                    "cuTensorMapEncodeTiled failed (%d): rank %d dims %lld %lld %lld %lld box %d %d %d %d stride0 %lld",
+                    (int)r, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0], box[1],
+                    rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, strides_el[0]);
+    return 0;
+}
+// NHWC activation viewed as (C, X, Y, N) with pixel strides (sx, sy, sn) elements.
+static int make_act_map(CUtensorMap* m, const void* base, int C, int X, int Y, int N, long long sx, long long sy,
+                        long long sn, int box_c, int bw, int bh, int bn) {
+    const long long dims[4] = {C, std::max(X, 1), std::max(Y, 1), N};
+    const long long st[3] = {sx, sy, sn};
+    const int box[4] = {box_c, bw, bh, bn};
+    return make_map(m, base, 4, dims, st, box, box_c * 2);
+}
+
+// ------------------------------------------------------------------------------------------------ igemm launch
+template <int BN, int KCH, int STAGES>
+static int launch_ig(const IgParams& p, dim3 grid, cudaStream_t st) {
+    using L = IgSmem<BN, KCH, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L::TOTAL));
+        attr_done = true;
+    }
+    igemm_kernel<BN, KCH, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    LAUNCH_OK();
+    return 0;
+}
+static int dispatch_ig(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
+    dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, p.n_tiles * p.splits, classes);
+    if (KCH == 64) {
+        switch (BN) {
+            case 256: return launch_ig<256, 64, 4>(p, grid, st);
+            case 128: return launch_ig<128, 64, 4>(p, grid, st);
+            case 64: return launch_ig<64, 64, 4>(p, grid, st);
+            case 32: return launch_ig<32, 64, 4>(p, grid, st);
+        }
+    } else if (KCH == 32) {
+        switch (BN) {
+            case 256: return launch_ig<256, 32, 4>(p, grid, st);
+            case 128: return launch_ig<128, 32, 4>(p, grid, st);
+            case 64: return launch_ig<64, 32, 4>(p, grid, st);
+            case 32: return launch_ig<32, 32, 4>(p, grid, st);
+        }
+    }
+    return fail(FMRI_ERR_UNSUPPORTED, "igemm tile BN=%d KCH=%d not instantiated", BN, KCH);
+}
+static int pick_bn(int n_total, long long m_tiles_times_classes) {
+    if (n_total % 256 == 0 && m_tiles_times_classes * (n_total / 256) >= 2 * 148) return 256;
+    if (n_total % 128 == 0) return 128;
+    if (n_total % 64 == 0) return 64;
+    if (n_total % 32 == 0) return 32;
+    return 0;
+}
+static void pick_box(int X, int Y, int N, int* bw, int* bh, int* bn) {
+    *bw = std::min(X, 128);
+    *bh = std::max(1, std::min(Y, 128 / *bw));
+    *bn = std::max(1, std::min(N, 128 / (*bw * *bh)));
+}
+
+// Gather-form plan: out[n,oy,ox,:] = sum_taps X[n, oy*s+kh-2, ox*s+kw-2, :] * pack[tap]
+// (Conv2d fprop; ConvTranspose2d dgrad). X: [N,H,W,Ck] bf16, out: [N,OH,OW,Ng].
+static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, int stride, const void* pack,
+                      const float* bias, int act, void* out, int out_fp32, double* ssum, double* ssq,
+                      cudaStream_t st) {
+    if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
+    const int KCH = (Ck % 64 == 0) ? 64 : 32;
+    IgParams p;
+    memset(&p, 0, sizeof(p));
+    pick_box(OW, OH, N, &p.bw, &p.bh, &p.bn);
+    p.tiles_x = cdiv(OW, p.bw);
+    p.tiles_y = cdiv(OH, p.bh);
+    p.tiles_n = cdiv(N, p.bn);
+    p.lim_n = N;
+    const int BN = pick_bn(Ng, (long long)p.tiles_x * p.tiles_y * p.tiles_n);
+    if (!BN) return fail(FMRI_ERR_UNSUPPORTED, "no N tile for %d", Ng);
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(X);
+    if (stride == 2) {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const int Wp = (W - pw + 1) / 2, Hp = (H - ph + 1) / 2;
+                int rc = make_act_map(&p.mapA[ph * 2 + pw], xb + ((long long)ph * W + pw) * Ck, Ck, Wp, Hp, N,
+                                      2LL * Ck, 2LL * W * Ck, (long long)H * W * Ck, KCH, p.bw, p.bh, p.bn);
+                if (rc) return rc;
+            }
+    } else {
+        int rc = make_act_map(&p.mapA[0], xb, Ck, W, H, N, Ck, (long long)W * Ck, (long long)H * W * Ck, KCH, p.bw,
+                              p.bh, p.bn);
+        if (rc) return rc;
+    }
+    {
+        const long long dims[2] = {Ck, 25LL * Ng};
+        const long long stv[1] = {Ck};
+        const int box[2] = {KCH, BN};
+        int rc = make_map(&p.mapB, pack, 2, dims, stv, box, KCH * 2);
+        if (rc) return rc;
+    }
+    TapClass& c = p.cls[0];
+    c.num_taps = 25;
+    c.lim_x = OW;
+    c.lim_y = OH;
+    c.out_off = 0;
+    for (int kh = 0; kh < 5; ++kh)
+        for (int kw = 0; kw < 5; ++kw) {
+            TapDesc& t = c.taps[kh * 5 + kw];
+            if (stride == 2) {
+                t.map = (int16_t)((kh & 1) * 2 + (kw & 1));
+                t.dy = (int16_t)((kh - 2 - (kh & 1)) / 2);
+                t.dx = (int16_t)((kw - 2 - (kw & 1)) / 2);
+            } else {
+                t.map = 0;
+                t.dy = (int16_t)(kh - 2);
+                t.dx = (int16_t)(kw - 2);
+            }
+            t.brow = (kh * 5 + kw) * Ng;
+        }
+    p.num_chunks = Ck / KCH;
+    p.n_total = Ng;
+    p.n_tiles = Ng / BN;
+    p.splits = 1;
+    p.a_bytes = p.bw * p.bh * p.bn * KCH * 2;
+    p.out_sn = (long long)OH * OW * Ng;
+    p.out_sy = (long long)OW * Ng;
+    p.out_sx = Ng;
+    p.out = out;
+    p.out_fp32 = out_fp32;
+    p.bias = bias;
+    p.act = act;
+    p.stat_sum = ssum;
+    p.stat_sq = ssq;
+    return dispatch_ig(p, BN, KCH, 1, st);
+}
+
+// Scatter-form plan (stride 2): out[n, 2a+ph, 2b+pw, :] = sum_{kh = ph (mod 2), kw = pw (mod 2)} X[n, a+(ph+2-kh)/2, ..] * pack[tap]
+// (ConvTranspose2d fprop; Conv2d dgrad). X: [N,H,W,Ck], out: [N,OH,OW,Ng] with OH in {2H-1, 2H}.
+static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, const void* pack, void* out,
+                       double* ssum, double* ssq, cudaStream_t st) {
+    if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
+    const int KCH = (Ck % 64 == 0) ? 64 : 32;
+    IgParams p;
+    memset(&p, 0, sizeof(p));
+    const int GX = (OW + 1) / 2, GY = (OH + 1) / 2;  // class (0,0) sub-grid, the largest
+    pick_box(GX, GY, N, &p.bw, &p.bh, &p.bn);
+    p.tiles_x = cdiv(GX, p.bw);
+    p.tiles_y = cdiv(GY, p.bh);
+    p.tiles_n = cdiv(N, p.bn);
+    p.lim_n = N;
+    const int BN = pick_bn(Ng, 4LL * p.tiles_x * p.tiles_y * p.tiles_n);
+    if (!BN) return fail(FMRI_ERR_UNSUPPORTED, "no N tile for %d", Ng);
+    int rc = make_act_map(&p.mapA[0], X, Ck, W, H, N, Ck, (long long)W * Ck, (long long)H * W * Ck, KCH, p.bw, p.bh,
+                          p.bn);
+    if (rc) return rc;
+    {
+        const long long dims[2] = {Ck, 25LL * Ng};
+        const long long stv[1] = {Ck};
+        const int box[2] = {KCH, BN};
+        rc = make_map(&p.mapB, pack, 2, dims, stv, box, KCH * 2);
+        if (rc) return rc;
+    }
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            TapClass& c = p.cls[ph * 2 + pw];
+            c.lim_y = (OH - ph + 1) / 2;
+            c.lim_x = (OW - pw + 1) / 2;
+            c.out_off = ((long long)ph * OW + pw) * Ng;
+            int nt = 0;
+            for (int kh = ph; kh < 5; kh += 2)
+                for (int kw = pw; kw < 5; kw += 2) {
+                    TapDesc& t = c.taps[nt++];
+                    t.map = 0;
+                    t.dy = (int16_t)((ph + 2 - kh) / 2);
+                    t.dx = (int16_t)((pw + 2 - kw) / 2);
+                    t.brow = (kh * 5 + kw) * Ng;
+                }
+            c.num_taps = nt;
+        }
+    p.num_chunks = Ck / KCH;
+    p.n_total = Ng;
+    p.n_tiles = Ng / BN;
+    p.splits = 1;
+    p.a_bytes = p.bw * p.bh * p.bn * KCH * 2;
+    p.out_sn = (long long)OH * OW * Ng;
+    p.out_sy = 2LL * OW * Ng;
+    p.out_sx = 2LL * Ng;
+    p.out = out;
+    p.out_fp32 = 0;
+    p.stat_sum = ssum;
+    p.stat_sq = ssq;
+    return dispatch_ig(p, BN, KCH, 4, st);
+}
+
+// Plain GEMM plan: C[M,N] = act(A[M,K] B[N,K]^T + bias), A/B bf16 K-major with pitches, optional split-K into fp32.
+static int run_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
+                       void* Cout, int ldc, int c_fp32, int accumulate, cudaStream_t st) {
+    if (N % 32) return fail(FMRI_ERR_UNSUPPORTED, "gemm N %% 32 != 0 (%d)", N);
+    if ((lda % 8) || (ldb % 8)) return fail(FMRI_ERR_ARG, "gemm pitches must be multiples of 8 elements");
+    const int KCH = 64;
+    IgParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = std::min(128, M);
+    p.bh = 1;
+    p.bn = 1;
+    p.tiles_x = cdiv(M, 128);
+    p.tiles_y = 1;
+    p.tiles_n = 1;
+    p.lim_n = 1;
+    int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+    if (N % 256 == 0 && (long long)p.tiles_x * (N / 256) >= 148) BN = 256;
+    int rc = make_act_map(&p.mapA[0], A, K, M, 1, 1, lda, (long long)lda * M, (long long)lda * M, KCH, p.bw, 1, 1);
+    if (rc) return rc;
+    {
+        const long long dims[2] = {K, N};
+        const long long stv[1] = {ldb};
+        const int box[2] = {KCH, BN};
+        rc = make_map(&p.mapB, B, 2, dims, stv, box, KCH * 2);
+        if (rc) return rc;
+    }
+    TapClass& c = p.cls[0];
+    c.num_taps = 1;
+    c.lim_x = M;
+    c.lim_y = 1;
+    c.out_off = 0;
+    c.taps[0].map = 0;
+    c.taps[0].dx = 0;
+    c.taps[0].dy = 0;
+    c.taps[0].brow = 0;
+    p.num_chunks = cdiv(K, KCH);
+    p.n_total = N;
+    p.n_tiles = N / BN;
+    // split-K: only for fp32 outputs without a nonlinear epilogue
+    int splits = 1;
+    const long long tiles = (long long)p.tiles_x * p.n_tiles;
+    if (c_fp32 && act == ACT_NONE && tiles < 148 && p.num_chunks >= 16) {
+        splits = (int)std::min<long long>(p.num_chunks / 8, std::max<long long>(1, (2 * 148) / tiles));
+        splits = std::max(1, splits);
+    }
+    p.splits = splits;
+    p.a_bytes = p.bw * KCH * 2;
+    p.out_sn = 0;
+    p.out_sy = 0;
+    p.out_sx = ldc;
+    p.out = Cout;
+    p.out_fp32 = c_fp32;
+    p.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
+    if (p.atomic_out && !c_fp32) return fail(FMRI_ERR_ARG, "accumulating gemm needs fp32 output");
+    if (splits > 1 && !accumulate) {
+        if (ldc != N) {
+            CUDA_OK(cudaMemset2DAsync(Cout, (size_t)ldc * 4, 0, (size_t)N * 4, M, st));
+        } else {
+            CUDA_OK(cudaMemsetAsync(Cout, 0, (size_t)M * N * 4, st));
+        }
+    }
+    p.bias = bias;
+    if (splits > 1 && bias) return fail(FMRI_ERR_ARG, "split-K gemm with bias unsupported");
+    p.act = act;
+    return dispatch_ig(p, BN, KCH, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad launch
+template <int BN, int NCH, int STAGES>
+static int launch_wg(const WgParams& p, dim3 grid, cudaStream_t st) {
+    using L = WgSmem<BN, NCH, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<BN, NCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L::TOTAL));
+        attr_done = true;
+    }
+    wgrad_kernel<BN, NCH, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    LAUNCH_OK();
+    return 0;
+}
+static int dispatch_wg(const WgParams& p, int BN, int NCH, cudaStream_t st) {
+    dim3 grid(p.num_taps, p.m_tiles * p.n_tiles, p.splits);
+    if (NCH == 64 && BN == 128) return launch_wg<128, 64, 3>(p, grid, st);
+    if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4>(p, grid, st);
+    if (NCH == 32 && BN == 32) return launch_wg<32, 32, 4>(p, grid, st);
+    return fail(FMRI_ERR_UNSUPPORTED, "wgrad tile BN=%d NCH=%d not instantiated", BN, NCH);
+}
+// ws[tap][m][n] += sum_pixels Dn[pixel][m] * Sh[pixel*stride + tap - 2][n]
+//   Dn: [N,PH,PW,Cd] bf16 (dense side), Sh: [N,BH,BW,Cs] bf16 (shifted side; stride-parity planes when stride = 2)
+static int run_wgrad_tc(const void* Dn, int N, int PH, int PW, int Cd, const void* Sh, int BH, int BW, int Cs,
+                        int stride, int num_taps, float* ws, cudaStream_t st) {
+    if (Cd % 64 || Cs % 32) return fail(FMRI_ERR_UNSUPPORTED, "wgrad tensor path needs Cd%%64==0, Cs%%32==0");
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    pick_box(PW, PH, N, &p.bw, &p.bh, &p.bn);
+    p.rows = p.bw * p.bh * p.bn;
+    if (p.rows % 16) return fail(FMRI_ERR_UNSUPPORTED, "wgrad pixel box %d not a multiple of 16", p.rows);
+    p.tiles_x = cdiv(PW, p.bw);
+    p.tiles_y = cdiv(PH, p.bh);
+    p.tiles_n = cdiv(N, p.bn);
+    const int NCH = (Cs % 64 == 0) ? 64 : 32;
+    const int BN = (Cs % 128 == 0) ? 128 : (Cs % 64 == 0 ? 64 : 32);
+    if (NCH == 32 && BN != 32) return fail(FMRI_ERR_UNSUPPORTED, "wgrad Cs=%d", Cs);
+    int rc = make_act_map(&p.mapD, Dn, Cd, PW, PH, N, Cd, (long long)PW * Cd, (long long)PH * PW * Cd, 64, p.bw,
+                          p.bh, p.bn);
+    if (rc) return rc;
+    const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(Sh);
+    if (stride == 2) {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const int Wp = (BW - pw + 1) / 2, Hp = (BH - ph + 1) / 2;
+                rc = make_act_map(&p.mapS[ph * 2 + pw], sb + ((long long)ph * BW + pw) * Cs, Cs, Wp, Hp, N, 2LL * Cs,
+                                  2LL * BW * Cs, (long long)BH * BW * Cs, NCH, p.bw, p.bh, p.bn);
+                if (rc) return rc;
+            }
+    } else {
+        rc = make_act_map(&p.mapS[0], sb, Cs, BW, BH, N, Cs, (long long)BW * Cs, (long long)BH * BW * Cs, NCH, p.bw,
+                          p.bh, p.bn);
+        if (rc) return rc;
+    }
+    p.num_taps = num_taps;
+    for (int kh = 0; kh < 5; ++kh)
+        for (int kw = 0; kw < 5; ++kw) {
+            TapDesc& t = p.taps[kh * 5 + kw];
+            if (num_taps == 1) {
+                t.map = 0;
+                t.dx = t.dy = 0;
+            } else if (stride == 2) {
+                t.map = (int16_t)((kh & 1) * 2 + (kw & 1));
+                t.dy = (int16_t)((kh - 2 - (kh & 1)) / 2);
+                t.dx = (int16_t)((kw - 2 - (kw & 1)) / 2);
+            } else {
+                t.map = 0;
+                t.dy = (int16_t)(kh - 2);
+                t.dx = (int16_t)(kw - 2);
+            }
+        }
+    p.m_total = Cd;
+    p.n_total = Cs;
+    p.m_tiles = cdiv(Cd, 128);
+    p.n_tiles = Cs / BN;
+    const long long pt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+    const long long base = (long long)num_taps * p.m_tiles * p.n_tiles;
+    long long splits = std::max<long long>(1, (2 * 148 + base - 1) / base);
+    splits = std::min<long long>(splits, std::max<long long>(1, pt / 4));
+    p.splits = (int)splits;
+    p.out = ws;
+    return dispatch_wg(p, BN, NCH, st);
+}
+
+// ================================================================================================ conv API
+extern "C" void fmri_conv_out_hw(const fmri_conv_desc* d, int* OH, int* OW) {
+    if (d->transposed) {
+        *OH = 2 * d->H - 1 + d->output_pad;
+        *OW = 2 * d->W - 1 + d->output_pad;
+    } else {
+        *OH = (d->H - 1) / d->stride + 1;
+        *OW = (d->W - 1) / d->stride + 1;
+    }
+}
+static int check_conv(const fmri_conv_desc* d) {
+    if (!d || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0)
+        return fail(FMRI_ERR_ARG, "bad conv descriptor");
+    if (d->stride != 1 && d->stride != 2) return fail(FMRI_ERR_ARG, "conv stride must be 1 or 2");
+    if (d->transposed && d->stride != 2) return fail(FMRI_ERR_ARG, "ConvTranspose2d is stride 2 only");
+    if (d->dtype != FMRI_F32 && d->dtype != FMRI_BF16) return fail(FMRI_ERR_ARG, "bad dtype");
+    return 0;
+}
+// reference-layout weight strides: Conv2d [Cout,Cin,25], ConvT [Cin,Cout,25]
+static inline long long w_so(const fmri_conv_desc* d) { return d->transposed ? 25LL : 25LL * d->Cin; }
+static inline long long w_si(const fmri_conv_desc* d) { return d->transposed ? 25LL * d->Cout : 25LL; }
+
+extern "C" int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, void* pack_f, void* pack_d,
+                                      void* stream) {
+    int rc = check_conv(d);
+    if (rc) return rc;
+    const long long n = 25LL * d->Cin * d->Cout;
+    if (pack_f) {  // [tap][co][ci]
+        permute4_kernel<float, __nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+            w, reinterpret_cast<__nv_bfloat16*>(pack_f), 1, 25, d->Cout, d->Cin, 0, 1, w_so(d), w_si(d), 0);
+        LAUNCH_OK();
+    }
+    if (pack_d) {  // [tap][ci][co]
+        permute4_kernel<float, __nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+            w, reinterpret_cast<__nv_bfloat16*>(pack_d), 1, 25, d->Cin, d->Cout, 0, 1, w_si(d), w_so(d), 0);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+
+template <typename T>
+static int direct_conv(const fmri_conv_desc* d, bool backward, const T* in, const float* w, const float* bias, int act,
+                       T* out, cudaStream_t st) {
+    int OH, OW;
+    fmri_conv_out_hw(d, &OH, &OW);
+    DirectConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N;
+    p.stride = d->stride;
+    if (!backward) {
+        p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.OH = OH; p.OW = OW; p.Cout = d->Cout;
+        p.transposed = d->transposed;
+        p.w_so = w_so(d);
+        p.w_si = w_si(d);
+    } else {  // data gradient: roles of the two grids and of the weight axes swap, gather/scatter form swaps
+        p.H = OH; p.W = OW; p.Cin = d->Cout; p.OH = d->H; p.OW = d->W; p.Cout = d->Cin;
+        p.transposed = !d->transposed;
+        p.w_so = w_si(d);
+        p.w_si = w_so(d);
+    }
+    p.in_sn = (long long)p.H * p.W * p.Cin; p.in_sy = (long long)p.W * p.Cin; p.in_sx = p.Cin; p.in_sc = 1;
+    p.out_sn = (long long)p.OH * p.OW * p.Cout; p.out_sy = (long long)p.OW * p.Cout; p.out_sx = p.Cout; p.out_sc = 1;
+    p.act = act;
+    const long long total = (long long)p.N * p.OH * p.OW * p.Cout;
+    direct_conv_kernel<T, T><<<grid1d(total, 256, 148 * 32), 256, 0, st>>>(in, w, bias, out, p);
+    LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const float* w, const void* pack_f,
+                               const float* bias, int act, void* y, double* stat_sum, double* stat_sq,
+                               void* stream) {
+    int rc = check_conv(d);
+    if (rc) return rc;
+    int OH, OW;
+    fmri_conv_out_hw(d, &OH, &OW);
+    if (stat_sum) {
+        CUDA_OK(cudaMemsetAsync(stat_sum, 0, sizeof(double) * d->Cout, S(stream)));
+        CUDA_OK(cudaMemsetAsync(stat_sq, 0, sizeof(double) * d->Cout, S(stream)));
+    }
+    if (d->dtype == FMRI_BF16) {
+        if (!pack_f) return fail(FMRI_ERR_ARG, "bf16 conv needs the packed weights");
+        if (d->transposed) {
+            if (bias || act) return fail(FMRI_ERR_UNSUPPORTED, "convT epilogue: bias/act unsupported");
+            return run_scatter(x, d->N, d->H, d->W, d->Cin, OH, OW, d->Cout, pack_f, y, stat_sum, stat_sq, S(stream));
+        }
+        return run_gather(x, d->N, d->H, d->W, d->Cin, OH, OW, d->Cout, d->stride, pack_f, bias, act, y, 0, stat_sum,
+                          stat_sq, S(stream));
+    }
+    rc = direct_conv<float>(d, false, reinterpret_cast<const float*>(x), w, bias, act, reinterpret_cast<float*>(y),
+                            S(stream));
+    if (rc) return rc;
+    if (stat_sum) return fmri_colstats(y, FMRI_F32, (long long)d->N * OH * OW, d->Cout, stat_sum, stat_sq, stream);
+    return 0;
+}
+
+extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const float* w, const void* pack_d, void* dx,
+                               void* stream) {
+    int rc = check_conv(d);
+    if (rc) return rc;
+    int OH, OW;
+    fmri_conv_out_hw(d, &OH, &OW);
+    if (d->dtype == FMRI_BF16) {
+        if (!pack_d) return fail(FMRI_ERR_ARG, "bf16 conv dgrad needs the packed weights");
+        if (d->transposed)  // gather over dy at stride 2
+            return run_gather(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, 2, pack_d, nullptr, 0, dx, 0, nullptr,
+                              nullptr, S(stream));
+        if (d->stride == 2)
+            return run_scatter(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, pack_d, dx, nullptr, nullptr, S(stream));
+        return fail(FMRI_ERR_UNSUPPORTED, "stride-1 conv dgrad on the tensor path");
+    }
+    return direct_conv<float>(d, true, reinterpret_cast<const float*>(dy), w, nullptr, 0, reinterpret_cast<float*>(dx),
+                              S(stream));
+}
+
+extern "C" size_t fmri_conv_wgrad_workspace(const fmri_conv_desc* d) {
+    return d->dtype == FMRI_BF16 ? sizeof(float) * 25 * (size_t)d->Cin * d->Cout : 0;
+}
+
+extern "C" int fmri_conv_wgrad(const fmri_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,
+                               void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_conv(d);
+    if (rc) return rc;
+    int OH, OW;
+    fmri_conv_out_hw(d, &OH, &OW);
+    if (d->dtype == FMRI_BF16) {
+        const size_t need = fmri_conv_wgrad_workspace(d);
+        if (!ws || ws_bytes < need) return fail(FMRI_ERR_WORKSPACE, "conv wgrad workspace %zu < %zu", ws_bytes, need);
+        if (d->stride != 2) return fail(FMRI_ERR_UNSUPPORTED, "stride-1 conv wgrad on the tensor path");
+        CUDA_OK(cudaMemsetAsync(ws, 0, need, S(stream)));
+        float* wsf = reinterpret_cast<float*>(ws);
+        int Cd, Cs;
+        if (!d->transposed) {  // dense = dy [N,OH,OW,Cout], shifted = x [N,H,W,Cin]
+            Cd = d->Cout; Cs = d->Cin;
+            rc = run_wgrad_tc(dy, d->N, OH, OW, Cd, x, d->H, d->W, Cs, 2, 25, wsf, S(stream));
+        } else {  // dense = x [N,H,W,Cin], shifted = dy [N,OH,OW,Cout]
+            Cd = d->Cin; Cs = d->Cout;
+            rc = run_wgrad_tc(x, d->N, d->H, d->W, Cd, dy, OH, OW, Cs, 2, 25, wsf, S(stream));
+        }
+        if (rc) return rc;
+        // ws[tap][m][n] -> dw[m][n][tap]
+        const long long n = 25LL * Cd * Cs;
+        scatter4_kernel<float, float><<<grid1d(n, 256), 256, 0, S(stream)>>>(wsf, dw, 1, 25, Cd, Cs, 0, 1, 25LL * Cs,
+                                                                            25, accumulate);
+        LAUNCH_OK();
+        return 0;
+    }
+    DirectWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N;
+    p.stride = d->stride;
+    p.accumulate = accumulate;
+    const float *A, *B;
+    if (!d->transposed) {
+        A = reinterpret_cast<const float*>(dy); p.PH = OH; p.PW = OW; p.Ca = d->Cout;
+        B = reinterpret_cast<const float*>(x); p.BH = d->H; p.BW = d->W; p.Cb = d->Cin;
+    } else {
+        A = reinterpret_cast<const float*>(x); p.PH = d->H; p.PW = d->W; p.Ca = d->Cin;
+        B = reinterpret_cast<const float*>(dy); p.BH = OH; p.BW = OW; p.Cb = d->Cout;
+    }
+    p.a_sn = (long long)p.PH * p.PW * p.Ca; p.a_sy = (long long)p.PW * p.Ca; p.a_sx = p.Ca; p.a_sc = 1;
+    p.b_sn = (long long)p.BH * p.BW * p.Cb; p.b_sy = (long long)p.BW * p.Cb; p.b_sx = p.Cb; p.b_sc = 1;
+    p.w_sa = 25LL * p.Cb;
+    p.w_sb = 25;
+    direct_wgrad_kernel<float, float><<<25 * p.Ca * p.Cb, 128, 0, S(stream)>>>(A, B, dw, p);
+    LAUNCH_OK();
+    return 0;
+}
+
+// ================================================================================================ edge convs
+extern "C" size_t fmri_edge_workspace(const fmri_edge_desc* d) { return sizeof(float) * 75 * (size_t)d->C; }
+static int check_edge(const fmri_edge_desc* d, const void* ws, size_t ws_bytes) {
+    if (!d || (d->C != 32 && d->C != 64)) return fail(FMRI_ERR_UNSUPPORTED, "edge conv supports C in {32,64}");
+    if (d->stride != 1 && d->stride != 2) return fail(FMRI_ERR_ARG, "edge stride");
+    if (!ws || ws_bytes < fmri_edge_workspace(d)) return fail(FMRI_ERR_WORKSPACE, "edge workspace too small");
+    return 0;
+}
+// "in" conv weight [C,3,25] -> wk[(ci*25+tap)*C + c]
+static int pack_edge_in(const fmri_edge_desc* d, const float* w, float* wk, cudaStream_t st) {
+    permute4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, st>>>(w, wk, 1, 3, 25, d->C, 0, 25, 1, 75, 0);
+    LAUNCH_OK();
+    return 0;
+}
+// "out" conv weight [3,C,25] -> wk[(co*25+tap)*C + c] (flip: tap -> 24-tap)
+static int pack_edge_out(const fmri_edge_desc* d, const float* w, float* wk, int flip, cudaStream_t st) {
+    permute4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, st>>>(
+        flip ? w + 24 : w, wk, 1, 3, 25, d->C, 0, 25LL * d->C, flip ? -1 : 1, 25, 0);
+    LAUNCH_OK();
+    return 0;
+}
+template <int C>
+static int edge_in_fprop_t(const fmri_edge_desc* d, const float* i0, const float* i1, const float* i2, int nps,
+                           const float* wk, const float* bias, int act, void* y, int OH, int OW, cudaStream_t st) {
+    const long long pix = (long long)d->N * OH * OW;
+    if (d->dtype == FMRI_BF16)
+        edge3_to_c_kernel<C, __nv_bfloat16><<<cdiv(pix, 128), 128, 0, st>>>(
+            i0, i1, i2, nps, wk, bias, reinterpret_cast<__nv_bfloat16*>(y), d->N, d->H, d->W, OH, OW, d->stride, act);
+    else
+        edge3_to_c_kernel<C, float><<<cdiv(pix, 128), 128, 0, st>>>(i0, i1, i2, nps, wk, bias,
+                                                                   reinterpret_cast<float*>(y), d->N, d->H, d->W, OH,
+                                                                   OW, d->stride, act);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_edge_in_fprop(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2,
+                                  int n_per_src, const float* w, const float* bias, int act, void* y, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    float* wk = reinterpret_cast<float*>(ws);
+    rc = pack_edge_in(d, w, wk, S(stream));
+    if (rc) return rc;
+    const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
+    if (!img1) img1 = img0;
+    if (!img2) img2 = img0;
+    return d->C == 32 ? edge_in_fprop_t<32>(d, img0, img1, img2, n_per_src, wk, bias, act, y, OH, OW, S(stream))
+                      : edge_in_fprop_t<64>(d, img0, img1, img2, n_per_src, wk, bias, act, y, OH, OW, S(stream));
+}
+template <int C>
+static int edge_to3_t(int dtype, const void* in, const float* wk, const float* bias, float* img, int N, int IH, int IW,
+                      int OH, int OW, int stride_up, int flip, int act, cudaStream_t st) {
+    const long long pix = (long long)N * OH * OW;
+    if (dtype == FMRI_BF16)
+        edgec_to_3_kernel<C, __nv_bfloat16><<<cdiv(pix, 128), 128, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(in), wk, bias, img, N, IH, IW, OH, OW, stride_up, flip, act, 0);
+    else
+        edgec_to_3_kernel<C, float><<<cdiv(pix, 128), 128, 0, st>>>(reinterpret_cast<const float*>(in), wk, bias, img,
+                                                                   N, IH, IW, OH, OW, stride_up, flip, act, 0);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const float* w, float* dimg, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    float* wk = reinterpret_cast<float*>(ws);
+    rc = pack_edge_in(d, w, wk, S(stream));
+    if (rc) return rc;
+    const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
+    // image pixel gathers from the C-side grid (OH,OW); stride 1: flipped taps, stride 2: divisibility form
+    const int flip = d->stride == 1 ? 1 : 0;
+    return d->C == 32 ? edge_to3_t<32>(d->dtype, dy, wk, nullptr, dimg, d->N, OH, OW, d->H, d->W, d->stride, flip, 0,
+                                       S(stream))
+                      : edge_to3_t<64>(d->dtype, dy, wk, nullptr, dimg, d->N, OH, OW, d->H, d->W, d->stride, flip, 0,
+                                       S(stream));
+}
+template <int C>
+static int edge_wgrad_t(int dtype, const void* T, const float* i0, const float* i1, const float* i2, int nps,
+                        float* dwk, int N, int PH, int PW, int IH, int IW, int stride, int sg, cudaStream_t st) {
+    const long long pix = (long long)N * PH * PW;
+    int ppb = (int)std::max<long long>(64, ((pix + 148 * 4 - 1) / (148 * 4) + 7) / 8 * 8);
+    const int blocks = cdiv(pix, ppb);
+    if (dtype == FMRI_BF16)
+        edge_wgrad_kernel<C, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(T), i0, i1,
+                                                                    i2, nps, dwk, N, PH, PW, IH, IW, stride, sg, ppb);
+    else
+        edge_wgrad_kernel<C, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(T), i0, i1, i2, nps, dwk, N,
+                                                            PH, PW, IH, IW, stride, sg, ppb);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2,
+                                  int n_per_src, const void* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
+                                  void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    float* dwk = reinterpret_cast<float*>(ws);
+    CUDA_OK(cudaMemsetAsync(dwk, 0, fmri_edge_workspace(d), S(stream)));
+    const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
+    if (!img1) img1 = img0;
+    if (!img2) img2 = img0;
+    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, d->N, OH, OW, d->H, d->W,
+                                       d->stride, 1, S(stream))
+                    : edge_wgrad_t<64>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, d->N, OH, OW, d->H, d->W,
+                                       d->stride, 1, S(stream));
+    if (rc) return rc;
+    // dwk[(ci*25+tap)*C + c] -> dw[c][ci][tap]
+    scatter4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, S(stream)>>>(dwk, dw, 1, 3, 25, d->C, 0, 25, 1,
+                                                                                  75, accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_edge_out_fprop(const fmri_edge_desc* d, const void* x, const float* w, const float* bias, int act,
+                                   float* img, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
+    float* wk = reinterpret_cast<float*>(ws);
+    rc = pack_edge_out(d, w, wk, 0, S(stream));
+    if (rc) return rc;
+    return d->C == 32
+               ? edge_to3_t<32>(d->dtype, x, wk, bias, img, d->N, d->H, d->W, d->H, d->W, 1, 0, act, S(stream))
+               : edge_to3_t<64>(d->dtype, x, wk, bias, img, d->N, d->H, d->W, d->H, d->W, 1, 0, act, S(stream));
+}
+extern "C" int fmri_edge_out_dgrad(const fmri_edge_desc* d, const float* dimg, const float* w, void* dx, void* ws,
+                                   size_t ws_bytes, void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
+    float* wk = reinterpret_cast<float*>(ws);
+    // dx[p][c] = sum_{co,tap'} dimg[co][p + tap' - 2] * w[co][c][24 - tap']  -> "3 -> C" form with a flipped pack
+    rc = pack_edge_out(d, w, wk, 1, S(stream));
+    if (rc) return rc;
+    fmri_edge_desc e = *d;
+    return e.C == 32 ? edge_in_fprop_t<32>(&e, dimg, dimg, dimg, d->N, wk, nullptr, 0, dx, d->H, d->W, S(stream))
+                     : edge_in_fprop_t<64>(&e, dimg, dimg, dimg, d->N, wk, nullptr, 0, dx, d->H, d->W, S(stream));
+}
+extern "C" int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const float* dimg, float* dw,
+                                   int accumulate, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_edge(d, ws, ws_bytes);
+    if (rc) return rc;
+    if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
+    float* dwk = reinterpret_cast<float*>(ws);
+    CUDA_OK(cudaMemsetAsync(dwk, 0, fmri_edge_workspace(d), S(stream)));
+    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, d->N, d->H, d->W, d->H, d->W, 1, -1,
+                                       S(stream))
+                    : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, d->N, d->H, d->W, d->H, d->W, 1, -1,
+                                       S(stream));
+    if (rc) return rc;
+    // dwk[(co*25+tap)*C + c] -> dw[co][c][tap]
+    scatter4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, S(stream)>>>(dwk, dw, 1, 3, 25, d->C, 0,
+                                                                                  25LL * d->C, 1, 25, accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+
+// ================================================================================================ linear
+extern "C" int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* w, void* wp, int ldw, void* wpt,
+                                        int ldwt, void* stream) {
+    if (!d || d->M < 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
+    if (wp) {
+        if (ldw < d->K) return fail(FMRI_ERR_ARG, "ldw < K");
+        if (ldw > d->K) CUDA_OK(cudaMemsetAsync(wp, 0, (size_t)d->N * ldw * 2, S(stream)));
+        int rc = fmri_cast2d(w, FMRI_F32, d->K, wp, FMRI_BF16, ldw, d->N, d->K, stream);
+        if (rc) return rc;
+    }
+    if (wpt) {  // [K][N]
+        if (ldwt < d->N) return fail(FMRI_ERR_ARG, "ldwt < N");
+        if (ldwt > d->N) CUDA_OK(cudaMemsetAsync(wpt, 0, (size_t)d->K * ldwt * 2, S(stream)));
+        // dst[k][n] (pitch ldwt) = w[n][k]
+        scatter4_kernel<float, __nv_bfloat16><<<grid1d((long long)d->N * d->K, 256), 256, 0, S(stream)>>>(
+            w, reinterpret_cast<__nv_bfloat16*>(wpt), 1, 1, d->N, d->K, 0, 0, 1, ldwt, 0);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+
+template <typename Ta, typename Tb, typename Tc>
+static int simt_gemm(const Ta* A, long long a_sm, long long a_sk, const Tb* B, long long b_sn, long long b_sk, Tc* C,
+                     long long c_sm, long long c_sn, const float* bias, int M, int N, int K, int act, int accumulate,
+                     cudaStream_t st) {
+    dim3 grid(cdiv(N, 64), cdiv(M, 64));
+    simt_gemm_kernel<Ta, Tb, Tc><<<grid, 256, 0, st>>>(A, a_sm, a_sk, B, b_sn, b_sk, C, c_sm, c_sn, bias, M, N, K,
+                                                      act, accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int fmri_linear_fprop(const fmri_linear_desc* d, const void* x, int ldx, const float* w, const void* wp,
+                                 int ldw, const float* bias, int act, void* y, int ldy, int y_dtype, void* stream) {
+    if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
+    if (d->dtype == FMRI_BF16) {
+        if (!wp) return fail(FMRI_ERR_ARG, "bf16 linear needs packed weights");
+        if (d->N % 32 == 0)
+            return run_gemm_tn(x, ldx, wp, ldw, d->M, d->N, d->K, bias, act, y, ldy, y_dtype == FMRI_F32, 0, S(stream));
+        // narrow outputs (not on the hot path) use the CUDA-core GEMM on the bf16 operands
+        if (y_dtype == FMRI_F32)
+            return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(x), ldx, 1,
+                             reinterpret_cast<const __nv_bfloat16*>(wp), ldw, 1, reinterpret_cast<float*>(y), ldy, 1,
+                             bias, d->M, d->N, d->K, act, 0, S(stream));
+        return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(x), ldx, 1, reinterpret_cast<const __nv_bfloat16*>(wp),
+                         ldw, 1, reinterpret_cast<__nv_bfloat16*>(y), ldy, 1, bias, d->M, d->N, d->K, act, 0,
+                         S(stream));
+    }
+    if (y_dtype != FMRI_F32) return fail(FMRI_ERR_ARG, "fp32 linear writes fp32");
+    return simt_gemm(reinterpret_cast<const float*>(x), ldx, 1, w, d->K, 1, reinterpret_cast<float*>(y), ldy, 1, bias,
+                     d->M, d->N, d->K, act, 0, S(stream));
+}
+
+extern "C" int fmri_linear_dgrad(const fmri_linear_desc* d, const void* dy, int lddy, const float* w, const void* wpt,
+                                 int ldwt, void* dx, int lddx, int dx_dtype, void* stream) {
+    if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
+    if (d->dtype == FMRI_BF16) {
+        if (!wpt) return fail(FMRI_ERR_ARG, "bf16 linear dgrad needs the transposed pack");
+        if (d->K % 32 == 0 && d->N % 8 == 0)  // dx[M,K] = dy[M,N] * wpt[K,N]^T
+            return run_gemm_tn(dy, lddy, wpt, ldwt, d->M, d->K, d->N, nullptr, 0, dx, lddx, dx_dtype == FMRI_F32, 0,
+                               S(stream));
+        if (dx_dtype == FMRI_F32)
+            return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, 1,
+                             reinterpret_cast<const __nv_bfloat16*>(wpt), ldwt, 1, reinterpret_cast<float*>(dx), lddx,
+                             1, nullptr, d->M, d->K, d->N, 0, 0, S(stream));
+        return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, 1,
+                         reinterpret_cast<const __nv_bfloat16*>(wpt), ldwt, 1, reinterpret_cast<__nv_bfloat16*>(dx),
+                         lddx, 1, nullptr, d->M, d->K, d->N, 0, 0, S(stream));
+    }
+    // dx[m,k] = sum_n dy[m,n] w[n,k] : "B" = w viewed as [K rows (stride 1)] x [N (stride K)]
+    return simt_gemm(reinterpret_cast<const float*>(dy), lddy, 1, w, 1, d->K, reinterpret_cast<float*>(dx), lddx, 1,
+                     nullptr, d->M, d->K, d->N, 0, 0, S(stream));
+}
+
+extern "C" int fmri_linear_wgrad(const fmri_linear_desc* d, const void* x, int ldx, const void* dy, int lddy,
+                                 float* dw, int accumulate, void* stream) {
+    if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
+    if (d->dtype == FMRI_BF16) {
+        // dw[n,k] = sum_m dy[m,n] x[m,k]; tensor path when the tiles fit: N%128 (dense side), K%32, pitch == extent
+        const bool tc_ok = (d->N % 128 == 0) && (d->K % 128 == 0 || d->K == 64 || d->K == 32) && (d->M % 16 == 0) &&
+                           (lddy % 8 == 0) && (ldx % 8 == 0);
+        if (tc_ok) {
+            if (!accumulate) CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->N * d->K, S(stream)));
+            // reuse the conv wgrad kernel with a [M rows] x 1 x 1 pixel grid; pitches come in through the maps
+            WgParams p;
+            memset(&p, 0, sizeof(p));
+            p.bw = std::min(128, d->M);
+            p.bh = p.bn = 1;
+            p.rows = p.bw;
+            if (p.rows % 16) return fail(FMRI_ERR_UNSUPPORTED, "linear wgrad rows");
+            p.tiles_x = cdiv(d->M, p.bw);
+            p.tiles_y = p.tiles_n = 1;
+            const int NCH = (d->K % 64 == 0) ? 64 : 32;
+            const int BN = (d->K % 128 == 0) ? 128 : (d->K % 64 == 0 ? 64 : 32);
+            int rc = make_act_map(&p.mapD, dy, d->N, d->M, 1, 1, lddy, (long long)lddy * d->M,
+                                  (long long)lddy * d->M, 64, p.bw, 1, 1);
+            if (rc) return rc;
+            rc = make_act_map(&p.mapS[0], x, d->K, d->M, 1, 1, ldx, (long long)ldx * d->M, (long long)ldx * d->M, NCH,
+                              p.bw, 1, 1);
+            if (rc) return rc;
+            p.num_taps = 1;
+            p.m_total = d->N;
+            p.n_total = d->K;
+            p.m_tiles = d->N / 128;
+            p.n_tiles = d->K / BN;
+            const long long base = (long long)p.m_tiles * p.n_tiles;
+            long long splits = std::max<long long>(1, (148 + base - 1) / base);
+            splits = std::min<long long>(splits, std::max<long long>(1, p.tiles_x / 2));
+            p.splits = (int)splits;
+            p.out = dw;
+            return dispatch_wg(p, BN, NCH, S(stream));
+        }
+        return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(dy), 1, lddy,
+                         reinterpret_cast<const __nv_bfloat16*>(x), 1, ldx, dw, d->K, 1, nullptr, d->N, d->K, d->M, 0,
+                         accumulate, S(stream));
+    }
+    return simt_gemm(reinterpret_cast<const float*>(dy), 1, lddy, reinterpret_cast<const float*>(x), 1, ldx, dw, d->K,
+                     1, nullptr, d->N, d->K, d->M, 0, accumulate, S(stream));
+}
+
+// ================================================================================================ BN / elementwise
+static int rows_per_block_for(long long rows) {
+    long long target = (rows + 148 * 4 - 1) / (148 * 4);
+    return (int)std::max<long long>(8, target);
+}
+extern "C" int fmri_colstats(const void* x, int dtype, long long rows, int C, double* sum, double* sq, void* stream) {
+    if (C <= 0 || rows <= 0) return fail(FMRI_ERR_ARG, "colstats shape");
+    if (C < 256 && (256 % C)) return fail(FMRI_ERR_UNSUPPORTED, "colstats C=%d", C);
+    const int rpb = rows_per_block_for(rows);
+    dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
+    CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double) * C, S(stream)));
+    CUDA_OK(cudaMemsetAsync(sq, 0, sizeof(double) * C, S(stream)));
+    if (dtype == FMRI_BF16)
+        colstats_kernel<__nv_bfloat16><<<grid, 256, 2 * 256 * 4, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), rows, C, sum, sq, rpb);
+    else
+        colstats_kernel<float><<<grid, 256, 2 * 256 * 4, S(stream)>>>(reinterpret_cast<const float*>(x), rows, C, sum,
+                                                                     sq, rpb);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_bn_finalize(const double* sum, const double* sq, long long rows, int C, float eps, float momentum,
+                                float* mean, float* invstd, float* running_mean, float* running_var, void* stream) {
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(sum, sq, (double)rows, C, eps, momentum, mean, invstd,
+                                                           running_mean, running_var);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, const float* mean,
+                             const float* invstd, const float* gamma, const float* beta, int relu, void* stream) {
+    if (C % 8) return fail(FMRI_ERR_UNSUPPORTED, "bn_apply needs C %% 8 == 0");
+    const long long total = rows * C;
+    const int g = grid1d((total + 7) / 8, 256, 148 * 8);
+    cudaStream_t st = S(stream);
+    if (x_dtype == FMRI_BF16 && y_dtype == FMRI_BF16)
+        bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), total, C, mean, invstd,
+            gamma, beta, relu);
+    else if (x_dtype == FMRI_F32 && y_dtype == FMRI_BF16)
+        bn_apply_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(reinterpret_cast<const float*>(x),
+                                                                reinterpret_cast<__nv_bfloat16*>(y), total, C, mean,
+                                                                invstd, gamma, beta, relu);
+    else if (x_dtype == FMRI_F32 && y_dtype == FMRI_F32)
+        bn_apply_kernel<float, float><<<g, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
+                                                        total, C, mean, invstd, gamma, beta, relu);
+    else
+        return fail(FMRI_ERR_UNSUPPORTED, "bn_apply dtype combination");
+    LAUNCH_OK();
+    return 0;
+}
+template <typename Tx, typename Tg>
+static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int C, const float* mean,
+                    const float* invstd, const float* gamma, const float* beta, int relu, int train, float* dgamma,
+                    float* dbeta, int accumulate, double* ws, cudaStream_t st) {
+    const int rpb = rows_per_block_for(rows);
+    dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
+    CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+    bn_bwd_reduce_kernel<Tx, Tg><<<grid, 256, 2 * 256 * 4, st>>>(reinterpret_cast<const Tx*>(x),
+                                                                reinterpret_cast<const Tg*>(dy), rows, C, mean, invstd,
+                                                                gamma, beta, relu, ws, ws + C, rpb);
+    LAUNCH_OK();
+    if (dx) {
+        bn_bwd_apply_kernel<Tx, Tg><<<grid1d(rows * C, 256, 148 * 16), 256, 0, st>>>(
+            reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), reinterpret_cast<Tg*>(dx), rows * C, C,
+            (double)rows, mean, invstd, gamma, beta, relu, train, ws, ws + C);
+        LAUNCH_OK();
+    }
+    if (dgamma) {
+        bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, C, dgamma, dbeta, accumulate);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+extern "C" int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
+                                const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                int relu, int train, float* dgamma, float* dbeta, int accumulate, double* ws,
+                                void* stream) {
+    if (C < 256 && (256 % C)) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward C=%d", C);
+    if (x_dtype == FMRI_BF16 && g_dtype == FMRI_BF16)
+        return bn_bwd_t<__nv_bfloat16, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train,
+                                                      dgamma, dbeta, accumulate, ws, S(stream));
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_BF16)
+        return bn_bwd_t<float, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
+                                              accumulate, ws, S(stream));
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_F32)
+        return bn_bwd_t<float, float>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
+                                      accumulate, ws, S(stream));
+    return fail(FMRI_ERR_UNSUPPORTED, "bn_backward dtype combination");
+}
+extern "C" int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream) {
+    if (dtype == FMRI_BF16)
+        relu_bwd_kernel<__nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
+            reinterpret_cast<__nv_bfloat16*>(dx), n);
+    else
+        relu_bwd_kernel<float><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+            reinterpret_cast<const float*>(y), reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(dx), n);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_colsum(const void* x, int dtype, long long rows, int C, float* out, void* stream) {
+    const int rpb = rows_per_block_for(rows);
+    if (dtype == FMRI_BF16)
+        colsum_kernel<__nv_bfloat16><<<cdiv(rows, rpb), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                            rows, C, out, rpb);
+    else
+        colsum_kernel<float><<<cdiv(rows, rpb), 256, 0, S(stream)>>>(reinterpret_cast<const float*>(x), rows, C, out,
+                                                                    rpb);
+    LAUNCH_OK();
+    return 0;
+}
+
+template <typename TI, typename TO>
+static int permute_launch(const void* src, void* dst, int d1, int d2, int d3, long long s1, long long s2, long long s3,
+                          int accumulate, cudaStream_t st) {
+    const long long n = (long long)d1 * d2 * d3;
+    permute4_kernel<TI, TO><<<grid1d(n, 256), 256, 0, st>>>(reinterpret_cast<const TI*>(src),
+                                                            reinterpret_cast<TO*>(dst), 1, d1, d2, d3, 0, s1, s2, s3,
+                                                            accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+static int permute_any(const void* src, int sdt, void* dst, int ddt, int d1, int d2, int d3, long long s1,
+                       long long s2, long long s3, int accumulate, cudaStream_t st) {
+    if (sdt == FMRI_F32 && ddt == FMRI_F32)
+        return permute_launch<float, float>(src, dst, d1, d2, d3, s1, s2, s3, accumulate, st);
+    if (sdt == FMRI_F32 && ddt == FMRI_BF16)
+        return permute_launch<float, __nv_bfloat16>(src, dst, d1, d2, d3, s1, s2, s3, accumulate, st);
+    if (sdt == FMRI_BF16 && ddt == FMRI_F32)
+        return permute_launch<__nv_bfloat16, float>(src, dst, d1, d2, d3, s1, s2, s3, accumulate, st);
+    if (sdt == FMRI_BF16 && ddt == FMRI_BF16)
+        return permute_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, d1, d2, d3, s1, s2, s3, accumulate, st);
+    return fail(FMRI_ERR_ARG, "bad dtype");
+}
+extern "C" int fmri_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+                                 void* stream) {
+    // dst[n][p][c] = src[n][c][p]
+    return permute_any(src, src_dtype, dst, dst_dtype, N, H * W, C, (long long)C * H * W, 1, (long long)H * W, 0,
+                       S(stream));
+}
+extern "C" int fmri_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+                                 int accumulate, void* stream) {
+    // dst[n][c][p] = src[n][p][c]
+    return permute_any(src, src_dtype, dst, dst_dtype, N, C, H * W, (long long)C * H * W, 1, C, accumulate,
+                       S(stream));
+}
+extern "C" int fmri_cast2d(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows,
+                           int cols, void* stream) {
+    const long long n = rows * cols;
+    cudaStream_t st = S(stream);
+    const int g = grid1d(n, 256);
+    // gather from a pitched source into a pitched destination: use scatter4 with dims (1,1,rows,cols) twice-strided
+    // dst[r*ldd + c] = src[r*lds + c]  -> implemented as a permute into a dense temp view when ldd == cols
+#define CAST_CASE(TI, TO)                                                                                         \
+    if (ldd == cols)                                                                                              \
+        permute4_kernel<TI, TO><<<g, 256, 0, st>>>(reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), 1, 1, \
+                                                   (int)rows, cols, 0, 0, lds, 1, 0);                             \
+    else if (lds == cols)                                                                                         \
+        scatter4_kernel<TI, TO><<<g, 256, 0, st>>>(reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), 1, 1, \
+                                                   (int)rows, cols, 0, 0, ldd, 1, 0);                             \
+    else                                                                                                          \
+        return fail(FMRI_ERR_UNSUPPORTED, "cast2d needs one dense side");
+    if (src_dtype == FMRI_F32 && dst_dtype == FMRI_BF16) {
+        CAST_CASE(float, __nv_bfloat16)
+    } else if (src_dtype == FMRI_BF16 && dst_dtype == FMRI_F32) {
+        CAST_CASE(__nv_bfloat16, float)
+    } else if (src_dtype == FMRI_F32 && dst_dtype == FMRI_F32) {
+        CAST_CASE(float, float)
+    } else {
+        CAST_CASE(__nv_bfloat16, __nv_bfloat16)
+    }
+#undef CAST_CASE
+    LAUNCH_OK();
+    return 0;
+}
+
+// ================================================================================================ losses
+extern "C" int fmri_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl, int B,
+                                   int Z, void* stream) {
+    if (z && !eps) return fail(FMRI_ERR_ARG, "reparam needs eps");
+    reparam_kl_fwd_kernel<<<cdiv(B, 4), 128, 0, S(stream)>>>(mu, logvar, eps, z, kl, B, Z);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* gz,
+                                   const float* gkl, float* dmu, float* dlogvar, int B, int Z, void* stream) {
+    reparam_kl_bwd_kernel<<<grid1d((long long)B * Z, 256), 256, 0, S(stream)>>>(mu, logvar, eps, gz, gkl, dmu, dlogvar,
+                                                                               B, Z);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_rowsqdiff_fwd(const void* a, const void* b, int dtype, float* out, long long rows, long long F,
+                                  float scale, void* stream) {
+    if (dtype == FMRI_BF16)
+        rowsqdiff_fwd_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), out, F, scale);
+    else
+        rowsqdiff_fwd_kernel<float><<<(unsigned)rows, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(a),
+                                                                          reinterpret_cast<const float*>(b), out, F,
+                                                                          scale);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_rowsqdiff_bwd(const void* a, const void* b, int dtype, const float* g, void* da, void* db,
+                                  long long rows, long long F, float scale, void* stream) {
+    const int gr = grid1d(rows * F, 256);
+    if (dtype == FMRI_BF16)
+        rowsqdiff_bwd_kernel<__nv_bfloat16><<<gr, 256, 0, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), g,
+            reinterpret_cast<__nv_bfloat16*>(da), reinterpret_cast<__nv_bfloat16*>(db), rows, F, scale);
+    else
+        rowsqdiff_bwd_kernel<float><<<gr, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(a),
+                                                              reinterpret_cast<const float*>(b), g,
+                                                              reinterpret_cast<float*>(da),
+                                                              reinterpret_cast<float*>(db), rows, F, scale);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_head_sigmoid_fwd(const void* x, int dtype, const float* w, const float* bias, float* p, int rows,
+                                     int F, void* stream) {
+    if (dtype == FMRI_BF16)
+        head_sigmoid_fwd_kernel<__nv_bfloat16><<<cdiv(rows, 4), 128, 0, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), w, bias, p, rows, F);
+    else
+        head_sigmoid_fwd_kernel<float><<<cdiv(rows, 4), 128, 0, S(stream)>>>(reinterpret_cast<const float*>(x), w, bias,
+                                                                            p, rows, F);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_head_sigmoid_bwd(const void* x, int dtype, const float* w, const float* p, const float* gp,
+                                     void* dx, float* dw, float* db, int rows, int F, void* stream) {
+    const int rpb = 16;
+    if (dtype == FMRI_BF16)
+        head_sigmoid_bwd_kernel<__nv_bfloat16><<<cdiv(rows, rpb), 256, 0, S(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), w, p, gp, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, F,
+            rpb);
+    else
+        head_sigmoid_bwd_kernel<float><<<cdiv(rows, rpb), 256, 0, S(stream)>>>(
+            reinterpret_cast<const float*>(x), w, p, gp, reinterpret_cast<float*>(dx), dw, db, rows, F, rpb);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_bce_fwd(const float* p, float* out, int n, int positive, float scale, void* stream) {
+    bce_fwd_kernel<<<cdiv(n, 256), 256, 0, S(stream)>>>(p, out, n, positive, scale);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_bce_bwd(const float* p, const float* g, float* dp, int n, int positive, float scale,
+                            int accumulate, void* stream) {
+    bce_bwd_kernel<<<cdiv(n, 256), 256, 0, S(stream)>>>(p, g, dp, n, positive, scale, accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+
+// ================================================================================================ optimizers
+extern "C" int fmri_multi_tensor_rmsprop(int n, float* const* p, const float* const* g, float* const* sq,
+                                         const int64_t* numel, float lr, float alpha, float eps, float clamp,
+                                         void* stream) {
+    for (int base = 0; base < n; base += FMRI_MT_MAX) {
+        MtArgs a;
+        a.count = std::min(FMRI_MT_MAX, n - base);
+        int64_t mx = 0;
+        for (int i = 0; i < a.count; ++i) {
+            a.t[i].p = p[base + i];
+            a.t[i].g = g[base + i];
+            a.t[i].s1 = sq[base + i];
+            a.t[i].s2 = nullptr;
+            a.t[i].n = (int)numel[base + i];
+            mx = std::max(mx, numel[base + i]);
+        }
+        dim3 grid(std::max(1, std::min(148 * 4, cdiv(mx, 256 * 4))), a.count);
+        mt_rmsprop_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, alpha, eps, clamp);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+extern "C" int fmri_multi_tensor_adam(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                      const int64_t* numel, float lr, float beta1, float beta2, float eps, int step,
+                                      float clamp, void* stream) {
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    for (int base = 0; base < n; base += FMRI_MT_MAX) {
+        MtArgs a;
+        a.count = std::min(FMRI_MT_MAX, n - base);
+        int64_t mx = 0;
+        for (int i = 0; i < a.count; ++i) {
+            a.t[i].p = p[base + i];
+            a.t[i].g = g[base + i];
+            a.t[i].s1 = m[base + i];
+            a.t[i].s2 = v[base + i];
+            a.t[i].n = (int)numel[base + i];
+            mx = std::max(mx, numel[base + i]);
+        }
+        dim3 grid(std::max(1, std::min(148 * 4, cdiv(mx, 256 * 4))), a.count);
+        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, bc1, bc2, clamp);
+        LAUNCH_OK();
+    }
+    return 0;
+}

@@ -1,0 +1,813 @@
+// CUDA-core kernels: the HBM-bound part of the training step (BatchNorm, losses, optimizers, layout/dtype
+// packers), the 3-channel edge convolutions, and a generic direct convolution used for the fp32-exact mode
+// and for shapes the tensor path does not tile.
+#pragma once
+#include "ptx.cuh"
+
+namespace fmri {
+
+template <typename T>
+__device__ __forceinline__ float ld_f(const T* p);
+template <>
+__device__ __forceinline__ float ld_f<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void st_f(T* p, float v);
+template <>
+__device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    if (act == 3) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic 5x5 direct convolution, gather form. Tensors are addressed through element strides so the same
+// kernel reads/writes NHWC (internal) and NCHW (module boundary) tensors.
+//   transposed == 0 : out[n,oy,ox,co] = sum in[n, oy*s+kh-2, ox*s+kw-2, ci] * w[co*w_so + ci*w_si + kh*5+kw]
+//   transposed == 1 : out[n,oy,ox,co] = sum over (kh,kw) with (oy+2-kh) % s == 0 of in[n,(oy+2-kh)/s,..,ci] * w[..]
+// (the second form is both ConvTranspose2d forward and Conv2d data-gradient).
+// ------------------------------------------------------------------------------------------------
+struct DirectConvParams {
+    int N, H, W, Cin;       // input
+    int OH, OW, Cout;       // output
+    int stride, transposed;
+    long long in_sn, in_sy, in_sx, in_sc;
+    long long out_sn, out_sy, out_sx, out_sc;
+    long long w_so, w_si;   // weight element strides for (output channel, input channel); taps are contiguous
+    int flip;               // use tap (4-kh, 4-kw) instead of (kh, kw)
+    int act;
+    int accumulate;         // out += result (fp32 out only)
+};
+
+template <typename Tin, typename Tout>
+__global__ void direct_conv_kernel(const Tin* __restrict__ in, const float* __restrict__ w,
+                                   const float* __restrict__ bias, Tout* __restrict__ out, DirectConvParams p) {
+    const long long total = (long long)p.N * p.OH * p.OW * p.Cout;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % p.Cout);
+        long long r = idx / p.Cout;
+        const int ox = (int)(r % p.OW);
+        r /= p.OW;
+        const int oy = (int)(r % p.OH);
+        const int n = (int)(r / p.OH);
+        float acc = bias ? __ldg(bias + co) : 0.f;
+        for (int kh = 0; kh < 5; ++kh) {
+            int iy;
+            if (!p.transposed) {
+                iy = oy * p.stride + kh - 2;
+            } else {
+                const int t = oy + 2 - kh;
+                if (t < 0 || (t % p.stride) != 0) continue;
+                iy = t / p.stride;
+            }
+            if (iy < 0 || iy >= p.H) continue;
+            for (int kw = 0; kw < 5; ++kw) {
+                int ix;
+                if (!p.transposed) {
+                    ix = ox * p.stride + kw - 2;
+                } else {
+                    const int t = ox + 2 - kw;
+                    if (t < 0 || (t % p.stride) != 0) continue;
+                    ix = t / p.stride;
+                }
+                if (ix < 0 || ix >= p.W) continue;
+                const int tap = p.flip ? (4 - kh) * 5 + (4 - kw) : kh * 5 + kw;
+                const Tin* ip = in + n * p.in_sn + iy * p.in_sy + ix * p.in_sx;
+                const float* wp = w + co * p.w_so + tap;
+                for (int ci = 0; ci < p.Cin; ++ci) acc += ld_f(ip + ci * p.in_sc) * __ldg(wp + ci * p.w_si);
+            }
+        }
+        acc = apply_act(acc, p.act);
+        Tout* o = out + n * p.out_sn + oy * p.out_sy + ox * p.out_sx + co * p.out_sc;
+        st_f(o, acc);
+    }
+}
+
+// Generic weight gradient: dw[a*w_sa + b*w_sb + tap] (+)= sum_{n,py,px} A[n,py,px,a] * B[n, py*s+kh-2, px*s+kw-2, b]
+// A is the tensor on the strided-output side of the convolution, B the one on its input side.
+struct DirectWgradParams {
+    int N, PH, PW, Ca;   // A grid
+    int BH, BW, Cb;      // B grid
+    int stride;
+    long long a_sn, a_sy, a_sx, a_sc;
+    long long b_sn, b_sy, b_sx, b_sc;
+    long long w_sa, w_sb;
+    int accumulate;
+};
+
+template <typename Ta, typename Tb>
+__global__ void direct_wgrad_kernel(const Ta* __restrict__ A, const Tb* __restrict__ B, float* __restrict__ dw,
+                                    DirectWgradParams p) {
+    // one block per (a, b, tap) triple; threads stride over pixels
+    const int tap = blockIdx.x % 25;
+    const int ab = blockIdx.x / 25;
+    const int b = ab % p.Cb;
+    const int a = ab / p.Cb;
+    const int kh = tap / 5, kw = tap % 5;
+    const long long pixels = (long long)p.N * p.PH * p.PW;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < pixels; i += blockDim.x) {
+        const int px = (int)(i % p.PW);
+        const long long r = i / p.PW;
+        const int py = (int)(r % p.PH);
+        const int n = (int)(r / p.PH);
+        const int by = py * p.stride + kh - 2, bx = px * p.stride + kw - 2;
+        if (by < 0 || by >= p.BH || bx < 0 || bx >= p.BW) continue;
+        acc += ld_f(A + n * p.a_sn + py * p.a_sy + px * p.a_sx + a * p.a_sc) *
+               ld_f(B + n * p.b_sn + by * p.b_sy + bx * p.b_sx + b * p.b_sc);
+    }
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            float* o = dw + a * p.w_sa + b * p.w_sb + tap;
+            *o = p.accumulate ? *o + v : v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge convolutions with a 3-channel side (image side, NCHW fp32) and a C-channel side (NHWC, C = 32/64).
+// ------------------------------------------------------------------------------------------------
+// (A) img3 -> C channels. out[n,oy,ox,c] = act(bias[c] + sum_{ci<3,kh,kw} img[n,ci,oy*s+kh-2,ox*s+kw-2] * wk[(ci*25+tap)*C + c])
+//     `wk` is a [75][C] fp32 pack staged in shared memory. Up to three source images are concatenated on
+//     the batch axis (the discriminator's torch.cat, vae_gan.py:165) without materialising the cat.
+template <int C, typename Tout>
+__global__ void __launch_bounds__(128) edge3_to_c_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                         const float* __restrict__ src2, int n_per_src,
+                                                         const float* __restrict__ wk, const float* __restrict__ bias,
+                                                         Tout* __restrict__ out, int N, int H, int W, int OH, int OW,
+                                                         int stride, int act) {
+    __shared__ float sw[75 * C];
+    for (int i = threadIdx.x; i < 75 * C; i += blockDim.x) sw[i] = wk[i];
+    __syncthreads();
+    const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * OH * OW) return;
+    const int ox = (int)(pix % OW);
+    const int oy = (int)((pix / OW) % OH);
+    const int n = (int)(pix / ((long long)OW * OH));
+    const int s = n / n_per_src;
+    const float* img = (s == 0 ? src0 : (s == 1 ? src1 : src2)) + (long long)(n - s * n_per_src) * 3 * H * W;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int kh = 0; kh < 5; ++kh) {
+            const int iy = oy * stride + kh - 2;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 5; ++kw) {
+                const int ix = ox * stride + kw - 2;
+                if (ix < 0 || ix >= W) continue;
+                const float v = __ldg(img + ((long long)ci * H + iy) * W + ix);
+                const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 25 + kh * 5 + kw) * C);
+#pragma unroll
+                for (int c4 = 0; c4 < C / 4; ++c4) {
+                    const float4 wv = wr[c4];
+                    acc[4 * c4 + 0] += v * wv.x;
+                    acc[4 * c4 + 1] += v * wv.y;
+                    acc[4 * c4 + 2] += v * wv.z;
+                    acc[4 * c4 + 3] += v * wv.w;
+                }
+            }
+        }
+    }
+    Tout* o = out + pix * C;
+    if constexpr (sizeof(Tout) == 2) {
+#pragma unroll
+        for (int c8 = 0; c8 < C / 8; ++c8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                pk[j] = pack_bf16x2(apply_act(acc[8 * c8 + 2 * j], act), apply_act(acc[8 * c8 + 2 * j + 1], act));
+            *reinterpret_cast<uint4*>(o + 8 * c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) st_f(o + c, apply_act(acc[c], act));
+    }
+}
+
+// (B) C channels -> img3. img[n,co,y,x] = act(bias[co] + sum_{c,taps} in[n, (y,x)@tap, c] * wk[(co*25+tap)*C + c])
+//     gather over the C-channel NHWC tensor. `up`: the C-side grid is the stride-s *output* of the forward conv
+//     (data gradient of a strided 3->C conv): in pixel = (y+2-kh)/s when divisible.
+template <int C, typename Tin>
+__global__ void __launch_bounds__(128) edgec_to_3_kernel(const Tin* __restrict__ in, const float* __restrict__ wk,
+                                                         const float* __restrict__ bias, float* __restrict__ img,
+                                                         int N, int IH, int IW, int OH, int OW, int stride_up,
+                                                         int flip, int act, int accumulate) {
+    __shared__ float sw[75 * C];
+    for (int i = threadIdx.x; i < 75 * C; i += blockDim.x) sw[i] = wk[i];
+    __syncthreads();
+    const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * OH * OW) return;
+    const int ox = (int)(pix % OW);
+    const int oy = (int)((pix / OW) % OH);
+    const int n = (int)(pix / ((long long)OW * OH));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int kh = 0; kh < 5; ++kh) {
+        int iy;
+        if (stride_up == 1) {
+            iy = oy + kh - 2;
+        } else {
+            const int t = oy + 2 - kh;
+            if (t < 0 || (t % stride_up)) continue;
+            iy = t / stride_up;
+        }
+        if (iy < 0 || iy >= IH) continue;
+        for (int kw = 0; kw < 5; ++kw) {
+            int ix;
+            if (stride_up == 1) {
+                ix = ox + kw - 2;
+            } else {
+                const int t = ox + 2 - kw;
+                if (t < 0 || (t % stride_up)) continue;
+                ix = t / stride_up;
+            }
+            if (ix < 0 || ix >= IW) continue;
+            const int tap = flip ? (4 - kh) * 5 + (4 - kw) : kh * 5 + kw;
+            const Tin* ip = in + (((long long)n * IH + iy) * IW + ix) * C;
+            const float* w0 = sw + (0 * 25 + tap) * C;
+            const float* w1 = sw + (1 * 25 + tap) * C;
+            const float* w2 = sw + (2 * 25 + tap) * C;
+            if constexpr (sizeof(Tin) == 2) {
+#pragma unroll
+                for (int c8 = 0; c8 < C / 8; ++c8) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ip + 8 * c8));
+                    const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float lo = __uint_as_float(rr[j] << 16), hi = __uint_as_float(rr[j] & 0xffff0000u);
+                        const int c = 8 * c8 + 2 * j;
+                        a0 += lo * w0[c] + hi * w0[c + 1];
+                        a1 += lo * w1[c] + hi * w1[c + 1];
+                        a2 += lo * w2[c] + hi * w2[c + 1];
+                    }
+                }
+            } else {
+#pragma unroll 8
+                for (int c = 0; c < C; ++c) {
+                    const float v = ld_f(ip + c);
+                    a0 += v * w0[c];
+                    a1 += v * w1[c];
+                    a2 += v * w2[c];
+                }
+            }
+        }
+    }
+    if (bias) {
+        a0 += __ldg(bias + 0);
+        a1 += __ldg(bias + 1);
+        a2 += __ldg(bias + 2);
+    }
+    float* o = img + ((long long)n * 3) * OH * OW + (long long)oy * OW + ox;
+    const long long cs = (long long)OH * OW;
+    if (accumulate) {
+        o[0] += apply_act(a0, act);
+        o[cs] += apply_act(a1, act);
+        o[2 * cs] += apply_act(a2, act);
+    } else {
+        o[0] = apply_act(a0, act);
+        o[cs] = apply_act(a1, act);
+        o[2 * cs] = apply_act(a2, act);
+    }
+}
+
+// (W) weight gradient with a 3-channel image side: dwk[(c3*25+tap)*C + c] += sum_{n,py,px} T[n,py,px,c] * img[n,c3,py*s+sg*(kh-2),..]
+//     T: C-channel NHWC tensor on grid (PH,PW); img: NCHW fp32 on grid (IH,IW). sg = +1 when T is the conv output
+//     (3->C conv: img is the input), sg = -1 with s=1 when T is the conv input (C->3 conv: img is dY).
+//     grid: blocks stride over pixel chunks; each block reduces into registers then atomics into dwk (fp32 [75][C]).
+template <int C, typename Tt>
+__global__ void __launch_bounds__(256) edge_wgrad_kernel(const Tt* __restrict__ T, const float* __restrict__ src0,
+                                                         const float* __restrict__ src1,
+                                                         const float* __restrict__ src2, int n_per_src,
+                                                         float* __restrict__ dwk, int N, int PH, int PW, int IH,
+                                                         int IW, int stride, int sg, int pix_per_block) {
+    // thread -> (channel c, tap-group g); 256 threads = C channels x (256/C) groups
+    constexpr int G = 256 / C;
+    constexpr int TPG = (75 + G - 1) / G;  // (c3,tap) pairs per group
+    const int c = threadIdx.x % C;
+    const int g = threadIdx.x / C;
+    float acc[TPG];
+#pragma unroll
+    for (int i = 0; i < TPG; ++i) acc[i] = 0.f;
+    __shared__ float patch[8][75];  // 8 pixels staged per iteration
+    const long long pixels = (long long)N * PH * PW;
+    const long long p_begin = (long long)blockIdx.x * pix_per_block;
+    const long long p_end = min(pixels, p_begin + pix_per_block);
+    for (long long p0 = p_begin; p0 < p_end; p0 += 8) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 75; i += 256) {
+            const int pi = i / 75, j = i % 75;
+            const long long pp = p0 + pi;
+            float v = 0.f;
+            if (pp < p_end) {
+                const int px = (int)(pp % PW);
+                const int py = (int)((pp / PW) % PH);
+                const int n = (int)(pp / ((long long)PW * PH));
+                const int c3 = j / 25, tap = j % 25;
+                const int iy = py * stride + sg * (tap / 5 - 2), ix = px * stride + sg * (tap % 5 - 2);
+                if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) {
+                    const int s = n / n_per_src;
+                    const float* img = (s == 0 ? src0 : (s == 1 ? src1 : src2)) +
+                                       (long long)(n - s * n_per_src) * 3 * IH * IW;
+                    v = __ldg(img + ((long long)c3 * IH + iy) * IW + ix);
+                }
+            }
+            patch[pi][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pi = 0; pi < 8; ++pi) {
+            const long long pp = p0 + pi;
+            if (pp >= p_end) break;
+            const float tv = ld_f(T + pp * C + c);
+#pragma unroll
+            for (int i = 0; i < TPG; ++i) {
+                const int j = g * TPG + i;
+                if (j < 75) acc[i] += tv * patch[pi][j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TPG; ++i) {
+        const int j = g * TPG + i;
+        if (j < 75) atomicAdd(dwk + j * C + c, acc[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Simple fp32 SIMT GEMM family (exact mode and small shapes): C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias, act)
+// with arbitrary element strides so that the transposed products of dgrad / wgrad reuse it.
+// ------------------------------------------------------------------------------------------------
+template <typename Ta, typename Tb, typename Tc>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const Ta* __restrict__ A, long long a_sm, long long a_sk,
+                                                        const Tb* __restrict__ B, long long b_sn, long long b_sk,
+                                                        Tc* __restrict__ Cm, long long c_sm, long long c_sn,
+                                                        const float* __restrict__ bias, int M, int N, int K, int act,
+                                                        int accumulate) {
+    __shared__ float sa[16][65];
+    __shared__ float sb[16][65];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int r, kk;
+            // pick the loop order that keeps global reads contiguous
+            if (a_sk == 1) { kk = i % 16; r = i / 16; } else { r = i % 64; kk = i / 64; }
+            const int m = m0 + r, k = k0 + kk;
+            sa[kk][r] = (m < M && k < K) ? ld_f(A + m * a_sm + k * a_sk) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int r, kk;
+            if (b_sk == 1) { kk = i % 16; r = i / 16; } else { r = i % 64; kk = i / 64; }
+            const int n = n0 + r, k = k0 + kk;
+            sb[kk][r] = (n < N && k < K) ? ld_f(B + n * b_sn + k * b_sk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+            v = apply_act(v, act);
+            Tc* o = Cm + m * c_sm + n * c_sn;
+            if (accumulate) v += ld_f(o);
+            st_f(o, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (train mode) on a [rows, C] channels-last matrix (conv: rows = N*H*W; linear: rows = batch)
+// ------------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares -> double accumulators (used when the producer kernel did not fuse them)
+template <typename T>
+__global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, long long rows, int C,
+                                                       double* __restrict__ sum, double* __restrict__ sq,
+                                                       int rows_per_block) {
+    // threads: 256 = cx columns x ry row-lanes, coalesced along C
+    const int cx = C >= 256 ? 256 : C;  // C is a power of two multiple of 32 or anything <= 256
+    const int ry = 256 / cx;
+    const int tc = threadIdx.x % cx, tr = threadIdx.x / cx;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    extern __shared__ float sred[];  // [2][256]
+    for (int cb = blockIdx.y * cx; cb < C; cb += gridDim.y * cx) {
+        const int col = cb + tc;
+        float s = 0.f, q = 0.f;
+        if (col < C && tr < ry)
+            for (long long r = r0 + tr; r < r1; r += ry) {
+                const float v = ld_f(x + r * C + col);
+                s += v;
+                q += v * v;
+            }
+        sred[threadIdx.x] = s;
+        sred[256 + threadIdx.x] = q;
+        __syncthreads();
+        if (tr == 0 && col < C) {
+            for (int j = 1; j < ry; ++j) {
+                s += sred[j * cx + tc];
+                q += sred[256 + j * cx + tc];
+            }
+            atomicAdd(sum + col, (double)s);
+            atomicAdd(sq + col, (double)q);
+        }
+        __syncthreads();
+    }
+}
+
+// finalize: mean / invstd from the sums, running-stat update (momentum semantic of torch: r = (1-m) r + m * batch,
+// unbiased variance for the running estimate), vae_gan.py:21 uses momentum=0.9.
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double count, int C,
+                                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sum[c] / count;
+    double var = sq[c] / count - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// y = relu(gamma * (x - mean) * invstd + beta); 8 elements per thread, channels-last
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const Tin* __restrict__ x, Tout* __restrict__ y,
+                                                       long long total, int C, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int relu) {
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < total;
+         i += (long long)gridDim.x * blockDim.x * 8) {
+        const int c0 = (int)(i % C);
+        float v[8];
+        if constexpr (sizeof(Tin) == 2) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(x + i);
+            const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[2 * j] = __uint_as_float(rr[j] << 16);
+                v[2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+            }
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(x + i);
+            const float4 b = *reinterpret_cast<const float4*>(x + i + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float sc = __ldg(gamma + c) * __ldg(invstd + c);
+            float o = (v[j] - __ldg(mean + c)) * sc + __ldg(beta + c);
+            v[j] = relu ? fmaxf(o, 0.f) : o;
+        }
+        if constexpr (sizeof(Tout) == 2) {
+            *reinterpret_cast<uint4*>(y + i) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        } else {
+            *reinterpret_cast<float4*>(y + i) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(y + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+}
+
+// backward pass 1: per channel sum(g) and sum(g * xhat), g = dy * (out > 0) where out = gamma*xhat+beta
+template <typename Tx, typename Tg>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy,
+                                                            long long rows, int C, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int relu,
+                                                            double* __restrict__ sum_g, double* __restrict__ sum_gx,
+                                                            int rows_per_block) {
+    const int cx = C >= 256 ? 256 : C;
+    const int ry = 256 / cx;
+    const int tc = threadIdx.x % cx, tr = threadIdx.x / cx;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    extern __shared__ float sred[];
+    for (int cb = blockIdx.y * cx; cb < C; cb += gridDim.y * cx) {
+        const int col = cb + tc;
+        float s = 0.f, q = 0.f;
+        if (col < C && tr < ry) {
+            const float mu = mean[col], is = invstd[col], ga = gamma[col], be = beta[col];
+            for (long long r = r0 + tr; r < r1; r += ry) {
+                const float xh = (ld_f(x + r * C + col) - mu) * is;
+                float g = ld_f(dy + r * C + col);
+                if (relu && !(ga * xh + be > 0.f)) g = 0.f;
+                s += g;
+                q += g * xh;
+            }
+        }
+        sred[threadIdx.x] = s;
+        sred[256 + threadIdx.x] = q;
+        __syncthreads();
+        if (tr == 0 && col < C) {
+            for (int j = 1; j < ry; ++j) {
+                s += sred[j * cx + tc];
+                q += sred[256 + j * cx + tc];
+            }
+            atomicAdd(sum_g + col, (double)s);
+            atomicAdd(sum_gx + col, (double)q);
+        }
+        __syncthreads();
+    }
+}
+
+// backward pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat)); dgamma = sum_gx, dbeta = sum_g (written by
+// block 0). `train`=0 (eval-mode BN: statistics are constants): dx = gamma*invstd*g.
+template <typename Tx, typename Tg>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy,
+                                                           Tg* __restrict__ dx, long long total, int C, double count,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int relu, int train,
+                                                           const double* __restrict__ sum_g,
+                                                           const double* __restrict__ sum_gx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float is = invstd[c], ga = gamma[c];
+        const float xh = (ld_f(x + i) - mean[c]) * is;
+        float g = ld_f(dy + i);
+        if (relu && !(ga * xh + beta[c] > 0.f)) g = 0.f;
+        float r = g;
+        if (train) r = g - (float)(sum_g[c] / count) - xh * (float)(sum_gx[c] / count);
+        st_f(dx + i, ga * is * r);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, int C,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float dg = (float)sum_gx[c], db = (float)sum_g[c];
+    dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+    dbeta[c] = accumulate ? dbeta[c] + db : db;
+}
+
+// relu backward on its own (bias+ReLU layers: discriminator conv0, WAE discriminator MLP): dx = dy * (y > 0)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        st_f(dx + i, ld_f(y + i) > 0.f ? ld_f(dy + i) : 0.f);
+}
+
+// column sums of a [rows, C] matrix into fp32 (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int C,
+                                                     float* __restrict__ out, int rows_per_block) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (long long r = r0; r < r1; ++r) s += ld_f(x + r * C + c);
+        atomicAdd(out + c, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout / dtype packers
+// ------------------------------------------------------------------------------------------------
+// strided gather copy with dtype conversion: dst[i0,i1,i2,i3] (dense, row-major) = src[i0*s0+i1*s1+i2*s2+i3*s3]
+template <typename Tin, typename Tout>
+__global__ void permute4_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int d0, int d1, int d2, int d3,
+                                long long s0, long long s1, long long s2, long long s3, int accumulate) {
+    const long long total = (long long)d0 * d1 * d2 * d3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int i3 = (int)(i % d3);
+        long long r = i / d3;
+        const int i2 = (int)(r % d2);
+        r /= d2;
+        const int i1 = (int)(r % d1);
+        const int i0 = (int)(r / d1);
+        float v = ld_f(src + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3);
+        if (accumulate) v += ld_f(dst + i);
+        st_f(dst + i, v);
+    }
+}
+// strided scatter: dst[i0*s0+i1*s1+i2*s2+i3*s3] (+)= src[i0,i1,i2,i3] (dense)
+template <typename Tin, typename Tout>
+__global__ void scatter4_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int d0, int d1, int d2, int d3,
+                                long long s0, long long s1, long long s2, long long s3, int accumulate) {
+    const long long total = (long long)d0 * d1 * d2 * d3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int i3 = (int)(i % d3);
+        long long r = i / d3;
+        const int i2 = (int)(r % d2);
+        r /= d2;
+        const int i1 = (int)(r % d1);
+        const int i0 = (int)(r / d1);
+        Tout* o = dst + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3;
+        float v = ld_f(src + i);
+        if (accumulate) v += ld_f(o);
+        st_f(o, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses (vae_gan.py:302-320, train_vgan_stage1.py:369-372, train_wae_stage1.py:281-282,301-303)
+// ------------------------------------------------------------------------------------------------
+// z = eps*exp(0.5*logvar)+mu ; kl[b] = -0.5 * sum_j (1 + lv - mu^2 - exp(lv)); one warp per row
+__global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                      const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ kl,
+                                      int B, int Z) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int j = lane; j < Z; j += 32) {
+        const float m = mu[row * (long long)Z + j], l = lv[row * (long long)Z + j];
+        const float e = __expf(l);
+        if (z) z[row * (long long)Z + j] = eps[row * (long long)Z + j] * __expf(0.5f * l) + m;
+        s += 1.f + l - m * m - e;
+    }
+    s = warp_sum(s);
+    if (lane == 0 && kl) kl[row] = -0.5f * s;
+}
+// dmu = gz + gkl[b]*mu ; dlv = gz*eps*0.5*exp(0.5 lv) + gkl[b]*0.5*(exp(lv)-1)
+__global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                      const float* __restrict__ eps, const float* __restrict__ gz,
+                                      const float* __restrict__ gkl, float* __restrict__ dmu, float* __restrict__ dlv,
+                                      int B, int Z) {
+    const long long n = (long long)B * Z;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / Z);
+        const float l = lv[i], m = mu[i];
+        const float g = gz ? gz[i] : 0.f;
+        const float k = gkl ? gkl[b] : 0.f;
+        dmu[i] = g + k * m;
+        dlv[i] = (gz ? g * eps[i] * 0.5f * __expf(0.5f * l) : 0.f) + k * 0.5f * (__expf(l) - 1.f);
+    }
+}
+// out[b] = scale * sum_j (a[b,j]-b[b,j])^2 ; one block per row, warp-shuffle reduction, vectorised loads
+template <typename T>
+__global__ void __launch_bounds__(256) rowsqdiff_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                            float* __restrict__ out, long long F, float scale) {
+    const long long row = blockIdx.x;
+    const T* pa = a + row * F;
+    const T* pb = b + row * F;
+    float s = 0.f;
+    for (long long j = threadIdx.x; j < F; j += blockDim.x) {
+        const float d = ld_f(pa + j) - ld_f(pb + j);
+        s += d * d;
+    }
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[row] = scale * v;
+    }
+}
+// da = 2*scale*g[b]*(a-b) ; db = -da  (either may be null)
+template <typename T>
+__global__ void rowsqdiff_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ g,
+                                     T* __restrict__ da, T* __restrict__ db, long long rows, long long F,
+                                     float scale) {
+    const long long n = rows * F;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = 2.f * scale * g[i / F] * (ld_f(a + i) - ld_f(b + i));
+        if (da) st_f(da + i, v);
+        if (db) st_f(db + i, -v);
+    }
+}
+// logit head: p = sigmoid(x . w + b) for a [rows, F] matrix and a single output unit (Linear(F,1) + sigmoid);
+// one warp per row. vae_gan.py:160,183 and :519-520.
+template <typename T>
+__global__ void head_sigmoid_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ bias, float* __restrict__ p, int rows, int F) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int j = lane; j < F; j += 32) s += ld_f(x + (long long)row * F + j) * __ldg(w + j);
+    s = warp_sum(s);
+    if (lane == 0) p[row] = 1.f / (1.f + __expf(-(s + bias[0])));
+}
+// given gp = dL/dp: dlogit = gp*p*(1-p); dx[row,:] = dlogit*w ; dw += sum_rows dlogit*x[row,:] ; db += sum dlogit
+template <typename T>
+__global__ void __launch_bounds__(256) head_sigmoid_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ p,
+                                                               const float* __restrict__ gp, T* __restrict__ dx,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               int rows, int F, int rows_per_block) {
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    for (int j = threadIdx.x; j < F; j += blockDim.x) {
+        const float wj = w[j];
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const float pr = p[r];
+            const float dl = gp[r] * pr * (1.f - pr);
+            if (dx) st_f(dx + (long long)r * F + j, dl * wj);
+            acc += dl * ld_f(x + (long long)r * F + j);
+        }
+        if (dw) atomicAdd(dw + j, acc);
+    }
+    if (db && threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) acc += gp[r] * p[r] * (1.f - p[r]);
+        atomicAdd(db, acc);
+    }
+}
+// bce[i] = -log(sign>0 ? p+1e-3 : 1-p+1e-3) * scale
+__global__ void bce_fwd_kernel(const float* __restrict__ p, float* __restrict__ out, int n, int positive,
+                               float scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = -scale * __logf(positive ? p[i] + 1e-3f : 1.f - p[i] + 1e-3f);
+}
+__global__ void bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ dp,
+                               int n, int positive, float scale, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = positive ? -scale * g[i] / (p[i] + 1e-3f) : scale * g[i] / (1.f - p[i] + 1e-3f);
+    dp[i] = accumulate ? dp[i] + v : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused multi-tensor optimizers (train_vgan_stage1.py:275-283 RMSprop(alpha=.9, eps=1e-8);
+// train_wae_stage1.py:221-224 Adam(betas=(.5,.999))). One launch updates a whole parameter bucket.
+// ------------------------------------------------------------------------------------------------
+struct MtChunk {
+    float* p;
+    const float* g;
+    float* s1;   // RMSprop: square_avg ; Adam: exp_avg
+    float* s2;   // Adam: exp_avg_sq
+    int n;
+};
+#define FMRI_MT_MAX 48
+struct MtArgs {
+    MtChunk t[FMRI_MT_MAX];
+    int count;
+};
+__global__ void __launch_bounds__(256) mt_rmsprop_kernel(const __grid_constant__ MtArgs a, float lr, float alpha,
+                                                         float eps, float clamp) {
+    const MtChunk t = a.t[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += gridDim.x * blockDim.x) {
+        float g = t.g[i];
+        if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+        const float sq = alpha * t.s1[i] + (1.f - alpha) * g * g;
+        t.s1[i] = sq;
+        t.p[i] = t.p[i] - lr * g / (sqrtf(sq) + eps);
+    }
+}
+__global__ void __launch_bounds__(256) mt_adam_kernel(const __grid_constant__ MtArgs a, float lr, float beta1,
+                                                      float beta2, float eps, float bc1, float bc2, float clamp) {
+    const MtChunk t = a.t[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += gridDim.x * blockDim.x) {
+        float g = t.g[i];
+        if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+        const float m = beta1 * t.s1[i] + (1.f - beta1) * g;
+        const float v = beta2 * t.s2[i] + (1.f - beta2) * g * g;
+        t.s1[i] = m;
+        t.s2[i] = v;
+        const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+        t.p[i] = t.p[i] - (lr / bc1) * m / denom;
+    }
+}
+
+}  // namespace fmri

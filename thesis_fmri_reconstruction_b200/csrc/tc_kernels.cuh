@@ -1,0 +1,432 @@
+// tcgen05 / TMEM / TMA kernels shared by every dense contraction on the VAE/GAN training path.
+//
+//  igemm_kernel : D[pixels or rows, N] = sum over (tap, k-chunk) A_tap[pixels, k] * B_tap[N, k]^T
+//                 A tiles are TMA boxes of an NHWC activation (one box per filter tap -> implicit GEMM),
+//                 B tiles are TMA boxes of a tap-major bf16 weight pack. Both K-major, 128B/64B swizzle.
+//                 Covers: 5x5 s2 conv fprop, convT dgrad (gather form, 4 stride-parity tensor maps),
+//                         5x5 s2 convT fprop, conv dgrad (scatter form, 4 output-parity classes),
+//                         5x5 s1 conv, and plain linear layers (1 tap), optional split-K.
+//  wgrad_kernel : dW[tap][M, N] = sum over pixels P_dense[pixel, M]^T * P_shift[pixel@tap, N]
+//                 both operands MN-major straight out of NHWC (pixels are the reduction dim).
+//
+// Reference ops replaced: nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward+backward as dispatched by
+// /root/reference/models/vae_gan.py:18-21,46-54,79-85,107-121,146-161,199-207,510-521.
+#pragma once
+#include "ptx.cuh"
+
+namespace fmri {
+
+struct TapDesc {
+    int16_t map;   // which A tensor map (stride-parity plane) this tap reads
+    int16_t dx;    // pixel offset added to the tile origin (x)
+    int16_t dy;    // pixel offset added to the tile origin (y)
+    int16_t pad_;
+    int32_t brow;  // first row of this tap's weights in the B pack
+};
+
+struct TapClass {       // one per blockIdx.z (output-parity class of a transposed conv); 1 class otherwise
+    int num_taps;
+    int lim_x, lim_y;   // valid extent of the output (sub)grid
+    long long out_off;  // element offset of this class' first output pixel
+    TapDesc taps[25];
+};
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
+
+struct IgParams {
+    CUtensorMap mapA[4];
+    CUtensorMap mapB;
+    TapClass cls[4];
+    int bw, bh, bn;                 // pixel box of one M tile (bw*bh*bn <= 128 rows)
+    int tiles_x, tiles_y, tiles_n;  // M tiles
+    int lim_n;                      // images
+    int num_chunks;                 // K chunks per tap
+    int n_total, n_tiles;           // GEMM N and its tiling
+    int splits;                     // split-K factor
+    int a_bytes;                    // bytes one A box delivers
+    long long out_sn, out_sy, out_sx;
+    void* out;
+    int out_fp32;    // 0: bf16 store, 1: fp32 store
+    int atomic_out;  // fp32 red.add (split-K / accumulate)
+    const float* bias;
+    int act;
+    double* stat_sum;  // optional per-column sum / sum of squares of the stored values
+    double* stat_sq;
+};
+
+template <int BN, int KCH, int STAGES>
+struct IgSmem {
+    static constexpr int A_BYTES = 128 * KCH * 2;
+    static constexpr int B_BYTES = BN * KCH * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int TOTAL = STAT_OFF + 2 * BN * 4 + 1024;  // +1024: manual base alignment
+};
+
+// transposing butterfly: on exit lane l holds the sum over the 32 lanes of f[l]
+__device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const bool up = lane & 16;
+        const float send = up ? f[j] : f[j + 16];
+        const float keep = up ? f[j + 16] : f[j];
+        f[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool up = lane & 8;
+        const float send = up ? f[j] : f[j + 8];
+        const float keep = up ? f[j + 8] : f[j];
+        f[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool up = lane & 4;
+        const float send = up ? f[j] : f[j + 4];
+        const float keep = up ? f[j + 4] : f[j];
+        f[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const bool up = lane & 2;
+        const float send = up ? f[j] : f[j + 2];
+        const float keep = up ? f[j + 2] : f[j];
+        f[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+        const bool up = lane & 1;
+        const float send = up ? f[0] : f[1];
+        const float keep = up ? f[1] : f[0];
+        f[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    return f[0];
+}
+
+template <int BN, int KCH, int STAGES>
+__global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgParams p) {
+    using L = IgSmem<BN, KCH, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* s_stat = reinterpret_cast<float*>(smem + L::STAT_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- which tile
+    const TapClass& c = p.cls[blockIdx.z];
+    const int mt = blockIdx.x;
+    const int tx = mt % p.tiles_x;
+    const int ty = (mt / p.tiles_x) % p.tiles_y;
+    const int tn = mt / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+    const int nt = blockIdx.y % p.n_tiles;
+    const int split = blockIdx.y / p.n_tiles;
+    if (x0 >= c.lim_x || y0 >= c.lim_y) return;  // tile outside this parity class' sub-grid
+    const int ks_total = c.num_taps * p.num_chunks;
+    const int ks_begin = (int)((long long)split * ks_total / p.splits);
+    const int ks_end = (int)((long long)(split + 1) * ks_total / p.splits);
+    if (ks_begin >= ks_end) return;
+    const int nks = ks_end - ks_begin;
+
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA[0]);
+        tma_prefetch_desc(&p.mapB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int i = 0; i < nks; ++i) {
+                const int st = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + L::B_BYTES);
+                const int ks = ks_begin + i;
+                const int tap = ks / p.num_chunks;
+                const int ch = ks - tap * p.num_chunks;
+                const TapDesc t = c.taps[tap];
+                uint8_t* sa = smem + st * L::STAGE_BYTES;
+                tma_load_4d(sa, &p.mapA[t.map], &full_bar[st], ch * KCH, x0 + t.dx, y0 + t.dy, n0);
+                tma_load_2d(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, t.brow + nt * BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+            constexpr uint64_t layout = (KCH == 64) ? UMMA_SW128 : UMMA_SW64;
+            constexpr uint32_t sbo = 8 * KCH * 2;
+            for (int i = 0; i < nks; ++i) {
+                const int st = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[st], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
+                const uint64_t adesc = umma_smem_desc(sa, 16, sbo, layout);
+                const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout);
+#pragma unroll
+                for (int k = 0; k < KCH / 16; ++k)
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs retire
+            }
+            umma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane;
+        const int xi = row % p.bw;
+        const int yi = (row / p.bw) % p.bh;
+        const int ni = row / (p.bw * p.bh);
+        const bool valid = (ni < p.bn) && (n0 + ni < p.lim_n) && (y0 + yi < c.lim_y) && (x0 + xi < c.lim_x);
+        const long long off = c.out_off + (long long)(n0 + ni) * p.out_sn + (long long)(y0 + yi) * p.out_sy +
+                              (long long)(x0 + xi) * p.out_sx + (long long)nt * BN;
+        const bool do_stats = p.stat_sum != nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            } else if (p.act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+            } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+            }
+            if (p.out_fp32) {
+                if (valid) {
+                    float* o = reinterpret_cast<float*>(p.out) + off + c0;
+                    if (p.atomic_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                }
+            } else {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (valid) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(o + 8 * j) =
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                if (do_stats) {  // statistics of exactly what was stored (bf16-rounded)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        f[2 * j] = __uint_as_float(pk[j] << 16);
+                        f[2 * j + 1] = __uint_as_float(pk[j] & 0xffff0000u);
+                    }
+                }
+            }
+            if (do_stats) {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    f[j] = valid ? f[j] : 0.f;
+                    g[j] = f[j] * f[j];
+                }
+                const float s1 = warp_colsum32(f, lane);
+                const float s2 = warp_colsum32(g, lane);
+                atomicAdd(&s_stat[c0 + lane], s1);
+                atomicAdd(&s_stat[BN + c0 + lane], s2);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (p.stat_sum != nullptr) {
+        for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+            atomicAdd(p.stat_sum + nt * BN + i, (double)s_stat[i]);
+            atomicAdd(p.stat_sq + nt * BN + i, (double)s_stat[BN + i]);
+        }
+    }
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: out[tap][m][n] += sum_pixels D[pixel][m] * S[pixel @ tap][n]
+// ------------------------------------------------------------------------------------------------
+struct WgParams {
+    CUtensorMap mapD;     // dense operand (C, X, Y, N) box (64, bw, bh, bn)
+    CUtensorMap mapS[4];  // shifted operand planes, box (NCH, bw, bh, bn)
+    TapDesc taps[25];
+    int num_taps;
+    int bw, bh, bn;
+    int tiles_x, tiles_y, tiles_n;  // pixel tiles (the reduction)
+    int m_total, n_total;
+    int m_tiles, n_tiles;
+    int splits;
+    int rows;  // bw*bh*bn, multiple of 16
+    float* out;
+};
+
+template <int BN, int NCH, int STAGES>
+struct WgSmem {
+    static constexpr int D_BYTES = 128 * 128 * 2;  // [2 chunks][128 pixels][64 ch]
+    static constexpr int S_BYTES = 128 * BN * 2;   // [BN/NCH chunks][128 pixels][NCH ch]
+    static constexpr int STAGE_BYTES = D_BYTES + S_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int NCH, int STAGES>
+__global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgParams p) {
+    using L = WgSmem<BN, NCH, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tap = blockIdx.x;
+    const int mtile = blockIdx.y % p.m_tiles;
+    const int ntile = blockIdx.y / p.m_tiles;
+    const int split = blockIdx.z;
+    const int pt_total = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int pt_begin = (int)((long long)split * pt_total / p.splits);
+    const int pt_end = (int)((long long)(split + 1) * pt_total / p.splits);
+    if (pt_begin >= pt_end) return;
+    const int npt = pt_end - pt_begin;
+    const TapDesc t = p.taps[tap];
+
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int D_CHUNKS = 2;
+    constexpr int S_CHUNKS = BN / NCH;
+    const uint32_t d_chunk_bytes = p.rows * 128;
+    const uint32_t s_chunk_bytes = p.rows * NCH * 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapD);
+        tma_prefetch_desc(&p.mapS[t.map]);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int d_chunks_live = (p.m_total - mtile * 128) >= 128 ? 2 : 1;
+            for (int i = 0; i < npt; ++i) {
+                const int st = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + S_CHUNKS * s_chunk_bytes);
+                const int pt = pt_begin + i;
+                const int tx = pt % p.tiles_x;
+                const int ty = (pt / p.tiles_x) % p.tiles_y;
+                const int tn = pt / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+                uint8_t* sd = smem + st * L::STAGE_BYTES;
+                uint8_t* ss = sd + L::D_BYTES;
+                for (int cchunk = 0; cchunk < d_chunks_live; ++cchunk)
+                    tma_load_4d(sd + cchunk * d_chunk_bytes, &p.mapD, &full_bar[st], mtile * 128 + cchunk * 64, x0,
+                                y0, n0);
+#pragma unroll
+                for (int cchunk = 0; cchunk < S_CHUNKS; ++cchunk)
+                    tma_load_4d(ss + cchunk * s_chunk_bytes, &p.mapS[t.map], &full_bar[st],
+                                ntile * BN + cchunk * NCH, x0 + t.dx, y0 + t.dy, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
+            constexpr uint64_t s_layout = (NCH == 64) ? UMMA_SW128 : UMMA_SW64;
+            constexpr uint32_t s_row = NCH * 2;
+            const int ksteps = p.rows / 16;
+            for (int i = 0; i < npt; ++i) {
+                const int st = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[st], ph);
+                tc_fence_after();
+                const uint32_t sd = smem_u32(smem + st * L::STAGE_BYTES);
+                const uint32_t ss = sd + L::D_BYTES;
+                // MN-major: LBO = distance between 64(32)-channel chunks, SBO = 8 pixel rows
+                const uint64_t adesc = umma_smem_desc(sd, d_chunk_bytes, 8 * 128, UMMA_SW128);
+                const uint64_t bdesc = umma_smem_desc(ss, s_chunk_bytes, 8 * s_row, s_layout);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(tmem_base, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc,
+                              (i | k) != 0);
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = mtile * 128 + q * 32 + lane;
+        const bool valid = m < p.m_total;
+        float* orow = p.out + ((long long)tap * p.m_total + m) * p.n_total + ntile * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    red_add_v4(orow + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace fmri

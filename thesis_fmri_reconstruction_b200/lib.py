@@ -1,0 +1,329 @@
+"""ctypes binding of libfmri_b200.so (C ABI in include/fmri_b200.h).
+
+The library is the product: there is no Python/CPU fallback. Loading fails loudly if the shared object is missing
+(run ``python -c "import __graft_entry__ as g; g.build()"``), and every wrapper raises ``FmriError`` on a non-zero
+status with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfmri_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fmri_b200.h")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+
+class FmriError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("N", "H", "W", "Cin", "Cout", "stride", "transposed", "output_pad", "dtype")]
+
+
+class EdgeDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("N", "H", "W", "C", "stride", "dtype")]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("M", "N", "K", "dtype")]
+
+
+def header_functions():
+    """Names of every function the public header declares (used by the CPU-side export test)."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fmri_[a-z0-9_]+)\s*\(", src)))
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FmriError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no fallback path."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _lib.fmri_last_error.restype = C.c_char_p
+        _lib.fmri_conv_wgrad_workspace.restype = C.c_size_t
+        _lib.fmri_edge_workspace.restype = C.c_size_t
+        _lib.fmri_conv_out_hw.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise FmriError(f"libfmri_b200 status {rc}: {load().fmri_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise FmriError(f"unsupported dtype {d}")
+
+
+def _ll(v):
+    return C.c_longlong(int(v))
+
+
+def _f(v):
+    return C.c_float(float(v))
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FmriError("libfmri_b200 operates on CUDA tensors only (no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise FmriError("libfmri_b200 expects contiguous tensors")
+
+
+# ------------------------------------------------------------------------------------------------ convs
+def conv_desc(N, H, W, Cin, Cout, stride, transposed, output_pad, dtype):
+    return ConvDesc(N, H, W, Cin, Cout, stride, int(transposed), int(output_pad), dt(dtype))
+
+
+def conv_out_hw(d):
+    oh, ow = C.c_int(), C.c_int()
+    load().fmri_conv_out_hw(C.byref(d), C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
+
+
+def conv_pack_weights(d, w, pack_f, pack_d):
+    _require_cuda(w, pack_f, pack_d)
+    _check(load().fmri_conv_pack_weights(C.byref(d), ptr(w), ptr(pack_f), ptr(pack_d), stream()))
+
+
+def conv_fprop(d, x, w, pack_f, bias, act, y, stat_sum=None, stat_sq=None):
+    _require_cuda(x, w, pack_f, bias, y, stat_sum, stat_sq)
+    _check(load().fmri_conv_fprop(C.byref(d), ptr(x), ptr(w), ptr(pack_f), ptr(bias), act, ptr(y), ptr(stat_sum),
+                                  ptr(stat_sq), stream()))
+
+
+def conv_dgrad(d, dy, w, pack_d, dx):
+    _require_cuda(dy, w, pack_d, dx)
+    _check(load().fmri_conv_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(pack_d), ptr(dx), stream()))
+
+
+def conv_wgrad_workspace(d):
+    return load().fmri_conv_wgrad_workspace(C.byref(d))
+
+
+def conv_wgrad(d, x, dy, dw, accumulate, ws):
+    _require_cuda(x, dy, dw, ws)
+    nbytes = ws.numel() * ws.element_size() if ws is not None else 0
+    _check(load().fmri_conv_wgrad(C.byref(d), ptr(x), ptr(dy), ptr(dw), int(accumulate), ptr(ws), C.c_size_t(nbytes),
+                                  stream()))
+
+
+def edge_desc(N, H, W, Cc, stride, dtype):
+    return EdgeDesc(N, H, W, Cc, stride, dt(dtype))
+
+
+def edge_workspace(d):
+    return load().fmri_edge_workspace(C.byref(d))
+
+
+def _wsb(ws):
+    return C.c_size_t(ws.numel() * ws.element_size())
+
+
+def edge_in_fprop(d, imgs, n_per_src, w, bias, act, y, ws):
+    i0, i1, i2 = (list(imgs) + [None, None])[:3]
+    _require_cuda(i0, i1, i2, w, bias, y, ws)
+    _check(load().fmri_edge_in_fprop(C.byref(d), ptr(i0), ptr(i1), ptr(i2), n_per_src, ptr(w), ptr(bias), act, ptr(y),
+                                     ptr(ws), _wsb(ws), stream()))
+
+
+def edge_in_dgrad(d, dy, w, dimg, ws):
+    _require_cuda(dy, w, dimg, ws)
+    _check(load().fmri_edge_in_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(dimg), ptr(ws), _wsb(ws), stream()))
+
+
+def edge_in_wgrad(d, imgs, n_per_src, dy, dw, accumulate, ws):
+    i0, i1, i2 = (list(imgs) + [None, None])[:3]
+    _require_cuda(i0, i1, i2, dy, dw, ws)
+    _check(load().fmri_edge_in_wgrad(C.byref(d), ptr(i0), ptr(i1), ptr(i2), n_per_src, ptr(dy), ptr(dw),
+                                     int(accumulate), ptr(ws), _wsb(ws), stream()))
+
+
+def edge_out_fprop(d, x, w, bias, act, img, ws):
+    _require_cuda(x, w, bias, img, ws)
+    _check(load().fmri_edge_out_fprop(C.byref(d), ptr(x), ptr(w), ptr(bias), act, ptr(img), ptr(ws), _wsb(ws),
+                                      stream()))
+
+
+def edge_out_dgrad(d, dimg, w, dx, ws):
+    _require_cuda(dimg, w, dx, ws)
+    _check(load().fmri_edge_out_dgrad(C.byref(d), ptr(dimg), ptr(w), ptr(dx), ptr(ws), _wsb(ws), stream()))
+
+
+def edge_out_wgrad(d, x, dimg, dw, accumulate, ws):
+    _require_cuda(x, dimg, dw, ws)
+    _check(load().fmri_edge_out_wgrad(C.byref(d), ptr(x), ptr(dimg), ptr(dw), int(accumulate), ptr(ws), _wsb(ws),
+                                      stream()))
+
+
+# ------------------------------------------------------------------------------------------------ linear
+def linear_desc(M, N, K, dtype):
+    return LinearDesc(M, N, K, dt(dtype))
+
+
+def linear_pack_weights(d, w, wp, ldw, wpt, ldwt):
+    _require_cuda(w, wp, wpt)
+    _check(load().fmri_linear_pack_weights(C.byref(d), ptr(w), ptr(wp), ldw, ptr(wpt), ldwt, stream()))
+
+
+def linear_fprop(d, x, ldx, w, wp, ldw, bias, act, y, ldy):
+    _require_cuda(x, w, wp, bias, y)
+    _check(load().fmri_linear_fprop(C.byref(d), ptr(x), ldx, ptr(w), ptr(wp), ldw, ptr(bias), act, ptr(y), ldy,
+                                    dt(y), stream()))
+
+
+def linear_dgrad(d, dy, lddy, w, wpt, ldwt, dx, lddx):
+    _require_cuda(dy, w, wpt, dx)
+    _check(load().fmri_linear_dgrad(C.byref(d), ptr(dy), lddy, ptr(w), ptr(wpt), ldwt, ptr(dx), lddx, dt(dx),
+                                    stream()))
+
+
+def linear_wgrad(d, x, ldx, dy, lddy, dw, accumulate):
+    _require_cuda(x, dy, dw)
+    _check(load().fmri_linear_wgrad(C.byref(d), ptr(x), ldx, ptr(dy), lddy, ptr(dw), int(accumulate), stream()))
+
+
+# ------------------------------------------------------------------------------------------------ BN / elementwise
+def colstats(x, rows, Cc, s, q):
+    _require_cuda(x, s, q)
+    _check(load().fmri_colstats(ptr(x), dt(x), _ll(rows), Cc, ptr(s), ptr(q), stream()))
+
+
+def bn_finalize(s, q, rows, Cc, eps, momentum, mean, invstd, running_mean, running_var):
+    _check(load().fmri_bn_finalize(ptr(s), ptr(q), _ll(rows), Cc, _f(eps), _f(momentum), ptr(mean), ptr(invstd),
+                                   ptr(running_mean), ptr(running_var), stream()))
+
+
+def bn_apply(x, y, rows, Cc, mean, invstd, gamma, beta, relu):
+    _require_cuda(x, y, mean, invstd, gamma, beta)
+    _check(load().fmri_bn_apply(ptr(x), dt(x), ptr(y), dt(y), _ll(rows), Cc, ptr(mean), ptr(invstd), ptr(gamma),
+                                ptr(beta), int(relu), stream()))
+
+
+def bn_backward(x, dy, dx, rows, Cc, mean, invstd, gamma, beta, relu, train, dgamma, dbeta, accumulate, ws):
+    _require_cuda(x, dy, dx, mean, invstd, gamma, beta, dgamma, dbeta, ws)
+    _check(load().fmri_bn_backward(ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), _ll(rows), Cc, ptr(mean), ptr(invstd),
+                                   ptr(gamma), ptr(beta), int(relu), int(train), ptr(dgamma), ptr(dbeta),
+                                   int(accumulate), ptr(ws), stream()))
+
+
+def relu_backward(y, dy, dx):
+    _require_cuda(y, dy, dx)
+    _check(load().fmri_relu_backward(ptr(y), ptr(dy), ptr(dx), dt(y), _ll(y.numel()), stream()))
+
+
+def colsum(x, rows, Cc, out):
+    _require_cuda(x, out)
+    _check(load().fmri_colsum(ptr(x), dt(x), _ll(rows), Cc, ptr(out), stream()))
+
+
+def nchw_to_nhwc(src, dst, N, Cc, H, W):
+    _require_cuda(src, dst)
+    _check(load().fmri_nchw_to_nhwc(ptr(src), dt(src), ptr(dst), dt(dst), N, Cc, H, W, stream()))
+
+
+def nhwc_to_nchw(src, dst, N, Cc, H, W, accumulate=False):
+    _require_cuda(src, dst)
+    _check(load().fmri_nhwc_to_nchw(ptr(src), dt(src), ptr(dst), dt(dst), N, Cc, H, W, int(accumulate), stream()))
+
+
+def cast2d(src, lds, dst, ldd, rows, cols):
+    _require_cuda(src, dst)
+    _check(load().fmri_cast2d(ptr(src), dt(src), lds, ptr(dst), dt(dst), ldd, _ll(rows), cols, stream()))
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def reparam_kl_fwd(mu, logvar, eps, z, kl, B, Z):
+    _require_cuda(mu, logvar, eps, z, kl)
+    _check(load().fmri_reparam_kl_fwd(ptr(mu), ptr(logvar), ptr(eps), ptr(z), ptr(kl), B, Z, stream()))
+
+
+def reparam_kl_bwd(mu, logvar, eps, gz, gkl, dmu, dlv, B, Z):
+    _require_cuda(mu, logvar, eps, gz, gkl, dmu, dlv)
+    _check(load().fmri_reparam_kl_bwd(ptr(mu), ptr(logvar), ptr(eps), ptr(gz), ptr(gkl), ptr(dmu), ptr(dlv), B, Z,
+                                      stream()))
+
+
+def rowsqdiff_fwd(a, b, out, rows, F, scale):
+    _require_cuda(a, b, out)
+    _check(load().fmri_rowsqdiff_fwd(ptr(a), ptr(b), dt(a), ptr(out), _ll(rows), _ll(F), _f(scale), stream()))
+
+
+def rowsqdiff_bwd(a, b, g, da, db, rows, F, scale):
+    _require_cuda(a, b, g, da, db)
+    _check(load().fmri_rowsqdiff_bwd(ptr(a), ptr(b), dt(a), ptr(g), ptr(da), ptr(db), _ll(rows), _ll(F), _f(scale),
+                                     stream()))
+
+
+def head_sigmoid_fwd(x, w, bias, p, rows, F):
+    _require_cuda(x, w, bias, p)
+    _check(load().fmri_head_sigmoid_fwd(ptr(x), dt(x), ptr(w), ptr(bias), ptr(p), rows, F, stream()))
+
+
+def head_sigmoid_bwd(x, w, p, gp, dx, dw, db, rows, F):
+    _require_cuda(x, w, p, gp, dx, dw, db)
+    _check(load().fmri_head_sigmoid_bwd(ptr(x), dt(x), ptr(w), ptr(p), ptr(gp), ptr(dx), ptr(dw), ptr(db), rows, F,
+                                        stream()))
+
+
+def bce_fwd(p, out, n, positive, scale):
+    _check(load().fmri_bce_fwd(ptr(p), ptr(out), n, int(positive), _f(scale), stream()))
+
+
+def bce_bwd(p, g, dp, n, positive, scale, accumulate=False):
+    _check(load().fmri_bce_bwd(ptr(p), ptr(g), ptr(dp), n, int(positive), _f(scale), int(accumulate), stream()))
+
+
+# ------------------------------------------------------------------------------------------------ optimizers
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def multi_tensor_rmsprop(params, grads, sqs, lr, alpha, eps, clamp=0.0):
+    n = len(params)
+    numel = (C.c_int64 * n)(*[p.numel() for p in params])
+    _check(load().fmri_multi_tensor_rmsprop(n, _ptr_array(params), _ptr_array(grads), _ptr_array(sqs), numel, _f(lr),
+                                            _f(alpha), _f(eps), _f(clamp), stream()))
+
+
+def multi_tensor_adam(params, grads, ms, vs, lr, beta1, beta2, eps, step, clamp=0.0):
+    n = len(params)
+    numel = (C.c_int64 * n)(*[p.numel() for p in params])
+    _check(load().fmri_multi_tensor_adam(n, _ptr_array(params), _ptr_array(grads), _ptr_array(ms), _ptr_array(vs),
+                                         numel, _f(lr), _f(beta1), _f(beta2), _f(eps), int(step), _f(clamp), stream()))
