@@ -1,0 +1,200 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules (TEST INFRASTRUCTURE ONLY).
+
+Run in the build container only:   python oracle/make_golden.py      (needs /root/reference; ~1 min on 8 cores)
+
+What runs on the reference side (imported from /root/reference, nothing copied):
+  * models.vae_gan.VaeGan / WaeGan built under the 64x64 configuration (configs/models_config.py:23-31 + :9),
+    .double(), weights loaded with load_state_dict from oracle.vaegan.make_vaegan / make_waegan (deterministic);
+  * VaeGan.forward (train) + VaeGan.loss + the loss mix, gate and backward order of train/train_vgan_stage1.py:330-432,
+    with torch.optim.RMSprop(alpha=0.9, eps=1e-8); the three optimizer steps are applied after the three backward sweeps
+    (equivalent under the torch-1.4 semantics the script was written for; torch >= 1.5 raises on the
+    interleaved order);
+  * train/train_wae_stage1.py:263-311 verbatim order (D-phase, Adam step, G-phase, Adam steps) with torch.optim.Adam.
+Noise (eps, z_p, z_fake) is injected by patching VaeGan.reparameterize / torch.randn for the duration of the call.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import vaegan as O  # noqa: E402
+from oracle.golden_util import summarize, summarize_dict  # noqa: E402
+
+
+def import_reference():
+    saved = list(sys.path)
+    sys.path[:] = [REF] + [q for q in sys.path if os.path.abspath(q or ".") != ROOT]  # reference's models/ is a namespace pkg
+    for m in [k for k in sys.modules if k == "configs" or k.startswith("configs.") or k == "models"
+              or k.startswith("models.")]:
+        del sys.modules[m]
+    import configs.models_config as mc
+
+    assert mc.__file__.startswith(REF), mc.__file__
+    mc.image_size = 64; mc.fc_input = 8; mc.fc_output = 1024; mc.fc_input_gan = 8; mc.fc_output_gan = 512
+    mc.stride_gan = 1; mc.latent_dim = 128; mc.output_pad_dec = [True, True, True]
+    mc.decoder_channels = [256, 128, 32, 3]
+    import models.vae_gan as ref
+
+    assert ref.__file__.startswith(REF), ref.__file__
+    sys.path[:] = saved
+    return ref
+
+
+@contextmanager
+def patched_randn(value):
+    orig = torch.randn
+
+    def fake(*a, **k):
+        return value.clone()
+
+    torch.randn = fake
+    try:
+        yield
+    finally:
+        torch.randn = orig
+
+
+def load(model, P, S):
+    sd = {**P, **S}
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+def buffers_of(model):
+    return {k: v for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
+
+
+def golden_stage1_vaegan(ref, B, seed):
+    torch.manual_seed(0)
+    P, S = O.make_vaegan(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    model = ref.VaeGan(device="cpu", z_size=128).double()
+    load(model, P, S)
+    model.train()
+    model.reparameterize = lambda mu, logvar: eps * torch.exp(0.5 * logvar) + mu  # models/vae_gan.py:266-269, eps injected
+    hp = O.HP_VGAN
+    opts = {b: torch.optim.RMSprop(getattr(model, b).parameters(), lr=hp["lr"], alpha=0.9, eps=1e-8, weight_decay=0,
+                                   momentum=0, centered=False) for b in ("encoder", "decoder", "discriminator")}
+    with patched_randn(z_p):
+        x_tilde, disc_class, disc_layer, mus, lv = model(x)                       # train_vgan_stage1.py:330
+    dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]          # :333-335
+    dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]          # :337-339
+    nle, kld, mse, bo, bp, bs = ref.VaeGan.loss(x, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)  # :342
+    loss_encoder = torch.sum(kld) + torch.sum(mse)                                # :369
+    loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)            # :370
+    loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator  # :372
+    train_dis, train_dec = True, True
+    if torch.mean(bo).item() < hp["equilibrium"] - hp["margin"] or torch.mean(bp).item() < hp["equilibrium"] - hp["margin"]:
+        train_dis = False
+    if torch.mean(bo).item() > hp["equilibrium"] + hp["margin"] or torch.mean(bp).item() > hp["equilibrium"] + hp["margin"]:
+        train_dec = False
+    if train_dec is False and train_dis is False:
+        train_dis = True
+        train_dec = True
+    grads = {}
+    model.zero_grad()                                                             # :408
+    loss_encoder.backward(retain_graph=True)                                      # :412
+    grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters()})
+    model.zero_grad()                                                             # :418
+    loss_decoder.backward(retain_graph=True)                                      # :422
+    grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+    model.discriminator.zero_grad()                                               # :426
+    loss_discriminator.backward()                                                 # :430
+    grads.update({"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()})
+    for b, on in (("encoder", True), ("decoder", train_dec), ("discriminator", train_dis)):
+        if not on:
+            continue
+        for k, p in getattr(model, b).named_parameters():
+            p.grad = grads[b + "." + k].clone()
+        opts[b].step()
+    newP = {k: v.detach() for k, v in model.named_parameters()}
+    delta = {k: newP[k] - P[k] for k in P}
+    fx = dict(B=np.array(B), seed=np.array(seed), train_dis=np.array(train_dis), train_dec=np.array(train_dec),
+              mu=mus.detach().numpy(), logvar=lv.detach().numpy(), kl=kld.detach().numpy(), mse=mse.detach().numpy(),
+              bce_o=bo.detach().numpy(), bce_p=bp.detach().numpy(), bce_s=bs.detach().numpy(),
+              disc_class=disc_class.detach().numpy(), nle_sum=nle.sum().detach().numpy(),
+              loss_encoder=loss_encoder.detach().numpy(), loss_decoder=loss_decoder.detach().numpy(),
+              loss_discriminator=loss_discriminator.detach().numpy(),
+              x_tilde=summarize(x_tilde), disc_layer=summarize(disc_layer))
+    fx.update(summarize_dict(grads, "grad:"))
+    fx.update(summarize_dict(delta, "delta:"))
+    fx.update(summarize_dict({k: v for k, v in buffers_of(model).items()}, "buf:"))
+    return fx
+
+
+def golden_stage1_waegan(ref, B, seed):
+    torch.manual_seed(0)
+    P, S = O.make_waegan(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    z_fake = (O.synthetic_noise(B, 128, seed=seed)[0] * 0.5).double()
+    model = ref.WaeGan(device="cpu", z_size=128).double()
+    load(model, P, S)
+    model.train()
+    hp = O.HP_WAE
+    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=hp["lr"], betas=(0.5, 0.999))           # wae1 :221
+    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=hp["lr"], betas=(0.5, 0.999))           # :222
+    opt_c = torch.optim.Adam(model.discriminator.parameters(), lr=0.5 * hp["lr"], betas=(0.5, 0.999))  # :223-224
+
+    def freeze(m, on):
+        for p in m.parameters():
+            p.requires_grad = not on
+
+    model.encoder.zero_grad(); model.decoder.zero_grad(); model.discriminator.zero_grad()   # :263-265
+    freeze(model.decoder, True); freeze(model.encoder, True); freeze(model.discriminator, False)  # :271-273
+    z_real, _ = model.encoder(x)                                                  # :275
+    d_real = model.discriminator(z_real)                                          # :278
+    d_fake = model.discriminator(z_fake)                                          # :279
+    loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))                         # :281
+    loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))                     # :282
+    loss_fake.backward(retain_graph=True)                                         # :283
+    loss_real.backward(retain_graph=True)                                         # :284
+    grads = {"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()}
+    opt_c.step()                                                                  # :288
+    freeze(model.encoder, False); freeze(model.decoder, False); freeze(model.discriminator, True)  # :292-294
+    z_real2, _ = model.encoder(x)                                                 # :296
+    x_recon = model.decoder(z_real2)                                              # :297
+    d_real2 = model.discriminator(z_real2)                                        # :298
+    loss_rec = torch.sum(torch.sum(0.5 * (x_recon - x) ** 2, 1))                  # :301
+    loss_pen = -10 * torch.sum(torch.log(d_real2 + 1e-3))                         # :303
+    loss_rec.backward(retain_graph=True)                                          # :306
+    loss_pen.backward()                                                           # :307
+    # l_var gets no gradient (the WAE ignores logvar): p.grad stays None and Adam skips it
+    grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters() if p.grad is not None})
+    grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+    opt_e.step()                                                                  # :310
+    opt_d.step()                                                                  # :311
+    newP = {k: v.detach() for k, v in model.named_parameters()}
+    delta = {k: newP[k] - P[k] for k in P}
+    fx = dict(B=np.array(B), seed=np.array(seed), z_real=z_real.detach().numpy(), d_real=d_real.detach().numpy(),
+              d_fake=d_fake.detach().numpy(), d_real_g=d_real2.detach().numpy(),
+              loss_discriminator_fake=loss_fake.detach().numpy(), loss_discriminator_real=loss_real.detach().numpy(),
+              loss_reconstruction=loss_rec.detach().numpy(), loss_penalty=loss_pen.detach().numpy(),
+              x_recon=summarize(x_recon))
+    fx.update(summarize_dict(grads, "grad:"))
+    fx.update(summarize_dict(delta, "delta:"))
+    fx.update(summarize_dict(buffers_of(model), "buf:"))
+    return fx
+
+
+def main():
+    ref = import_reference()
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    for B, seed in ((4, 12345), (6, 777)):
+        np.savez_compressed(os.path.join(out, f"stage1_vaegan_B{B}_s{seed}.npz"), **golden_stage1_vaegan(ref, B, seed))
+        np.savez_compressed(os.path.join(out, f"stage1_waegan_B{B}_s{seed}.npz"), **golden_stage1_waegan(ref, B, seed))
+        print("wrote goldens for", B, seed)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""The CPU oracle (oracle/vaegan.py) against fixtures produced by the UNMODIFIED reference modules
+(tests/golden/*.npz, written by oracle/make_golden.py in the build container).
+
+Tolerances: the fixtures are fp64 runs of the reference; the oracle in fp64 must agree to 1e-9 relative (same
+arithmetic, different operator grouping only); in fp32 the forward tensors / losses must agree to 1e-4 (the fp32 noise
+floor of the reference itself is ~1e-6 forward, ~1e-3 on end-to-end gradients through ReLU-mask flips).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vaegan as O
+from oracle.golden_util import summarize, summary_error
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _cases(kind):
+    fs = sorted(glob.glob(os.path.join(GOLD, f"{kind}_B*_s*.npz")))
+    assert fs, f"no golden fixtures for {kind}"
+    return fs
+
+
+@pytest.mark.parametrize("path", _cases("stage1_vaegan"))
+def test_stage1_vaegan_fp64_matches_reference(path):
+    g = np.load(path)
+    B, seed = int(g["B"]), int(g["seed"])
+    P, S = O.make_vaegan(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    out = O.stage1_vaegan_step(P, S, x, eps, z_p)
+    assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
+    for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder", "loss_decoder",
+              "loss_discriminator"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-9, k
+    assert _rel(out["nle"].sum().numpy(), g["nle_sum"]) < 1e-9
+    assert summary_error(summarize(out["x_tilde"]), g["x_tilde"]) < 1e-9
+    assert summary_error(summarize(out["disc_layer"]), g["disc_layer"]) < 1e-9
+    n = 0
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert summary_error(summarize(out["grads"][k[5:]]), g[k]) < 1e-8, k
+            n += 1
+        elif k.startswith("delta:"):
+            name = k[6:]
+            assert summary_error(summarize(out["params"][name] - P[name]), g[k]) < 1e-6, k
+        elif k.startswith("buf:"):
+            assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
+    assert n == len(P)
+
+
+@pytest.mark.parametrize("path", _cases("stage1_vaegan")[:1])
+def test_stage1_vaegan_fp32_forward_close(path):
+    g = np.load(path)
+    B, seed = int(g["B"]), int(g["seed"])
+    P, S = O.make_vaegan(O.CFG64, seed=seed, dtype=torch.float32)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    out = O.stage1_vaegan_step(P, S, x, eps, z_p, update=False)
+    for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder",
+              "loss_discriminator"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("path", _cases("stage1_waegan"))
+def test_stage1_waegan_fp64_matches_reference(path):
+    g = np.load(path)
+    B, seed = int(g["B"]), int(g["seed"])
+    P, S = O.make_waegan(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    z_fake = (O.synthetic_noise(B, 128, seed=seed)[0] * 0.5).double()
+    out = O.stage1_waegan_step(P, S, x, z_fake)
+    for k in ("z_real", "d_real", "d_fake", "d_real_g", "loss_discriminator_fake", "loss_discriminator_real",
+              "loss_reconstruction", "loss_penalty"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-9, k
+    assert summary_error(summarize(out["x_recon"]), g["x_recon"]) < 1e-9
+    n = 0
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert summary_error(summarize(out["grads"][k[5:]]), g[k]) < 1e-8, k
+            n += 1
+        elif k.startswith("delta:"):
+            name = k[6:]
+            assert summary_error(summarize(out["params"][name] - P[name]), g[k]) < 1e-6, k
+        elif k.startswith("buf:"):
+            assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
+    assert n == len(out["grads"]) == len(P) - 2  # l_var.{weight,bias} receive no gradient in the WAE
+
+
+def test_gate_table():
+    # train/train_vgan_stage1.py:396-404
+    assert O.gate(0.5, 0.7) == (True, True)
+    assert O.gate(0.2, 0.7) == (False, True)
+    assert O.gate(0.5, 1.2) == (True, False)
+    assert O.gate(0.2, 1.2) == (True, True)
+
+
+def test_optimizer_restatements_match_torch_optim():
+    g0 = torch.Generator().manual_seed(3)
+    p0 = torch.randn(1000, generator=g0, dtype=torch.float64)
+    grads = [torch.randn(1000, generator=g0, dtype=torch.float64) for _ in range(3)]
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.RMSprop([p], lr=1e-3, alpha=0.9, eps=1e-8)
+    q, sq = p0.clone(), torch.zeros_like(p0)
+    for g in grads:
+        p.grad = g.clone()
+        opt.step()
+        q, sq = O.rmsprop_update(q, g, sq, 1e-3)
+    assert _rel(q.numpy(), p.detach().numpy()) < 1e-12
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.5, 0.999))
+    q, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for t, g in enumerate(grads, 1):
+        p.grad = g.clone()
+        opt.step()
+        q, m, v = O.adam_update(q, g, m, v, t, 1e-3)
+    assert _rel(q.numpy(), p.detach().numpy()) < 1e-12
