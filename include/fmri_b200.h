@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FMRI_ABI_VERSION 1
+#define FMRI_ABI_VERSION 2
 
 typedef enum { FMRI_OK = 0, FMRI_ERR_ARG = -1, FMRI_ERR_UNSUPPORTED = -2, FMRI_ERR_CUDA = -3, FMRI_ERR_WORKSPACE = -4 } fmri_status;
 typedef enum { FMRI_F32 = 0, FMRI_BF16 = 1 } fmri_dtype;
@@ -105,12 +105,14 @@ typedef struct {
     int M, N, K;
     int dtype;
 } fmri_linear_desc;
+/* Padding columns (ldw > K, ldwt > N) are never written: zero-initialise a padded buffer once. Several layers may
+ * share one pitched buffer (the l_mu / l_var heads are packed side by side, vae_gan.py:84-85). */
 int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* w, void* wp, int ldw, void* wpt, int ldwt,
                              void* stream);
 int fmri_linear_fprop(const fmri_linear_desc* d, const void* x, int ldx, const float* w, const void* wp, int ldw,
                       const float* bias, int act, void* y, int ldy, int y_dtype, void* stream);
 int fmri_linear_dgrad(const fmri_linear_desc* d, const void* dy, int lddy, const float* w, const void* wpt, int ldwt,
-                      void* dx, int lddx, int dx_dtype, void* stream);
+                      void* dx, int lddx, int dx_dtype, int accumulate /* fp32 dx only */, void* stream);
 int fmri_linear_wgrad(const fmri_linear_desc* d, const void* x, int ldx, const void* dy, int lddy, float* dw,
                       int accumulate, void* stream);
 
@@ -142,10 +144,14 @@ int fmri_cast2d(const void* src, int src_dtype, int lds, void* dst, int dst_dtyp
 /* ---------------------------------------------------------------------------------------------------------
  * Losses. vae_gan.py:266-269 (reparameterize), :302-320 (VaeGan.loss), train_wae_stage1.py:281-282,301-303
  * --------------------------------------------------------------------------------------------------------- */
-int fmri_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, float* z /*nullable*/,
+/* mu / logvar have row pitch `ld` floats (the two halves of one [B, 2Z] head output); z, eps, kl dense. */
+int fmri_reparam_kl_fwd(const float* mu, const float* logvar, int ld, const float* eps, float* z /*nullable*/,
                         float* kl /*nullable*/, int B, int Z, void* stream);
-int fmri_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* gz /*nullable*/,
-                        const float* gkl /*nullable*/, float* dmu, float* dlogvar, int B, int Z, void* stream);
+/* dmu / dlogvar (d_dtype, row pitch ldd) from gz = dL/dz (nullable) and dL/dkl = gkl[b] (or the constant gkl_const
+ * when gkl is NULL: the reference sums kl over the batch, train_vgan_stage1.py:369). */
+int fmri_reparam_kl_bwd(const float* mu, const float* logvar, int ld, const float* eps, const float* gz /*nullable*/,
+                        const float* gkl /*nullable*/, float gkl_const, void* dmu, void* dlogvar, int ldd, int d_dtype,
+                        int B, int Z, void* stream);
 /* out[b] = scale * sum_j (a[b,j]-b[b,j])^2   (feature-matching MSE scale=.5 over 16384 features; NLE / WAE recon) */
 int fmri_rowsqdiff_fwd(const void* a, const void* b, int dtype, float* out, long long rows, long long F, float scale,
                        void* stream);
@@ -166,11 +172,32 @@ int fmri_bce_bwd(const float* p, const float* g, float* dp, int n, int positive,
  * train_vgan_stage1.py:275-283 (RMSprop alpha=.9 eps=1e-8), train_wae_stage1.py:221-224 (Adam betas=(.5,.999)),
  * clamp>0 folds the `p.grad.data.clamp_(-1,1)` of train_vgan_stage2.py:391,406.
  * --------------------------------------------------------------------------------------------------------- */
+/* lr_dev (nullable) overrides lr from device memory; gate_dev (nullable): the update is skipped when *gate_dev == 0
+ * (the equilibrium gate of train_vgan_stage1.py:396-404 decided on the device by fmri_vgan_gate). */
 int fmri_multi_tensor_rmsprop(int n, float* const* p, const float* const* g, float* const* sq, const int64_t* numel,
-                              float lr, float alpha, float eps, float clamp, void* stream);
+                              float lr, float alpha, float eps, float clamp, const float* lr_dev,
+                              const float* gate_dev, void* stream);
 int fmri_multi_tensor_adam(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                            const int64_t* numel, float lr, float beta1, float beta2, float eps, int step, float clamp,
-                           void* stream);
+                           const float* lr_dev, const float* gate_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Glue of the fused training step (no reference counterpart as separate ops: autograd does these implicitly)
+ * --------------------------------------------------------------------------------------------------------- */
+/* out = (a*x + b*y) * (img ? 1 - img^2 : 1): mixes two image gradients (loss_decoder = lambda*mse - (1-lambda)*loss_dis,
+ * train_vgan_stage1.py:372) and applies the tanh backward of Decoder.conv[3] (vae_gan.py:120). y, img nullable. */
+int fmri_axpby_tanh_bwd(float a, const float* x, float b, const float* y, const float* img, float* out, long long n,
+                        void* stream);
+/* out[c] (+)= sum over n, hw of x[n,c,hw]  (bias gradient of Decoder.conv[3], NCHW fp32) */
+int fmri_chansum_nchw(const float* x, int N, int C, long long HW, float* out, int accumulate, void* stream);
+/* out[0] (+)= scale * sum x[0..n)  (the torch.sum of per-sample losses, train_vgan_stage1.py:369-372) */
+int fmri_vecsum(const float* x, long long n, float scale, float* out, int accumulate, void* stream);
+/* gates[0] = train_dis, gates[1] = train_dec (0.f / 1.f) from sums[0] = sum bce_original, sums[1] = sum bce_predicted
+ * over `count` samples (train_vgan_stage1.py:396-404) */
+int fmri_vgan_gate(const float* sums, float count, float margin, float equilibrium, float* gates, void* stream);
+/* eval-mode BatchNorm statistics: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int fmri_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                       float* invstd, void* stream);
 
 #ifdef __cplusplus
 }

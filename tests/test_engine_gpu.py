@@ -1,0 +1,90 @@
+"""Whole-step parity of the fused Stage-I VAE/GAN engine (CUDA kernels behind the C ABI) against the CPU oracle on the
+same seeded inputs and weights.
+
+Tolerances (rel-L2 per tensor, vs the fp32 oracle on CPU):
+  fp32 exact path : forward tensors / losses 1e-4; gradient buckets 5e-3 (the reference's own fp32 noise on end-to-end
+                    gradients is 1e-3..2e-3 through single ReLU-mask flips); BN buffers 1e-4.
+  bf16 tensor path: forward tensors / losses 2e-2 (north_star); end-to-end gradient buckets are REPORTED and bounded
+                    loosely (0.5) because thousands of ReLU masks flip under bf16 rounding -- CPU bf16 autocast of the
+                    reference itself shows 6e-2 .. 2.4e-1.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vaegan as O
+from thesis_fmri_reconstruction_b200 import engine, hp
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def nchw_flat(raw_nhwc):
+    return raw_nhwc.float().permute(0, 3, 1, 2).reshape(raw_nhwc.shape[0], -1)
+
+
+def run_case(B, adt, seed=4242):
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_vaegan_step(P, S_ref, x, eps, z_p)
+    tr = engine.VaeGanStage1(P, S, hp.CFG64, 128, adt)
+    out = tr.forward_backward(x.cuda(), eps.cuda(), z_p.cuda())
+    grads = {k: v.clone() for k, v in tr.named_grads().items()}
+    tr.update(B)
+    torch.cuda.synchronize()
+    errs = {}
+    errs["mu"] = rel(out["mu"], ref["mu"])
+    errs["logvar"] = rel(out["logvar"], ref["logvar"])
+    errs["x_tilde"] = rel(out["x_tilde"], ref["x_tilde"])
+    errs["disc_layer"] = rel(nchw_flat(out["disc_layer_nhwc"]), ref["disc_layer"])
+    errs["disc_class"] = rel(out["disc_class"], ref["disc_class"].reshape(-1))
+    errs["kl"] = rel(out["kl"], ref["kl"])
+    errs["mse"] = rel(out["mse"], ref["mse"])
+    errs["bce"] = rel(out["bce"], torch.cat([ref["bce_o"], ref["bce_p"], ref["bce_s"]]).reshape(-1))
+    lo = tr.losses()
+    for k in ("loss_encoder", "loss_decoder", "loss_discriminator"):
+        errs[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    gate_ok = (lo["train_dis"], lo["train_dec"]) == (ref["train_dis"], ref["train_dec"])
+    gerr = {}
+    for b in ("encoder.", "decoder.", "discriminator."):
+        a = torch.cat([grads[k].reshape(-1) for k in grads if k.startswith(b)])
+        r = torch.cat([ref["grads"][k].reshape(-1) for k in grads if k.startswith(b)])
+        gerr[b] = rel(a, r)
+    gten = {k: rel(grads[k], ref["grads"][k]) for k in grads}
+    newP = tr.named_parameters()
+    derr = {}
+    for b in ("encoder.", "decoder.", "discriminator."):
+        a = torch.cat([(newP[k].cpu() - P[k]).reshape(-1) for k in newP if k.startswith(b)])
+        r = torch.cat([(ref["params"][k] - P[k]).reshape(-1) for k in newP if k.startswith(b)])
+        derr[b] = rel(a, r)
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
+    rep = dict(B=B, dtype=str(adt), forward=errs, grad_bucket=gerr, grad_tensor_worst=max(gten.items(), key=lambda t: t[1]),
+               delta_bucket=derr, bn_worst=max(berr.items(), key=lambda t: t[1]), gate_ok=gate_ok, nbt_ok=nbt_ok)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/parity_stage1_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+def test_stage1_vaegan_fp32_exact_path():
+    rep = run_case(4, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert rep["bn_worst"][1] < 1e-4 and rep["gate_ok"] and rep["nbt_ok"]
+
+
+def test_stage1_vaegan_bf16_tensor_path():
+    rep = run_case(16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["bn_worst"][1] < 2e-2 and rep["gate_ok"] and rep["nbt_ok"]

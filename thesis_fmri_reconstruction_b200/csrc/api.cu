@@ -763,13 +763,11 @@ extern "C" int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* 
     if (!d || d->M < 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
     if (wp) {
         if (ldw < d->K) return fail(FMRI_ERR_ARG, "ldw < K");
-        if (ldw > d->K) CUDA_OK(cudaMemsetAsync(wp, 0, (size_t)d->N * ldw * 2, S(stream)));
         int rc = fmri_cast2d(w, FMRI_F32, d->K, wp, FMRI_BF16, ldw, d->N, d->K, stream);
         if (rc) return rc;
     }
     if (wpt) {  // [K][N]
         if (ldwt < d->N) return fail(FMRI_ERR_ARG, "ldwt < N");
-        if (ldwt > d->N) CUDA_OK(cudaMemsetAsync(wpt, 0, (size_t)d->K * ldwt * 2, S(stream)));
         // dst[k][n] (pitch ldwt) = w[n][k]
         scatter4_kernel<float, __nv_bfloat16><<<grid1d((long long)d->N * d->K, 256), 256, 0, S(stream)>>>(
             w, reinterpret_cast<__nv_bfloat16*>(wpt), 1, 1, d->N, d->K, 0, 0, 1, ldwt, 0);
@@ -811,24 +809,25 @@ extern "C" int fmri_linear_fprop(const fmri_linear_desc* d, const void* x, int l
 }
 
 extern "C" int fmri_linear_dgrad(const fmri_linear_desc* d, const void* dy, int lddy, const float* w, const void* wpt,
-                                 int ldwt, void* dx, int lddx, int dx_dtype, void* stream) {
+                                 int ldwt, void* dx, int lddx, int dx_dtype, int accumulate, void* stream) {
     if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
+    if (accumulate && dx_dtype != FMRI_F32) return fail(FMRI_ERR_ARG, "accumulating dgrad needs an fp32 dx");
     if (d->dtype == FMRI_BF16) {
         if (!wpt) return fail(FMRI_ERR_ARG, "bf16 linear dgrad needs the transposed pack");
         if (d->K % 32 == 0 && d->N % 8 == 0)  // dx[M,K] = dy[M,N] * wpt[K,N]^T
-            return run_gemm_tn(dy, lddy, wpt, ldwt, d->M, d->K, d->N, nullptr, 0, dx, lddx, dx_dtype == FMRI_F32, 0,
-                               S(stream));
+            return run_gemm_tn(dy, lddy, wpt, ldwt, d->M, d->K, d->N, nullptr, 0, dx, lddx, dx_dtype == FMRI_F32,
+                               accumulate, S(stream));
         if (dx_dtype == FMRI_F32)
             return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, 1,
                              reinterpret_cast<const __nv_bfloat16*>(wpt), ldwt, 1, reinterpret_cast<float*>(dx), lddx,
-                             1, nullptr, d->M, d->K, d->N, 0, 0, S(stream));
+                             1, nullptr, d->M, d->K, d->N, 0, accumulate, S(stream));
         return simt_gemm(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, 1,
                          reinterpret_cast<const __nv_bfloat16*>(wpt), ldwt, 1, reinterpret_cast<__nv_bfloat16*>(dx),
                          lddx, 1, nullptr, d->M, d->K, d->N, 0, 0, S(stream));
     }
     // dx[m,k] = sum_n dy[m,n] w[n,k] : "B" = w viewed as [K rows (stride 1)] x [N (stride K)]
     return simt_gemm(reinterpret_cast<const float*>(dy), lddy, 1, w, 1, d->K, reinterpret_cast<float*>(dx), lddx, 1,
-                     nullptr, d->M, d->K, d->N, 0, 0, S(stream));
+                     nullptr, d->M, d->K, d->N, 0, accumulate, S(stream));
 }
 
 extern "C" int fmri_linear_wgrad(const fmri_linear_desc* d, const void* x, int ldx, const void* dy, int lddy,
@@ -1054,17 +1053,27 @@ extern "C" int fmri_cast2d(const void* src, int src_dtype, int lds, void* dst, i
 }
 
 // ================================================================================================ losses
-extern "C" int fmri_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl, int B,
-                                   int Z, void* stream) {
+extern "C" int fmri_reparam_kl_fwd(const float* mu, const float* logvar, int ld, const float* eps, float* z, float* kl,
+                                   int B, int Z, void* stream) {
     if (z && !eps) return fail(FMRI_ERR_ARG, "reparam needs eps");
-    reparam_kl_fwd_kernel<<<cdiv(B, 4), 128, 0, S(stream)>>>(mu, logvar, eps, z, kl, B, Z);
+    if (ld < Z) return fail(FMRI_ERR_ARG, "reparam pitch < Z");
+    reparam_kl_fwd_kernel<<<cdiv(B, 4), 128, 0, S(stream)>>>(mu, logvar, ld, eps, z, kl, B, Z);
     LAUNCH_OK();
     return 0;
 }
-extern "C" int fmri_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* gz,
-                                   const float* gkl, float* dmu, float* dlogvar, int B, int Z, void* stream) {
-    reparam_kl_bwd_kernel<<<grid1d((long long)B * Z, 256), 256, 0, S(stream)>>>(mu, logvar, eps, gz, gkl, dmu, dlogvar,
-                                                                               B, Z);
+extern "C" int fmri_reparam_kl_bwd(const float* mu, const float* logvar, int ld, const float* eps, const float* gz,
+                                   const float* gkl, float gkl_const, void* dmu, void* dlogvar, int ldd, int d_dtype,
+                                   int B, int Z, void* stream) {
+    if (ld < Z || ldd < Z) return fail(FMRI_ERR_ARG, "reparam pitch < Z");
+    const int g = grid1d((long long)B * Z, 256);
+    if (d_dtype == FMRI_BF16)
+        reparam_kl_bwd_kernel<__nv_bfloat16><<<g, 256, 0, S(stream)>>>(
+            mu, logvar, ld, eps, gz, gkl, gkl_const, reinterpret_cast<__nv_bfloat16*>(dmu),
+            reinterpret_cast<__nv_bfloat16*>(dlogvar), ldd, B, Z);
+    else
+        reparam_kl_bwd_kernel<float><<<g, 256, 0, S(stream)>>>(mu, logvar, ld, eps, gz, gkl, gkl_const,
+                                                              reinterpret_cast<float*>(dmu),
+                                                              reinterpret_cast<float*>(dlogvar), ldd, B, Z);
     LAUNCH_OK();
     return 0;
 }
@@ -1132,46 +1141,75 @@ extern "C" int fmri_bce_bwd(const float* p, const float* g, float* dp, int n, in
 }
 
 // ================================================================================================ optimizers
+static void mt_fill(MtArgs& a, int base, int n, float* const* p, const float* const* g, float* const* s1,
+                    float* const* s2, const int64_t* numel, int64_t* mx) {
+    a.count = std::min(FMRI_MT_MAX, n - base);
+    *mx = 0;
+    for (int i = 0; i < a.count; ++i) {
+        a.t[i].p = p[base + i];
+        a.t[i].g = g[base + i];
+        a.t[i].s1 = s1[base + i];
+        a.t[i].s2 = s2 ? s2[base + i] : nullptr;
+        a.t[i].n = numel[base + i];
+        *mx = std::max(*mx, numel[base + i]);
+    }
+}
 extern "C" int fmri_multi_tensor_rmsprop(int n, float* const* p, const float* const* g, float* const* sq,
                                          const int64_t* numel, float lr, float alpha, float eps, float clamp,
-                                         void* stream) {
+                                         const float* lr_dev, const float* gate_dev, void* stream) {
     for (int base = 0; base < n; base += FMRI_MT_MAX) {
         MtArgs a;
-        a.count = std::min(FMRI_MT_MAX, n - base);
-        int64_t mx = 0;
-        for (int i = 0; i < a.count; ++i) {
-            a.t[i].p = p[base + i];
-            a.t[i].g = g[base + i];
-            a.t[i].s1 = sq[base + i];
-            a.t[i].s2 = nullptr;
-            a.t[i].n = (int)numel[base + i];
-            mx = std::max(mx, numel[base + i]);
-        }
-        dim3 grid(std::max(1, std::min(148 * 4, cdiv(mx, 256 * 4))), a.count);
-        mt_rmsprop_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, alpha, eps, clamp);
+        int64_t mx;
+        mt_fill(a, base, n, p, g, sq, nullptr, numel, &mx);
+        dim3 grid(std::max(1, std::min(148 * 8, cdiv(mx, 256 * 4))), a.count);
+        mt_rmsprop_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, alpha, eps, clamp, lr_dev, gate_dev);
         LAUNCH_OK();
     }
     return 0;
 }
 extern "C" int fmri_multi_tensor_adam(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                                       const int64_t* numel, float lr, float beta1, float beta2, float eps, int step,
-                                      float clamp, void* stream) {
-    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+                                      float clamp, const float* lr_dev, const float* gate_dev, void* stream) {
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     for (int base = 0; base < n; base += FMRI_MT_MAX) {
         MtArgs a;
-        a.count = std::min(FMRI_MT_MAX, n - base);
-        int64_t mx = 0;
-        for (int i = 0; i < a.count; ++i) {
-            a.t[i].p = p[base + i];
-            a.t[i].g = g[base + i];
-            a.t[i].s1 = m[base + i];
-            a.t[i].s2 = v[base + i];
-            a.t[i].n = (int)numel[base + i];
-            mx = std::max(mx, numel[base + i]);
-        }
-        dim3 grid(std::max(1, std::min(148 * 4, cdiv(mx, 256 * 4))), a.count);
-        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, bc1, bc2, clamp);
+        int64_t mx;
+        mt_fill(a, base, n, p, g, m, v, numel, &mx);
+        dim3 grid(std::max(1, std::min(148 * 8, cdiv(mx, 256 * 4))), a.count);
+        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, bc1, bc2, clamp, lr_dev, gate_dev);
         LAUNCH_OK();
     }
+    return 0;
+}
+
+// ================================================================================================ step glue
+extern "C" int fmri_axpby_tanh_bwd(float a, const float* x, float b, const float* y, const float* img, float* out,
+                                   long long n, void* stream) {
+    axpby_tanh_bwd_kernel<<<grid1d(n, 256), 256, 0, S(stream)>>>(a, x, b, y, img, out, n);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_chansum_nchw(const float* x, int N, int C, long long HW, float* out, int accumulate, void* stream) {
+    if (!accumulate) CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, S(stream)));
+    dim3 grid(C, std::max(1, std::min(N, 148 * 2 / std::max(C, 1))));
+    chansum_nchw_kernel<<<grid, 256, 0, S(stream)>>>(x, N, C, HW, out);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_vecsum(const float* x, long long n, float scale, float* out, int accumulate, void* stream) {
+    vecsum_kernel<<<1, 256, 0, S(stream)>>>(x, n, scale, out, accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_vgan_gate(const float* sums, float count, float margin, float equilibrium, float* gates,
+                              void* stream) {
+    vgan_gate_kernel<<<1, 32, 0, S(stream)>>>(sums, count, margin, equilibrium, gates);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                                  float* invstd, void* stream) {
+    bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+    LAUNCH_OK();
     return 0;
 }

@@ -528,10 +528,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const Tx* __restrict
         float s = 0.f, q = 0.f;
         if (col < C && tr < ry) {
             const float mu = mean[col], is = invstd[col], ga = gamma[col], be = beta[col];
+            const float sc = ga * is;
             for (long long r = r0 + tr; r < r1; r += ry) {
-                const float xh = (ld_f(x + r * C + col) - mu) * is;
+                const float xc = ld_f(x + r * C + col) - mu;
+                const float xh = xc * is;
                 float g = ld_f(dy + r * C + col);
-                if (relu && !(ga * xh + be > 0.f)) g = 0.f;
+                if (relu && !(xc * sc + be > 0.f)) g = 0.f;  // same expression as bn_apply_kernel -> same mask
                 s += g;
                 q += g * xh;
             }
@@ -566,9 +568,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
          i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const float is = invstd[c], ga = gamma[c];
-        const float xh = (ld_f(x + i) - mean[c]) * is;
+        const float xc = ld_f(x + i) - mean[c];
+        const float xh = xc * is;
         float g = ld_f(dy + i);
-        if (relu && !(ga * xh + beta[c] > 0.f)) g = 0.f;
+        if (relu && !(xc * (ga * is) + beta[c] > 0.f)) g = 0.f;
         float r = g;
         if (train) r = g - (float)(sum_g[c] / count) - xh * (float)(sum_gx[c] / count);
         st_f(dx + i, ga * is * r);
@@ -648,8 +651,9 @@ __global__ void scatter4_kernel(const Tin* __restrict__ src, Tout* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // losses (vae_gan.py:302-320, train_vgan_stage1.py:369-372, train_wae_stage1.py:281-282,301-303)
 // ------------------------------------------------------------------------------------------------
-// z = eps*exp(0.5*logvar)+mu ; kl[b] = -0.5 * sum_j (1 + lv - mu^2 - exp(lv)); one warp per row
-__global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+// z = eps*exp(0.5*logvar)+mu ; kl[b] = -0.5 * sum_j (1 + lv - mu^2 - exp(lv)); one warp per row.
+// mu / lv have row pitch `ld` (they may be the two halves of one [B, 2Z] head output); z / eps / kl are dense.
+__global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int ld,
                                       const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ kl,
                                       int B, int Z) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -657,27 +661,29 @@ __global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float*
     const int lane = threadIdx.x & 31;
     float s = 0.f;
     for (int j = lane; j < Z; j += 32) {
-        const float m = mu[row * (long long)Z + j], l = lv[row * (long long)Z + j];
-        const float e = __expf(l);
-        if (z) z[row * (long long)Z + j] = eps[row * (long long)Z + j] * __expf(0.5f * l) + m;
+        const float m = mu[row * (long long)ld + j], l = lv[row * (long long)ld + j];
+        const float e = expf(l);
+        if (z) z[row * (long long)Z + j] = eps[row * (long long)Z + j] * expf(0.5f * l) + m;
         s += 1.f + l - m * m - e;
     }
     s = warp_sum(s);
     if (lane == 0 && kl) kl[row] = -0.5f * s;
 }
-// dmu = gz + gkl[b]*mu ; dlv = gz*eps*0.5*exp(0.5 lv) + gkl[b]*0.5*(exp(lv)-1)
-__global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+// dmu = gz + gkl[b]*mu ; dlv = gz*eps*0.5*exp(0.5 lv) + gkl[b]*0.5*(exp(lv)-1); outputs with row pitch ldd
+template <typename Tg>
+__global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int ld,
                                       const float* __restrict__ eps, const float* __restrict__ gz,
-                                      const float* __restrict__ gkl, float* __restrict__ dmu, float* __restrict__ dlv,
-                                      int B, int Z) {
+                                      const float* __restrict__ gkl, float gkl_const, Tg* __restrict__ dmu,
+                                      Tg* __restrict__ dlv, int ldd, int B, int Z) {
     const long long n = (long long)B * Z;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / Z);
-        const float l = lv[i], m = mu[i];
+        const int j = (int)(i - (long long)b * Z);
+        const float l = lv[(long long)b * ld + j], m = mu[(long long)b * ld + j];
         const float g = gz ? gz[i] : 0.f;
-        const float k = gkl ? gkl[b] : 0.f;
-        dmu[i] = g + k * m;
-        dlv[i] = (gz ? g * eps[i] * 0.5f * __expf(0.5f * l) : 0.f) + k * 0.5f * (__expf(l) - 1.f);
+        const float k = gkl ? gkl[b] : gkl_const;
+        st_f(dmu + (long long)b * ldd + j, g + k * m);
+        st_f(dlv + (long long)b * ldd + j, (gz ? g * eps[i] * 0.5f * expf(0.5f * l) : 0.f) + k * 0.5f * (expf(l) - 1.f));
     }
 }
 // out[b] = scale * sum_j (a[b,j]-b[b,j])^2 ; one block per row, warp-shuffle reduction, vectorised loads
@@ -725,7 +731,7 @@ __global__ void head_sigmoid_fwd_kernel(const T* __restrict__ x, const float* __
     float s = 0.f;
     for (int j = lane; j < F; j += 32) s += ld_f(x + (long long)row * F + j) * __ldg(w + j);
     s = warp_sum(s);
-    if (lane == 0) p[row] = 1.f / (1.f + __expf(-(s + bias[0])));
+    if (lane == 0) p[row] = 1.f / (1.f + expf(-(s + bias[0])));
 }
 // given gp = dL/dp: dlogit = gp*p*(1-p); dx[row,:] = dlogit*w ; dw += sum_rows dlogit*x[row,:] ; db += sum dlogit
 template <typename T>
@@ -758,7 +764,7 @@ __global__ void bce_fwd_kernel(const float* __restrict__ p, float* __restrict__ 
                                float scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = -scale * __logf(positive ? p[i] + 1e-3f : 1.f - p[i] + 1e-3f);
+    out[i] = -scale * logf(positive ? p[i] + 1e-3f : 1.f - p[i] + 1e-3f);
 }
 __global__ void bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ dp,
                                int n, int positive, float scale, int accumulate) {
@@ -777,17 +783,22 @@ struct MtChunk {
     const float* g;
     float* s1;   // RMSprop: square_avg ; Adam: exp_avg
     float* s2;   // Adam: exp_avg_sq
-    int n;
+    long long n;
 };
 #define FMRI_MT_MAX 48
 struct MtArgs {
     MtChunk t[FMRI_MT_MAX];
     int count;
 };
+// `gate` (nullable): a device flag; the launch is a no-op when *gate == 0 (equilibrium gate decided on the device,
+// train_vgan_stage1.py:396-404, so the step needs no host round trip). `lr_dev` (nullable) overrides lr.
 __global__ void __launch_bounds__(256) mt_rmsprop_kernel(const __grid_constant__ MtArgs a, float lr, float alpha,
-                                                         float eps, float clamp) {
+                                                         float eps, float clamp, const float* __restrict__ lr_dev,
+                                                         const float* __restrict__ gate) {
+    if (gate && *gate == 0.f) return;
+    if (lr_dev) lr = *lr_dev;
     const MtChunk t = a.t[blockIdx.y];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += gridDim.x * blockDim.x) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
         float g = t.g[i];
         if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
         const float sq = alpha * t.s1[i] + (1.f - alpha) * g * g;
@@ -796,9 +807,13 @@ __global__ void __launch_bounds__(256) mt_rmsprop_kernel(const __grid_constant__
     }
 }
 __global__ void __launch_bounds__(256) mt_adam_kernel(const __grid_constant__ MtArgs a, float lr, float beta1,
-                                                      float beta2, float eps, float bc1, float bc2, float clamp) {
+                                                      float beta2, float eps, float bc1, float bc2, float clamp,
+                                                      const float* __restrict__ lr_dev,
+                                                      const float* __restrict__ gate) {
+    if (gate && *gate == 0.f) return;
+    if (lr_dev) lr = *lr_dev;
     const MtChunk t = a.t[blockIdx.y];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += gridDim.x * blockDim.x) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
         float g = t.g[i];
         if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
         const float m = beta1 * t.s1[i] + (1.f - beta1) * g;
@@ -808,6 +823,77 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(const __grid_constant__ Mt
         const float denom = sqrtf(v) / sqrtf(bc2) + eps;
         t.p[i] = t.p[i] - (lr / bc1) * m / denom;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small glue kernels of the fused training step
+// ------------------------------------------------------------------------------------------------
+// out = (a*x + b*y) * (img ? 1 - img^2 : 1): gradient mixing (loss_decoder = lambda*mse - (1-lambda)*loss_dis,
+// train_vgan_stage1.py:372) fused with the tanh backward of Decoder.conv[3] (vae_gan.py:118-121). y nullable.
+__global__ void axpby_tanh_bwd_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
+                                      const float* __restrict__ img, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = a * x[i] + (y ? b * y[i] : 0.f);
+        if (img) {
+            const float t = img[i];
+            v *= 1.f - t * t;
+        }
+        out[i] = v;
+    }
+}
+// per-channel sum of an NCHW fp32 tensor (bias gradient of Decoder.conv[3]); one block per (channel, image chunk)
+__global__ void __launch_bounds__(256) chansum_nchw_kernel(const float* __restrict__ x, int N, int C, long long HW,
+                                                           float* __restrict__ out) {
+    const int c = blockIdx.x;
+    float s = 0.f;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const float* p = x + ((long long)n * C + c) * HW;
+        for (long long i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
+    }
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out + c, v);
+    }
+}
+// out[0] (+)= scale * sum(x[0..n)) in fp64 internally; single block (n is a batch-sized vector of per-sample losses)
+__global__ void __launch_bounds__(256) vecsum_kernel(const float* __restrict__ x, long long n, float scale,
+                                                     float* __restrict__ out, int accumulate) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + scale * (float)red[0];
+}
+// equilibrium gate on the device (train_vgan_stage1.py:396-404): sums[0] = sum bce_original, sums[1] = sum bce_predicted
+// over `count` samples (already reduced across ranks); gates[0] = train_dis, gates[1] = train_dec as 0.f / 1.f
+__global__ void vgan_gate_kernel(const float* __restrict__ sums, float count, float margin, float equilibrium,
+                                 float* __restrict__ gates) {
+    if (threadIdx.x || blockIdx.x) return;
+    const float mo = sums[0] / count, mp = sums[1] / count;
+    bool dis = true, dec = true;
+    if (mo < equilibrium - margin || mp < equilibrium - margin) dis = false;
+    if (mo > equilibrium + margin || mp > equilibrium + margin) dec = false;
+    if (!dis && !dec) dis = dec = true;
+    gates[0] = dis ? 1.f : 0.f;
+    gates[1] = dec ? 1.f : 0.f;
+}
+// eval-mode BatchNorm: mean / invstd from the running statistics
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rm[c];
+    invstd[c] = rsqrtf(rv[c] + eps);
 }
 
 }  // namespace fmri

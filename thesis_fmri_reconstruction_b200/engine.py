@@ -1,0 +1,237 @@
+"""Fused training steps: one forward, the minimal backward, gradient exchange and the optimizer update, all as
+launches of libfmri_b200.so kernels on raw device buffers (no autograd graph, no host round trip inside the step).
+
+VaeGanStage1 follows /root/reference/train/train_vgan_stage1.py:316-432 (mode 'vae-gan') and computes exactly the
+three gradients its optimizers consume -- g_enc = d loss_encoder / d encoder, g_dec = d loss_decoder / d decoder,
+g_dis = d loss_discriminator / d discriminator at the pre-step weights -- with ONE discriminator forward
+(the reference runs it twice on the same inputs, vae_gan.py:284-285; BN running statistics are updated twice to match)
+and no discarded gradient (the reference's three full autograd sweeps execute 2.35x the necessary FLOPs).
+
+WaeGanStage1 follows /root/reference/train/train_wae_stage1.py:259-311.
+
+Data parallelism: every rank holds full replicas; each parameter bucket's flat fp32 gradient buffer is
+all-reduced (SUM, no averaging: the losses are batch sums) on a side stream as soon as its last gradient kernel has
+been issued, overlapping the rest of the backward; BatchNorm statistics stay per rank; the equilibrium gate is decided
+on the device from the all-reduced BCE sums so every rank takes the same branch.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+from . import lib as L
+from . import nets as NN
+from .nets import BF16, F32, E, Z
+
+
+class Bucket:
+    """Flat fp32 parameter / gradient / optimizer-state buffers of one sub-network; the named tensors are views."""
+
+    def __init__(self, prefix, named_params, n_states):
+        self.prefix = prefix
+        self.names = list(named_params)
+        sizes = [named_params[k].numel() for k in self.names]
+        offs, o = [], 0
+        for s in sizes:
+            offs.append(o)
+            o += (s + 3) // 4 * 4  # keep every tensor 16-byte aligned inside the flat buffer
+        self.numel = o
+        self.flat_p, self.flat_g = Z(o), Z(o)
+        self.states = [Z(o) for _ in range(n_states)]
+        self.P, self.G = OrderedDict(), OrderedDict()
+        for k, off, s in zip(self.names, offs, sizes):
+            shape = named_params[k].shape
+            self.P[k] = self.flat_p[off:off + s].view(shape)
+            self.G[k] = self.flat_g[off:off + s].view(shape)
+            self.P[k].copy_(named_params[k])
+        self.offsets = dict(zip(self.names, zip(offs, sizes)))
+
+    def state_view(self, i, name):
+        off, s = self.offsets[name]
+        return self.states[i][off:off + s].view(self.P[name].shape)
+
+
+def _split(full, prefix):
+    return OrderedDict((k[len(prefix):], v) for k, v in full.items() if k.startswith(prefix))
+
+
+class _TrainerBase:
+    def _setup_dist(self, dist_group):
+        self.dist = dist_group
+        self.world = 1
+        if dist_group is not None:
+            import torch.distributed as td
+
+            self.td = td
+            self.world = td.get_world_size()
+            self.comm_stream = torch.cuda.Stream()
+
+    def _allreduce_async(self, tensors):
+        """SUM all-reduce on the side stream, ordered after everything issued so far on the compute stream."""
+        if self.world == 1:
+            return
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            for t in tensors:
+                self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+                t.record_stream(self.comm_stream)
+
+    def _wait_comm(self):
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def _flush_nbt(self):
+        for name, n in self.nbt.items():
+            self.S[name] += n
+        self.nbt.clear()
+
+    def named_parameters(self):
+        out = OrderedDict()
+        for b in self.buckets.values():
+            for k, v in b.P.items():
+                out[b.prefix + k] = v
+        return out
+
+    def named_grads(self):
+        out = OrderedDict()
+        for b in self.buckets.values():
+            for k, v in b.G.items():
+                out[b.prefix + k] = v
+        return out
+
+    def named_buffers(self):
+        self._flush_nbt()
+        return self.S
+
+
+class VaeGanStage1(_TrainerBase):
+    """Stage-I VAE/GAN trainer (image -> image): visual Encoder, Decoder, Discriminator, three RMSprop optimizers."""
+
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None, gate=True):
+        from .hp import HP_VGAN
+
+        self.cfg, self.z, self.adt = cfg, z, adt
+        self.hp = dict(HP_VGAN if hp is None else hp)
+        self.gate_on = gate
+        self.enc = NN.EncoderNet(cfg, z, adt)
+        self.dec = NN.DecoderNet(cfg, z, adt)
+        self.dis = NN.DiscriminatorNet(cfg, adt)
+        dev = torch.device("cuda")
+        self.buckets = OrderedDict()
+        for pre, net in (("encoder.", self.enc), ("decoder.", self.dec), ("discriminator.", self.dis)):
+            named = _split(params, pre)
+            missing = set(net.param_names()) ^ set(named)
+            if missing:
+                raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(missing)}")
+            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named), 1)
+        self.S = OrderedDict((k, v.to(dev).clone()) for k, v in buffers.items())
+        self.Ssub = {pre: _split(self.S, pre) for pre in self.buckets}
+        self.nbt = {}
+        self.sc = Z(16)      # [0..5] = sum bce_o, bce_p, bce_s, kl, mse, nle ; [8],[9] = gates (train_dis, train_dec)
+        self.lr = {pre: float(self.hp["lr"]) for pre in self.buckets}
+        self._setup_dist(dist_group)
+        self.refresh()
+        self.launches = 0
+
+    def refresh(self):
+        """Re-derive the bf16 operand packs from the fp32 master weights (after every optimizer step)."""
+        for pre, net in (("encoder.", self.enc), ("decoder.", self.dec), ("discriminator.", self.dis)):
+            net.refresh(self.buckets[pre].P, inplace=True)
+
+    def forward_backward(self, x, eps, z_p):
+        """x [B,3,H,W] fp32 NCHW, eps / z_p [B,z] fp32, all on the device. Leaves gradients in the buckets' flat_g and the
+        loss sums in self.sc. Returns a dict of the forward tensors (device)."""
+        hp, B, z = self.hp, x.shape[0], self.z
+        lam = float(hp["lambda_mse"])
+        be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
+        Se, Sd, Sc = self.Ssub["encoder."], self.Ssub["decoder."], self.Ssub["discriminator."]
+        nbe, nbd, nbc = {}, {}, {}
+        sc = self.sc
+        # ------------------------------------------------------------------ forward (vae_gan.py:276-286)
+        ycat, ce = self.enc.forward(be.P, Se, x, True, 1, nbe)
+        mu, lv = ycat[:, :z], ycat[:, z:]
+        zz, kl = E(B, z), E(B)
+        L.reparam_kl_fwd(mu, lv, eps, zz, kl, B, z, ld=2 * z)
+        x_tilde, cd1 = self.dec.forward(bd.P, Sd, zz, True, 1, nbd)
+        x_p, cd2 = self.dec.forward(bd.P, Sd, z_p, True, 1, nbd)
+        raw3, p, cc = self.dis.forward(bc.P, Sc, [x, x_tilde, x_p], True, 2, True, nbc)  # REC + GAN passes -> 2 BN updates
+        for pre, d in (("encoder.", nbe), ("decoder.", nbd), ("discriminator.", nbc)):
+            for k, v in d.items():
+                self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
+        # ------------------------------------------------------------------ losses (vae_gan.py:302-320, stage1 :369-372)
+        Fd = raw3[0].numel()
+        mse, nle = E(B), E(B)
+        L.rowsqdiff_fwd(raw3[:B], raw3[B:2 * B], mse, B, Fd, 0.5)
+        L.rowsqdiff_fwd(x, x_tilde, nle, B, x[0].numel(), 0.5)
+        bce = E(3 * B)
+        L.bce_fwd(p[:B], bce[:B], B, True, 1.0)
+        L.bce_fwd(p[B:], bce[B:], 2 * B, False, 1.0)
+        L.vecsum(bce[:B], B, 1.0, sc[0:1])
+        L.vecsum(bce[B:2 * B], B, 1.0, sc[1:2])
+        L.vecsum(bce[2 * B:], B, 1.0, sc[2:3])
+        L.vecsum(kl, B, 1.0, sc[3:4])
+        L.vecsum(mse, B, 1.0, sc[4:5])
+        L.vecsum(nle, B, 1.0, sc[5:6])
+        self._allreduce_async([sc[:8]])  # global loss sums: the gate must agree on every rank
+        # ------------------------------------------------------------------ backward
+        # (1) discriminator, class-score path: g_dis = d loss_discriminator / d discriminator, plus d loss_dis / d(x_tilde, x_p)
+        gp = E(3 * B)
+        ones = self._ones(3 * B)
+        L.bce_bwd(p[:B], ones, gp[:B], B, True, 1.0)
+        L.bce_bwd(p[B:], ones, gp[B:], 2 * B, False, 1.0)
+        dimg_bce = self.dis.backward_gan(bc.P, cc, gp, bc.G, False, True, (1, 3))
+        self._allreduce_async([bc.flat_g])
+        # (2) discriminator, feature-tap path: d sum(mse) / d x_tilde (data gradient only; BN couples the whole 3B batch)
+        draw3 = torch.empty_like(raw3)
+        draw3[2 * B:].zero_()
+        L.rowsqdiff_bwd(raw3[:B], raw3[B:2 * B], ones, draw3[:B], draw3[B:2 * B], B, Fd, 0.5)
+        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2))
+        # (3) decoder: g_dec = d [lambda * mse - (1 - lambda) * loss_dis] / d decoder over both decoder calls
+        self.dec.backward(bd.P, cd1, lam, dimg_mse, -(1.0 - lam), dimg_bce[:B], bd.G, False, True, False)
+        self.dec.backward(bd.P, cd2, -(1.0 - lam), dimg_bce[B:], 0.0, None, bd.G, True, True, False)
+        self._allreduce_async([bd.flat_g])
+        # (4) encoder: g_enc = d [sum kl + sum mse] / d encoder; the mse term flows x_tilde -> decoder (data gradient) -> z
+        dz = self.dec.backward(bd.P, cd1, 1.0, dimg_mse, 0.0, None, None, False, False, True)
+        dycat = E(B, 2 * z, dtype=self.adt)
+        L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=1.0)
+        self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
+        self._allreduce_async([be.flat_g])
+        return dict(x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, z=zz, kl=kl, mse=mse,
+                    bce=bce, nle=nle)
+
+    def _ones(self, n):
+        if getattr(self, "_ones_buf", None) is None or self._ones_buf.numel() < n:
+            self._ones_buf = torch.ones(n, device="cuda")
+        return self._ones_buf
+
+    def update(self, B_global):
+        """Equilibrium gate (device side) + the three RMSprop updates (train_vgan_stage1.py:396-432), then repack."""
+        hp = self.hp
+        self._wait_comm()
+        gates = self.sc[8:10]
+        if self.gate_on:
+            L.vgan_gate(self.sc, float(B_global), hp["margin"], hp["equilibrium"], gates)
+        else:
+            gates.fill_(1.0)
+        for pre, g in (("encoder.", None), ("decoder.", gates[1:2]), ("discriminator.", gates[0:1])):
+            b = self.buckets[pre]
+            L.multi_tensor_rmsprop([b.flat_p], [b.flat_g], [b.states[0]], self.lr[pre], hp["alpha"], hp["eps"], 0.0,
+                                   None, g)
+        self.refresh()
+
+    def step(self, x, eps, z_p):
+        """One full training iteration on device-resident inputs. Returns the device tensor of loss sums."""
+        out = self.forward_backward(x, eps, z_p)
+        self.update(x.shape[0] * self.world)
+        return out
+
+    def losses(self):
+        """Host view of the last step's (globally reduced) loss sums, as the reference logs them (stage1 :391-394)."""
+        s = self.sc.tolist()
+        lam = float(self.hp["lambda_mse"])
+        loss_dis = s[0] + s[1] + s[2]
+        return dict(loss_encoder=s[3] + s[4], loss_discriminator=loss_dis, loss_decoder=lam * s[4] - (1 - lam) * loss_dis,
+                    nle=s[5], bce_o=s[0], bce_p=s[1], bce_s=s[2], kl=s[3], mse=s[4], train_dis=s[8] != 0,
+                    train_dec=s[9] != 0)

@@ -1,0 +1,25 @@
+"""Hyper-parameters and architecture presets of the reference, restated (no import of the reference or the oracle).
+
+/root/reference/configs/models_config.py:3-31 (architecture: the active block is 100x100 / latent 512, the commented
+block 64x64 / latent 128), configs/gan_config.py:17-32, configs/wae_config.py:16-30, configs/data_config.py:62-73.
+"""
+CFG64 = dict(image_size=64, fc_input=8, fc_output=1024, fc_input_gan=8, fc_output_gan=512, stride_gan=1,
+             latent_dim=128, output_pad_dec=[True, True, True], encoder_channels=[64, 128, 256],
+             decoder_channels=[256, 128, 32, 3], discrim_channels=[32, 128, 256, 256, 512])
+CFG100 = dict(image_size=100, fc_input=13, fc_output=1024, fc_input_gan=7, fc_output_gan=256, stride_gan=2,
+              latent_dim=512, output_pad_dec=[False, True, True], encoder_channels=[64, 128, 256],
+              decoder_channels=[256, 128, 64, 3], discrim_channels=[32, 128, 256, 256, 512])
+NUM_VOXELS = 3620
+
+# train_vgan_stage1.py:275-283 (RMSprop alpha 0.9, eps 1e-8), gan_config.py:18,25,30,31
+HP_VGAN = dict(lr=1e-4, alpha=0.9, eps=1e-8, lambda_mse=1e-6, margin=0.35, equilibrium=0.68)
+# train_wae_stage1.py:221-224 (Adam betas (0.5, 0.999); the discriminator runs at lr / 2), wae_config.py:17
+HP_WAE = dict(lr=1e-4, beta1=0.5, beta2=0.999, eps=1e-8)
+
+
+def cfg_from_module(mc):
+    """Architecture dict from a configs.models_config-style module (attribute names of the reference)."""
+    return dict(image_size=mc.image_size, fc_input=mc.fc_input, fc_output=mc.fc_output, fc_input_gan=mc.fc_input_gan,
+                fc_output_gan=mc.fc_output_gan, stride_gan=mc.stride_gan, latent_dim=mc.latent_dim,
+                output_pad_dec=list(mc.output_pad_dec), encoder_channels=list(mc.encoder_channels),
+                decoder_channels=list(mc.decoder_channels), discrim_channels=list(mc.discrim_channels))

@@ -95,11 +95,12 @@ def _f(v):
     return C.c_float(float(v))
 
 
-def _require_cuda(*ts):
+def _require_cuda(*ts, contiguous=True):
+    """contiguous=False for entry points that take explicit row pitches (pitched views are passed by base pointer)."""
     for t in ts:
         if t is not None and not t.is_cuda:
             raise FmriError("libfmri_b200 operates on CUDA tensors only (no CPU fallback)")
-        if t is not None and not t.is_contiguous():
+        if contiguous and t is not None and not t.is_contiguous():
             raise FmriError("libfmri_b200 expects contiguous tensors")
 
 
@@ -195,24 +196,24 @@ def linear_desc(M, N, K, dtype):
 
 
 def linear_pack_weights(d, w, wp, ldw, wpt, ldwt):
-    _require_cuda(w, wp, wpt)
+    _require_cuda(w, wp, wpt, contiguous=False)
     _check(load().fmri_linear_pack_weights(C.byref(d), ptr(w), ptr(wp), ldw, ptr(wpt), ldwt, stream()))
 
 
 def linear_fprop(d, x, ldx, w, wp, ldw, bias, act, y, ldy):
-    _require_cuda(x, w, wp, bias, y)
+    _require_cuda(x, w, wp, bias, y, contiguous=False)
     _check(load().fmri_linear_fprop(C.byref(d), ptr(x), ldx, ptr(w), ptr(wp), ldw, ptr(bias), act, ptr(y), ldy,
                                     dt(y), stream()))
 
 
-def linear_dgrad(d, dy, lddy, w, wpt, ldwt, dx, lddx):
-    _require_cuda(dy, w, wpt, dx)
+def linear_dgrad(d, dy, lddy, w, wpt, ldwt, dx, lddx, accumulate=False):
+    _require_cuda(dy, w, wpt, dx, contiguous=False)
     _check(load().fmri_linear_dgrad(C.byref(d), ptr(dy), lddy, ptr(w), ptr(wpt), ldwt, ptr(dx), lddx, dt(dx),
-                                    stream()))
+                                    int(accumulate), stream()))
 
 
 def linear_wgrad(d, x, ldx, dy, lddy, dw, accumulate):
-    _require_cuda(x, dy, dw)
+    _require_cuda(x, dy, dw, contiguous=False)
     _check(load().fmri_linear_wgrad(C.byref(d), ptr(x), ldx, ptr(dy), lddy, ptr(dw), int(accumulate), stream()))
 
 
@@ -261,20 +262,18 @@ def nhwc_to_nchw(src, dst, N, Cc, H, W, accumulate=False):
 
 
 def cast2d(src, lds, dst, ldd, rows, cols):
-    _require_cuda(src, dst)
+    _require_cuda(src, dst, contiguous=False)
     _check(load().fmri_cast2d(ptr(src), dt(src), lds, ptr(dst), dt(dst), ldd, _ll(rows), cols, stream()))
 
 
 # ------------------------------------------------------------------------------------------------ losses
-def reparam_kl_fwd(mu, logvar, eps, z, kl, B, Z):
-    _require_cuda(mu, logvar, eps, z, kl)
-    _check(load().fmri_reparam_kl_fwd(ptr(mu), ptr(logvar), ptr(eps), ptr(z), ptr(kl), B, Z, stream()))
+def reparam_kl_fwd(mu, logvar, eps, z, kl, B, Z, ld=None):
+    _check(load().fmri_reparam_kl_fwd(ptr(mu), ptr(logvar), ld or Z, ptr(eps), ptr(z), ptr(kl), B, Z, stream()))
 
 
-def reparam_kl_bwd(mu, logvar, eps, gz, gkl, dmu, dlv, B, Z):
-    _require_cuda(mu, logvar, eps, gz, gkl, dmu, dlv)
-    _check(load().fmri_reparam_kl_bwd(ptr(mu), ptr(logvar), ptr(eps), ptr(gz), ptr(gkl), ptr(dmu), ptr(dlv), B, Z,
-                                      stream()))
+def reparam_kl_bwd(mu, logvar, eps, gz, gkl, dmu, dlv, B, Z, ld=None, ldd=None, gkl_const=0.0):
+    _check(load().fmri_reparam_kl_bwd(ptr(mu), ptr(logvar), ld or Z, ptr(eps), ptr(gz), ptr(gkl), _f(gkl_const),
+                                      ptr(dmu), ptr(dlv), ldd or Z, dt(dmu), B, Z, stream()))
 
 
 def rowsqdiff_fwd(a, b, out, rows, F, scale):
@@ -315,15 +314,38 @@ def _ptr_array(tensors):
     return arr
 
 
-def multi_tensor_rmsprop(params, grads, sqs, lr, alpha, eps, clamp=0.0):
+def multi_tensor_rmsprop(params, grads, sqs, lr, alpha, eps, clamp=0.0, lr_dev=None, gate_dev=None):
     n = len(params)
     numel = (C.c_int64 * n)(*[p.numel() for p in params])
     _check(load().fmri_multi_tensor_rmsprop(n, _ptr_array(params), _ptr_array(grads), _ptr_array(sqs), numel, _f(lr),
-                                            _f(alpha), _f(eps), _f(clamp), stream()))
+                                            _f(alpha), _f(eps), _f(clamp), ptr(lr_dev), ptr(gate_dev), stream()))
 
 
-def multi_tensor_adam(params, grads, ms, vs, lr, beta1, beta2, eps, step, clamp=0.0):
+def multi_tensor_adam(params, grads, ms, vs, lr, beta1, beta2, eps, step, clamp=0.0, lr_dev=None, gate_dev=None):
     n = len(params)
     numel = (C.c_int64 * n)(*[p.numel() for p in params])
     _check(load().fmri_multi_tensor_adam(n, _ptr_array(params), _ptr_array(grads), _ptr_array(ms), _ptr_array(vs),
-                                         numel, _f(lr), _f(beta1), _f(beta2), _f(eps), int(step), _f(clamp), stream()))
+                                         numel, _f(lr), _f(beta1), _f(beta2), _f(eps), int(step), _f(clamp),
+                                         ptr(lr_dev), ptr(gate_dev), stream()))
+
+
+# ------------------------------------------------------------------------------------------------ step glue
+def axpby_tanh_bwd(a, x, b, y, img, out):
+    _require_cuda(x, y, img, out)
+    _check(load().fmri_axpby_tanh_bwd(_f(a), ptr(x), _f(b), ptr(y), ptr(img), ptr(out), _ll(out.numel()), stream()))
+
+
+def chansum_nchw(x, N, Cc, HW, out, accumulate=False):
+    _check(load().fmri_chansum_nchw(ptr(x), N, Cc, _ll(HW), ptr(out), int(accumulate), stream()))
+
+
+def vecsum(x, n, scale, out, accumulate=False):
+    _check(load().fmri_vecsum(ptr(x), _ll(n), _f(scale), ptr(out), int(accumulate), stream()))
+
+
+def vgan_gate(sums, count, margin, equilibrium, gates):
+    _check(load().fmri_vgan_gate(ptr(sums), _f(count), _f(margin), _f(equilibrium), ptr(gates), stream()))
+
+
+def bn_eval_stats(rm, rv, Cc, eps, mean, invstd):
+    _check(load().fmri_bn_eval_stats(ptr(rm), ptr(rv), Cc, _f(eps), ptr(mean), ptr(invstd), stream()))
