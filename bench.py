@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the training hot path (BASELINE.json: "Stage-I VAE/GAN train samples/sec @64x64").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stage1_vaegan] [--batch GLOBAL_B]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...     # the CPU arm: the oracle port of the reference step on the host cores
+
+One step = one full training iteration (forward, minimal backward, gradient all-reduce for N > 1, three RMSprop updates,
+bf16 operand repack) on one synthetic batch. `value` times K steps with inputs resident in HBM; `e2e` times K steps fed
+from pinned host memory (H2D of the batch + noise, D2H of the loss sums, every step). Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic MFLOP per sample per optimisation step (2 x MACs of the necessary GEMMs only)
+ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8}
+METRIC = "stage1_vaegan_train_samples_per_sec_64x64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan"])
+    ap.add_argument("--batch", type=int, default=4096, help="GLOBAL batch (BASELINE.json configs[4]: 4096, strong scaling)")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    except Exception:
+        return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_steps(workload, B, steps, warmup, threads=None):
+    """The oracle port of the reference step (oracle/vaegan.py: reference modules' arithmetic restated functionally, the
+    reference's two discriminator passes and three autograd sweeps) on the host cores. Returns (samples/s, ms/step, cores)."""
+    import torch
+
+    from oracle import vaegan as O
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    if workload == "stage1_vaegan":
+        P, S = O.make_vaegan(O.CFG64, seed=12345, jitter=False)
+        x = O.synthetic_images(B)
+        eps, z_p = O.synthetic_noise(B, 128)
+        sq = None
+
+        def one():
+            nonlocal P, sq
+            out = O.stage1_vaegan_step(P, S, x, eps, z_p, sq=sq)
+            P, sq = out["params"], out["square_avg"]
+    else:
+        P, S = O.make_waegan(O.CFG64, seed=12345, jitter=False)
+        x = O.synthetic_images(B)
+        z_fake = O.synthetic_noise(B, 128)[0] * 0.5
+        st = dict(opt=None, t=1)
+
+        def one():
+            nonlocal P
+            out = O.stage1_waegan_step(P, S, x, z_fake, opt=st["opt"], step=st["t"])
+            P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return B / dt, dt * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    B = args.cpu_batch
+    v, ms, cores = cpu_reference_steps(args.workload, B, steps, warm)
+    sample = f"{steps} timed + {warm} warm-up steps of batch {B} (bounded sample of the workload), fp32, torch CPU"
+    line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=f"{args.workload} 64x64 z=128, oracle port of the reference step on host CPU", global_batch=B),
+                cpu_baseline=dict(value=v, unit="samples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        import torch.distributed as td
+
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = td.group.WORLD
+    from thesis_fmri_reconstruction_b200 import engine, hp, init, lib
+
+    if args.batch % world:
+        raise SystemExit(f"global batch {args.batch} not divisible by {world} ranks")
+    B = args.batch // world
+    cfg, z = hp.CFG64, 128
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = (torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1).pin_memory()
+    if args.workload == "stage1_vaegan":
+        P, S = init.init_vaegan(cfg, z, seed=12345)
+        tr = engine.VaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group, gate=True)
+        n1_host = torch.randn(B, z, generator=gen).pin_memory()
+        n2_host = torch.randn(B, z, generator=gen).pin_memory()
+    else:
+        P, S = init.init_waegan(cfg, z, seed=12345)
+        tr = engine.WaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group)
+        n1_host = (torch.randn(B, z, generator=gen) * 0.5).pin_memory()
+        n2_host = None
+    x = x_host.cuda(non_blocking=True)
+    n1 = n1_host.cuda(non_blocking=True)
+    n2 = n2_host.cuda(non_blocking=True) if n2_host is not None else None
+
+    def step_dev():
+        if n2 is not None:
+            tr.step(x, n1, n2)
+        else:
+            tr.step(x, n1)
+
+    def sync_all():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            td.all_reduce(ms, op=td.ReduceOp.MAX)
+        return ms.item()
+
+    # ---------------------------------------------------------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        step_dev()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.launch_count(reset=True)
+    ms_total = timed(step_dev, args.steps)
+    launches = lib.launch_count()
+    ck = clocks.stop() if rank == 0 else None
+    losses = tr.losses()
+    ms_step = ms_total / args.steps
+    value = args.batch / (ms_step * 1e-3)
+
+    # ---------------------------------------------------------------- end to end from pinned host memory (`e2e`)
+    copy_stream = torch.cuda.Stream()
+    bufs = [[torch.empty_like(x), torch.empty_like(n1), torch.empty_like(n2) if n2 is not None else None] for _ in range(2)]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    sc_host = torch.empty(16).pin_memory()
+    state = dict(i=0)
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[slot])  # the step that last read this slot has finished
+            bufs[slot][0].copy_(x_host, non_blocking=True)
+            bufs[slot][1].copy_(n1_host, non_blocking=True)
+            if n2 is not None:
+                bufs[slot][2].copy_(n2_host, non_blocking=True)
+            evs[slot].record(copy_stream)
+
+    def step_e2e():
+        i = state["i"]
+        slot = i & 1
+        torch.cuda.current_stream().wait_event(evs[slot])
+        upload(slot ^ 1)  # prefetch the next batch while this step computes (the DataLoader's role in the reference)
+        b = bufs[slot]
+        if n2 is not None:
+            tr.step(b[0], b[1], b[2])
+        else:
+            tr.step(b[0], b[1])
+        done[slot].record()
+        sc_host.copy_(tr.sc, non_blocking=True)  # D2H of the step's loss sums (what train_vgan_stage1.py:391-401 reads)
+        state["i"] = i + 1
+
+    done[0].record(); done[1].record()
+    upload(0)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = args.batch / (ms_e2e * 1e-3)
+    h2d = world * (x_host.numel() + n1_host.numel() + (n2_host.numel() if n2_host is not None else 0)) * 4
+    d2h = world * 16 * 4
+
+    # ---------------------------------------------------------------- per-kernel-family device times (CUDA events)
+    pk = peaks()
+    roof = None
+    if not args.no_profile:
+        torch.cuda.synchronize()
+        lib.profile_begin()
+        psteps = max(1, min(3, args.steps))
+        for _ in range(psteps):
+            step_dev()
+        agg = lib.profile_end()
+        tot_ms = sum(a["ms"] for a in agg.values())
+        fam = {}
+        for name, a in agg.items():
+            k = "igemm" if name in ("fmri_conv_fprop", "fmri_conv_dgrad", "fmri_linear_fprop", "fmri_linear_dgrad") else (
+                "wgrad" if name in ("fmri_conv_wgrad", "fmri_linear_wgrad") else name)
+            f = fam.setdefault(k, dict(ms=0.0, calls=0, flops=0.0))
+            for q in ("ms", "calls", "flops"):
+                f[q] += a[q]
+        dom = max(("igemm", "wgrad"), key=lambda k: fam.get(k, dict(ms=0))["ms"])
+        d = fam[dom]
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        top = sorted(((k, round(v["ms"] / psteps, 3)) for k, v in fam.items()), key=lambda t: -t[1])[:8]
+        roof = dict(bound="tensor", kernel=("igemm_kernel (conv/convT fprop+dgrad, linear fprop+dgrad)" if dom == "igemm"
+                                            else "wgrad_kernel (conv/convT/linear weight gradients)"),
+                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None,
+                    peak_source=pk["src"], kernel_ms_per_step=d["ms"] / psteps, kernel_launches_per_step=d["calls"] / psteps,
+                    kernel_share_of_step=d["ms"] / tot_ms if tot_ms else None,
+                    whole_step_achieved=ALG_MFLOP[args.workload] * 1e6 * value / 1e12,
+                    whole_step_frac=ALG_MFLOP[args.workload] * 1e6 * value / 1e12 / pk["tflops"],
+                    top_entry_points_ms_per_step=top)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        v, ms, cores = cpu_reference_steps(args.workload, args.cpu_batch, 2, 1)
+        cpu = dict(value=v, unit="samples/s", cores=cores, kind="port",
+                   sample=f"2 timed + 1 warm-up steps of batch {args.cpu_batch} of the same workload (oracle port, fp32, torch CPU)")
+    if rank == 0:
+        act_gb = B * 3 * (64 * 64 * 32 + 32 * 32 * 128 + 16 * 16 * 256 + 8 * 8 * 256) * 2 * 2 / 1e9
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
+                    data="synthetic", impl="ours",
+                    config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json configs[4]: global batch {args.batch})",
+                                global_batch=args.batch, per_gpu_batch=B, parallelism=f"dp{world}",
+                                l2="inputs larger than L2: per-step activation working set ~%.1f GB per GPU >> 126 MB" % act_gb,
+                                optimizer="3 x RMSprop (fused multi-tensor), equilibrium gate on device"),
+                    e2e=dict(value=e2e_value, unit="samples/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=d2h), gpu_launches=launches, clocks=ck, roofline=roof, cpu_baseline=cpu,
+                    losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in losses.items()})
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ typedef enum { FMRI_ACT_NONE = 0, FMRI_ACT_RELU = 1, FMRI_ACT_TANH = 2, FMRI_ACT
 
 int fmri_version(void);
 const char* fmri_last_error(void);
+/* number of kernels this library has launched since the last reset (memsets excluded) */
+long long fmri_launch_count(int reset);
 /* 1 when the running device is sm_100 and the tensor path can be used, 0 otherwise (no GPU: 0, no error). */
 int fmri_tensor_path_available(void);
 

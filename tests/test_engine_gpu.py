@@ -2,8 +2,9 @@
 same seeded inputs and weights.
 
 Tolerances (rel-L2 per tensor, vs the fp32 oracle on CPU):
-  fp32 exact path : forward tensors / losses 1e-4; gradient buckets 5e-3 (the reference's own fp32 noise on end-to-end
-                    gradients is 1e-3..2e-3 through single ReLU-mask flips); BN buffers 1e-4.
+  fp32 exact path : forward tensors / losses 1e-4; BN buffers 1e-4; gradient buckets vs the fp64 oracle:
+                    max(1e-3, 3 x the oracle's own fp32-vs-fp64 deviation measured in the same run) -- end-to-end gradients
+                    are dominated by single ReLU-mask flips (1e-3..2e-3 for the reference against itself).
   bf16 tensor path: forward tensors / losses 2e-2 (north_star); end-to-end gradient buckets are REPORTED and bounded
                     loosely (0.5) because thousands of ReLU masks flip under bf16 rounding -- CPU bf16 autocast of the
                     reference itself shows 6e-2 .. 2.4e-1.
@@ -35,6 +36,9 @@ def run_case(B, adt, seed=4242):
     eps, z_p = O.synthetic_noise(B, 128, seed=seed)
     S_ref = {k: v.clone() for k, v in S.items()}
     ref = O.stage1_vaegan_step(P, S_ref, x, eps, z_p)
+    P64 = {k: v.double() for k, v in P.items()}
+    S64 = {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in S.items()}
+    ref64 = O.stage1_vaegan_step(P64, S64, x.double(), eps.double(), z_p.double(), update=False)
     tr = engine.VaeGanStage1(P, S, hp.CFG64, 128, adt)
     out = tr.forward_backward(x.cuda(), eps.cuda(), z_p.cuda())
     grads = {k: v.clone() for k, v in tr.named_grads().items()}
@@ -53,11 +57,13 @@ def run_case(B, adt, seed=4242):
     for k in ("loss_encoder", "loss_decoder", "loss_discriminator"):
         errs[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
     gate_ok = (lo["train_dis"], lo["train_dec"]) == (ref["train_dis"], ref["train_dec"])
-    gerr = {}
+    gerr, gnoise = {}, {}
     for b in ("encoder.", "decoder.", "discriminator."):
         a = torch.cat([grads[k].reshape(-1) for k in grads if k.startswith(b)])
         r = torch.cat([ref["grads"][k].reshape(-1) for k in grads if k.startswith(b)])
-        gerr[b] = rel(a, r)
+        r64 = torch.cat([ref64["grads"][k].reshape(-1) for k in grads if k.startswith(b)])
+        gerr[b] = rel(a, r64)
+        gnoise[b] = rel(r, r64)
     gten = {k: rel(grads[k], ref["grads"][k]) for k in grads}
     newP = tr.named_parameters()
     derr = {}
@@ -67,7 +73,7 @@ def run_case(B, adt, seed=4242):
         derr[b] = rel(a, r)
     berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
     nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
-    rep = dict(B=B, dtype=str(adt), forward=errs, grad_bucket=gerr, grad_tensor_worst=max(gten.items(), key=lambda t: t[1]),
+    rep = dict(B=B, dtype=str(adt), forward=errs, grad_bucket=gerr, grad_bucket_oracle_fp32_noise=gnoise, grad_tensor_worst=max(gten.items(), key=lambda t: t[1]),
                delta_bucket=derr, bn_worst=max(berr.items(), key=lambda t: t[1]), gate_ok=gate_ok, nbt_ok=nbt_ok)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/parity_stage1_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
@@ -77,9 +83,10 @@ def run_case(B, adt, seed=4242):
 
 
 def test_stage1_vaegan_fp32_exact_path():
-    rep = run_case(4, torch.float32)
+    rep = run_case(8, torch.float32)
     assert max(rep["forward"].values()) < 1e-4, rep["forward"]
-    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    for b, e in rep["grad_bucket"].items():
+        assert e < max(1e-3, 3 * rep["grad_bucket_oracle_fp32_noise"][b]), (b, e, rep["grad_bucket_oracle_fp32_noise"])
     assert rep["bn_worst"][1] < 1e-4 and rep["gate_ok"] and rep["nbt_ok"]
 
 

@@ -25,14 +25,21 @@ static int fail(int code, const char* fmt, ...) {
         cudaError_t e_ = (expr);                                                                   \
         if (e_ != cudaSuccess) return fail(FMRI_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
+static long long g_launches = 0;  // kernels launched by this library (memsets not counted); host-thread confined
 #define LAUNCH_OK()                                                                                    \
     do {                                                                                               \
+        ++g_launches;                                                                                  \
         cudaError_t e_ = cudaGetLastError();                                                           \
         if (e_ != cudaSuccess) return fail(FMRI_ERR_CUDA, "launch %s:%d: %s", __FILE__, __LINE__,      \
                                            cudaGetErrorString(e_));                                    \
     } while (0)
 
 extern "C" int fmri_version(void) { return FMRI_ABI_VERSION; }
+extern "C" long long fmri_launch_count(int reset) {
+    const long long n = g_launches;
+    if (reset) g_launches = 0;
+    return n;
+}
 extern "C" const char* fmri_last_error(void) { return g_err; }
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -342,7 +349,6 @@ static int run_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, in
         }
     }
     p.bias = bias;
-    if (splits > 1 && bias) return fail(FMRI_ERR_ARG, "split-K gemm with bias unsupported");
     p.act = act;
     return dispatch_ig(p, BN, KCH, 1, st);
 }

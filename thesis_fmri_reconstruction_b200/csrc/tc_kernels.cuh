@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
+            if (p.bias && split == 0) {  // split-K: exactly one split adds the bias
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
             }

@@ -44,6 +44,70 @@ def header_functions():
 
 
 _lib = None
+PROF = None      # list of (entry point, algorithmic flops, start event, end event) while profiling
+_FLOPS = 0.0     # algorithmic FLOPs of the next call (set by the conv / linear wrappers)
+
+
+class _Proxy:
+    """Attribute proxy over the CDLL: while profiling is on, brackets every entry point with CUDA events on the
+    current stream (the stream the library launches on)."""
+
+    def __init__(self, cdll):
+        self._c = cdll
+
+    def __getattr__(self, name):
+        f = getattr(self._c, name)
+        if PROF is None or name in ("fmri_last_error", "fmri_conv_out_hw", "fmri_conv_wgrad_workspace",
+                                    "fmri_edge_workspace", "fmri_launch_count", "fmri_version"):
+            return f
+
+        def timed(*a):
+            global _FLOPS
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = f(*a)
+            e1.record()
+            PROF.append((name, _FLOPS, e0, e1))
+            _FLOPS = 0.0
+            return rc
+
+        return timed
+
+
+def profile_begin():
+    global PROF
+    PROF = []
+
+
+def profile_end():
+    """Stop profiling; returns {entry point: dict(ms=total device ms, calls=n, flops=total algorithmic flops)}."""
+    global PROF
+    torch.cuda.synchronize()
+    agg = {}
+    for name, fl, e0, e1 in PROF or []:
+        a = agg.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
+        a["ms"] += e0.elapsed_time(e1)
+        a["calls"] += 1
+        a["flops"] += fl
+    PROF = None
+    return agg
+
+
+def launch_count(reset=False):
+    return int(load().fmri_launch_count(int(reset)))
+
+
+def _conv_flops(d):
+    if d.transposed:
+        return 2.0 * d.N * d.H * d.W * d.Cin * d.Cout * 25
+    oh, ow = (d.H - 1) // d.stride + 1, (d.W - 1) // d.stride + 1
+    return 2.0 * d.N * oh * ow * d.Cin * d.Cout * 25
+
+
+def _note_flops(v):
+    global _FLOPS
+    if PROF is not None:
+        _FLOPS = float(v)
 
 
 def load():
@@ -54,11 +118,13 @@ def load():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "There is no fallback path."
             )
-        _lib = C.CDLL(LIB_PATH)
-        _lib.fmri_last_error.restype = C.c_char_p
-        _lib.fmri_conv_wgrad_workspace.restype = C.c_size_t
-        _lib.fmri_edge_workspace.restype = C.c_size_t
-        _lib.fmri_conv_out_hw.restype = None
+        c = C.CDLL(LIB_PATH)
+        c.fmri_last_error.restype = C.c_char_p
+        c.fmri_conv_wgrad_workspace.restype = C.c_size_t
+        c.fmri_edge_workspace.restype = C.c_size_t
+        c.fmri_conv_out_hw.restype = None
+        c.fmri_launch_count.restype = C.c_longlong
+        _lib = _Proxy(c)
     return _lib
 
 
@@ -122,12 +188,14 @@ def conv_pack_weights(d, w, pack_f, pack_d):
 
 def conv_fprop(d, x, w, pack_f, bias, act, y, stat_sum=None, stat_sq=None):
     _require_cuda(x, w, pack_f, bias, y, stat_sum, stat_sq)
+    _note_flops(_conv_flops(d))
     _check(load().fmri_conv_fprop(C.byref(d), ptr(x), ptr(w), ptr(pack_f), ptr(bias), act, ptr(y), ptr(stat_sum),
                                   ptr(stat_sq), stream()))
 
 
 def conv_dgrad(d, dy, w, pack_d, dx):
     _require_cuda(dy, w, pack_d, dx)
+    _note_flops(_conv_flops(d))
     _check(load().fmri_conv_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(pack_d), ptr(dx), stream()))
 
 
@@ -138,6 +206,7 @@ def conv_wgrad_workspace(d):
 def conv_wgrad(d, x, dy, dw, accumulate, ws):
     _require_cuda(x, dy, dw, ws)
     nbytes = ws.numel() * ws.element_size() if ws is not None else 0
+    _note_flops(_conv_flops(d))
     _check(load().fmri_conv_wgrad(C.byref(d), ptr(x), ptr(dy), ptr(dw), int(accumulate), ptr(ws), C.c_size_t(nbytes),
                                   stream()))
 
@@ -202,18 +271,21 @@ def linear_pack_weights(d, w, wp, ldw, wpt, ldwt):
 
 def linear_fprop(d, x, ldx, w, wp, ldw, bias, act, y, ldy):
     _require_cuda(x, w, wp, bias, y, contiguous=False)
+    _note_flops(2.0 * d.M * d.N * d.K)
     _check(load().fmri_linear_fprop(C.byref(d), ptr(x), ldx, ptr(w), ptr(wp), ldw, ptr(bias), act, ptr(y), ldy,
                                     dt(y), stream()))
 
 
 def linear_dgrad(d, dy, lddy, w, wpt, ldwt, dx, lddx, accumulate=False):
     _require_cuda(dy, w, wpt, dx, contiguous=False)
+    _note_flops(2.0 * d.M * d.N * d.K)
     _check(load().fmri_linear_dgrad(C.byref(d), ptr(dy), lddy, ptr(w), ptr(wpt), ldwt, ptr(dx), lddx, dt(dx),
                                     int(accumulate), stream()))
 
 
 def linear_wgrad(d, x, ldx, dy, lddy, dw, accumulate):
     _require_cuda(x, dy, dw, contiguous=False)
+    _note_flops(2.0 * d.M * d.N * d.K)
     _check(load().fmri_linear_wgrad(C.byref(d), ptr(x), ldx, ptr(dy), lddy, ptr(dw), int(accumulate), stream()))
 
 
