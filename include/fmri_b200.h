@@ -85,8 +85,9 @@ int fmri_edge_in_fprop(const fmri_edge_desc* d, const float* img0, const float* 
 /* dimg[N,3,H,W] = data gradient wrt the concatenated image batch */
 int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const float* w, float* dimg, void* ws, size_t ws_bytes,
                        void* stream);
+/* dbias (nullable): also emits the bias gradient dbias[c] (+)= sum over pixels of dy (Discriminator.conv[0] has a bias) */
 int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2, int n_per_src,
-                       const void* dy, float* dw, int accumulate, void* ws, size_t ws_bytes, void* stream);
+                       const void* dy, float* dw, float* dbias, int accumulate, void* ws, size_t ws_bytes, void* stream);
 int fmri_edge_out_fprop(const fmri_edge_desc* d, const void* x, const float* w, const float* bias, int act, float* img,
                         void* ws, size_t ws_bytes, void* stream);
 int fmri_edge_out_dgrad(const fmri_edge_desc* d, const float* dimg, const float* w, void* dx, void* ws, size_t ws_bytes,

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol that
+include/fmri_b200.h declares, reports its ABI version, and refuses CPU tensors loudly (no fallback path)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from thesis_fmri_reconstruction_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_present_and_loads():
+    assert os.path.exists(L.LIB_PATH), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    L.load()
+
+
+def test_every_header_symbol_is_exported():
+    names = L.header_functions()
+    assert len(names) >= 40, names
+    c = ctypes.CDLL(L.LIB_PATH)
+    missing = [n for n in names if not hasattr(c, n)]
+    assert not missing, missing
+
+
+def test_abi_version_matches_header():
+    src = open(L.HEADER_PATH).read()
+    want = int(re.search(r"#define\s+FMRI_ABI_VERSION\s+(\d+)", src).group(1))
+    assert L.load().fmri_version() == want
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(L.HEADER_PATH).read()
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)  # comments may cite torch call sites; declarations may not use torch types
+    assert "at::" not in code and "torch" not in code.lower() and "#include <torch" not in src
+    assert 'extern "C"' in src
+
+
+def test_tensor_path_query_without_gpu_is_clean():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert L.load().fmri_tensor_path_available() == 0
+
+
+def test_cpu_tensors_are_refused():
+    x = torch.zeros(4, 8)
+    with pytest.raises(L.FmriError):
+        L.colsum(x, 4, 8, torch.zeros(8))
+
+
+def test_conv_geometry_helper():
+    # Conv2d: OH = (H-1)/s + 1 ; ConvTranspose2d: OH = 2H - 1 + output_pad   (vae_gan.py:18-20, 46-53)
+    for H, s, want in ((64, 2, 32), (25, 2, 13), (13, 2, 7), (64, 1, 64), (100, 2, 50)):
+        d = L.conv_desc(1, H, H, 32, 32, s, False, 0, torch.float32)
+        assert L.conv_out_hw(d) == (want, want)
+    for H, op, want in ((8, 1, 16), (13, 0, 25), (25, 1, 50), (50, 1, 100)):
+        d = L.conv_desc(1, H, H, 32, 32, 2, True, op, torch.float32)
+        assert L.conv_out_hw(d) == (want, want)
+
+
+def test_product_path_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "thesis_fmri_reconstruction_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py") and f != "smoke.py":
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+    for f in ("vae_gan.py",):
+        p = os.path.join(ROOT, "models", f)
+        if os.path.exists(p):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(p).read(), flags=re.M)

@@ -685,7 +685,22 @@ extern "C" int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const
 }
 template <int C>
 static int edge_wgrad_t(int dtype, const void* T, const float* i0, const float* i1, const float* i2, int nps,
-                        float* dwk, int N, int PH, int PW, int IH, int IW, int stride, int sg, cudaStream_t st) {
+                        float* dwk, float* dbias, int N, int PH, int PW, int IH, int IW, int stride, int sg,
+                        cudaStream_t st) {
+    if (PW <= 128 && (PW - 1) * stride + 5 <= 144) {
+        const long long lines = (long long)N * PH;
+        const int rpb = (int)std::max<long long>(1, (lines + 148 * 3 - 1) / (148 * 3));
+        const int blocks = cdiv(lines, rpb);
+        if (dtype == FMRI_BF16)
+            edge_wgrad_rows_kernel<C, __nv_bfloat16><<<blocks, 256, 0, st>>>(
+                reinterpret_cast<const __nv_bfloat16*>(T), i0, i1, i2, nps, dwk, dbias, N, PH, PW, IH, IW, stride, sg, rpb);
+        else
+            edge_wgrad_rows_kernel<C, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(T), i0, i1, i2, nps,
+                                                                    dwk, dbias, N, PH, PW, IH, IW, stride, sg, rpb);
+        LAUNCH_OK();
+        return 0;
+    }
+    if (dbias) return fail(FMRI_ERR_UNSUPPORTED, "edge wgrad: fused bias gradient needs rows of <= 128 pixels");
     const long long pix = (long long)N * PH * PW;
     int ppb = (int)std::max<long long>(64, ((pix + 148 * 4 - 1) / (148 * 4) + 7) / 8 * 8);
     const int blocks = cdiv(pix, ppb);
@@ -699,8 +714,8 @@ static int edge_wgrad_t(int dtype, const void* T, const float* i0, const float* 
     return 0;
 }
 extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, const float* img1, const float* img2,
-                                  int n_per_src, const void* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
-                                  void* stream) {
+                                  int n_per_src, const void* dy, float* dw, float* dbias, int accumulate, void* ws,
+                                  size_t ws_bytes, void* stream) {
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
     float* dwk = reinterpret_cast<float*>(ws);
@@ -708,9 +723,10 @@ extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, co
     const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
     if (!img1) img1 = img0;
     if (!img2) img2 = img0;
-    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, d->N, OH, OW, d->H, d->W,
+    if (dbias && !accumulate) CUDA_OK(cudaMemsetAsync(dbias, 0, sizeof(float) * d->C, S(stream)));
+    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
                                        d->stride, 1, S(stream))
-                    : edge_wgrad_t<64>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, d->N, OH, OW, d->H, d->W,
+                    : edge_wgrad_t<64>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
                                        d->stride, 1, S(stream));
     if (rc) return rc;
     // dwk[(ci*25+tap)*C + c] -> dw[c][ci][tap]
@@ -751,10 +767,10 @@ extern "C" int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const
     if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
     float* dwk = reinterpret_cast<float*>(ws);
     CUDA_OK(cudaMemsetAsync(dwk, 0, fmri_edge_workspace(d), S(stream)));
-    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, d->N, d->H, d->W, d->H, d->W, 1, -1,
-                                       S(stream))
-                    : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, d->N, d->H, d->W, d->H, d->W, 1, -1,
-                                       S(stream));
+    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
+                                       1, -1, S(stream))
+                    : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
+                                       1, -1, S(stream));
     if (rc) return rc;
     // dwk[(co*25+tap)*C + c] -> dw[co][c][tap]
     scatter4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, S(stream)>>>(dwk, dw, 1, 3, 25, d->C, 0,
@@ -944,7 +960,8 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
                                                                 gamma, beta, relu, ws, ws + C, rpb);
     LAUNCH_OK();
     if (dx) {
-        bn_bwd_apply_kernel<Tx, Tg><<<grid1d(rows * C, 256, 148 * 16), 256, 0, st>>>(
+        if (C % 8) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward needs C %% 8 == 0");
+        bn_bwd_apply_kernel<Tx, Tg><<<grid1d((rows * C + 7) / 8, 256, 148 * 8), 256, 0, st>>>(
             reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), reinterpret_cast<Tg*>(dx), rows * C, C,
             (double)rows, mean, invstd, gamma, beta, relu, train, ws, ws + C);
         LAUNCH_OK();

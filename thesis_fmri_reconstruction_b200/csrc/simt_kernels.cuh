@@ -348,6 +348,114 @@ __global__ void __launch_bounds__(256) edge_wgrad_kernel(const Tt* __restrict__ 
     }
 }
 
+// (W2) register-tiled version of (W) for T-grid rows of up to 128 pixels (every shape of the 64x64 and 100x100 configs).
+//     One block walks `rows_per_block` consecutive (image, row) lines of the T grid. Per line it stages the 15 image
+//     rows (3 channels x 5 kh) the line touches and the line of T (as fp32) in shared memory; thread (g, cq, half) owns
+//     the 5 kw taps x 4 channels accumulators of patch row g = c3*5+kh for a contiguous half of the line, so the inner
+//     loop is 1 LDS.128 (T) + 1..5 LDS.32 (sliding image window) for 20 FMAs. Partial sums go out as fp32 atomics.
+//     Optionally also emits dbias[c] += sum_pixels T[pixel][c] (bias gradient of Discriminator.conv[0], vae_gan.py:145).
+template <int C, typename Tt>
+__global__ void __launch_bounds__(256) edge_wgrad_rows_kernel(const Tt* __restrict__ T, const float* __restrict__ src0,
+                                                              const float* __restrict__ src1,
+                                                              const float* __restrict__ src2, int n_per_src,
+                                                              float* __restrict__ dwk, float* __restrict__ dbias, int N,
+                                                              int PH, int PW, int IH, int IW, int stride, int sg,
+                                                              int rows_per_block) {
+    constexpr int CQ = C / 4;          // channel quads
+    constexpr int TPS = 15 * CQ;       // threads per pixel set
+    constexpr int PS = 256 / TPS;      // pixel sets (2 for C = 32, 1 for C = 64)
+    constexpr int IWS = 144;           // staged image row pitch (>= (PW-1)*stride + 5)
+    __shared__ float s_img[15][IWS];
+    __shared__ __align__(16) float s_t[128 * C];
+    const int tid = threadIdx.x;
+    const int set = tid / TPS;
+    const int r = tid - set * TPS;
+    const int g = r / CQ, cq = r - g * CQ;
+    const bool active = set < PS;
+    float acc[5][4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long lines = (long long)N * PH;
+    const long long l0 = (long long)blockIdx.x * rows_per_block;
+    const long long l1 = min(lines, l0 + rows_per_block);
+    const int span = (PW - 1) * stride + 5;  // staged columns: ix = -2 .. (PW-1)*stride + 2
+    const int half = (PW + PS - 1) / PS;
+    for (long long line = l0; line < l1; ++line) {
+        const int n = (int)(line / PH), py = (int)(line - (long long)n * PH);
+        const int sidx = n / n_per_src;
+        const float* img = (sidx == 0 ? src0 : (sidx == 1 ? src1 : src2)) + (long long)(n - sidx * n_per_src) * 3 * IH * IW;
+        __syncthreads();
+        for (int i = tid; i < 15 * span; i += 256) {
+            const int row = i / span, col = i - row * span;
+            const int c3 = row / 5, kh = row - c3 * 5;
+            const int iy = py * stride + sg * (kh - 2), ix = col - 2;
+            float v = 0.f;
+            if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = __ldg(img + ((long long)c3 * IH + iy) * IW + ix);
+            s_img[row][col] = v;
+        }
+        const Tt* trow = T + line * (long long)PW * C;
+        for (int i = tid; i < PW * C; i += 256) s_t[i] = ld_f(trow + i);
+        __syncthreads();
+        if (active) {
+            const int p0 = set * half, p1 = min(PW, p0 + half);
+            const float* ir = s_img[g];
+            if (stride == 1) {
+                float w0 = ir[p0], w1 = ir[p0 + 1], w2 = ir[p0 + 2], w3 = ir[p0 + 3];
+                for (int px = p0; px < p1; ++px) {
+                    const float w4 = ir[px + 4];
+                    const float4 t = *reinterpret_cast<const float4*>(s_t + px * C + cq * 4);
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[0][j] += w0 * tv[j];
+                        acc[1][j] += w1 * tv[j];
+                        acc[2][j] += w2 * tv[j];
+                        acc[3][j] += w3 * tv[j];
+                        acc[4][j] += w4 * tv[j];
+                    }
+                    if (g == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bsum[j] += tv[j];
+                    }
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+                }
+            } else {
+                for (int px = p0; px < p1; ++px) {
+                    const float* w = ir + px * stride;
+                    const float4 t = *reinterpret_cast<const float4*>(s_t + px * C + cq * 4);
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float wv = w[k];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[k][j] += wv * tv[j];
+                    }
+                    if (g == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bsum[j] += tv[j];
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    // staged column k' of the window corresponds to ix = px*stride - 2 + k' = px*stride + sg*(kw-2)  ->  kw = sg > 0 ? k' : 4 - k'
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int kw = sg > 0 ? k : 4 - k;
+        float* o = dwk + (size_t)(g * 5 + kw) * C + cq * 4;  // g = c3*5 + kh -> (c3*25 + kh*5 + kw)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(o + j, acc[k][j]);
+    }
+    if (dbias && g == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dbias + cq * 4 + j, bsum[j]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Simple fp32 SIMT GEMM family (exact mode and small shapes): C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias, act)
 // with arbitrary element strides so that the transposed products of dgrad / wgrad reuse it.
@@ -553,8 +661,35 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const Tx* __restrict
     }
 }
 
-// backward pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat)); dgamma = sum_gx, dbeta = sum_g (written by
-// block 0). `train`=0 (eval-mode BN: statistics are constants): dx = gamma*invstd*g.
+// backward pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat)). `train`=0 (eval-mode BN: statistics are
+// constants): dx = gamma*invstd*g. 8 channels-last elements per thread (C % 8 == 0), 128-bit loads/stores; the
+// per-channel means are taken once per channel in fp64 (sum/count) and rounded to fp32.
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[2 * j] = __uint_as_float(rr[j] << 16);
+            v[2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+        }
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
 template <typename Tx, typename Tg>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy,
                                                            Tg* __restrict__ dx, long long total, int C, double count,
@@ -564,17 +699,36 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
                                                            const float* __restrict__ beta, int relu, int train,
                                                            const double* __restrict__ sum_g,
                                                            const double* __restrict__ sum_gx) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const float is = invstd[c], ga = gamma[c];
-        const float xc = ld_f(x + i) - mean[c];
-        const float xh = xc * is;
-        float g = ld_f(dy + i);
-        if (relu && !(xc * (ga * is) + beta[c] > 0.f)) g = 0.f;
-        float r = g;
-        if (train) r = g - (float)(sum_g[c] / count) - xh * (float)(sum_gx[c] / count);
-        st_f(dx + i, ga * is * r);
+    const long long step = (long long)gridDim.x * blockDim.x * 8;
+    long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+    if (i >= total) return;
+    // when step % C == 0 every iteration of this thread sees the same 8 channels: hoist the coefficients
+    const bool hoist = (step % C) == 0;
+    float mu[8], is[8], sc[8], be[8], mg[8], mgx[8];
+    int c0 = -1;
+    for (; i < total; i += step) {
+        const int cc = (int)(i % C);
+        if (!hoist || c0 < 0) {
+            c0 = cc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = cc + j;
+                mu[j] = mean[c]; is[j] = invstd[c]; sc[j] = gamma[c] * is[j]; be[j] = beta[c];
+                mg[j] = train ? (float)(sum_g[c] / count) : 0.f;
+                mgx[j] = train ? (float)(sum_gx[c] / count) : 0.f;
+            }
+        }
+        float xv[8], gv[8], o[8];
+        ld8(x + i, xv);
+        ld8(dy + i, gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xc = xv[j] - mu[j];
+            float g = gv[j];
+            if (relu && !(xc * sc[j] + be[j] > 0.f)) g = 0.f;
+            o[j] = sc[j] * (g - mg[j] - (xc * is[j]) * mgx[j]);
+        }
+        st8(dx + i, o);
     }
 }
 

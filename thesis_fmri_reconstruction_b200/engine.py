@@ -22,34 +22,12 @@ import torch
 
 from . import lib as L
 from . import nets as NN
+from .dp import FlatBucket
 from .nets import BF16, F32, E, Z
 
 
-class Bucket:
-    """Flat fp32 parameter / gradient / optimizer-state buffers of one sub-network; the named tensors are views."""
-
-    def __init__(self, prefix, named_params, n_states):
-        self.prefix = prefix
-        self.names = list(named_params)
-        sizes = [named_params[k].numel() for k in self.names]
-        offs, o = [], 0
-        for s in sizes:
-            offs.append(o)
-            o += (s + 3) // 4 * 4  # keep every tensor 16-byte aligned inside the flat buffer
-        self.numel = o
-        self.flat_p, self.flat_g = Z(o), Z(o)
-        self.states = [Z(o) for _ in range(n_states)]
-        self.P, self.G = OrderedDict(), OrderedDict()
-        for k, off, s in zip(self.names, offs, sizes):
-            shape = named_params[k].shape
-            self.P[k] = self.flat_p[off:off + s].view(shape)
-            self.G[k] = self.flat_g[off:off + s].view(shape)
-            self.P[k].copy_(named_params[k])
-        self.offsets = dict(zip(self.names, zip(offs, sizes)))
-
-    def state_view(self, i, name):
-        off, s = self.offsets[name]
-        return self.states[i][off:off + s].view(self.P[name].shape)
+def Bucket(prefix, named_params, n_states):
+    return FlatBucket(prefix, named_params, n_states, "cuda")
 
 
 def _split(full, prefix):

@@ -235,10 +235,10 @@ def edge_in_dgrad(d, dy, w, dimg, ws):
     _check(load().fmri_edge_in_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(dimg), ptr(ws), _wsb(ws), stream()))
 
 
-def edge_in_wgrad(d, imgs, n_per_src, dy, dw, accumulate, ws):
+def edge_in_wgrad(d, imgs, n_per_src, dy, dw, accumulate, ws, dbias=None):
     i0, i1, i2 = (list(imgs) + [None, None])[:3]
-    _require_cuda(i0, i1, i2, dy, dw, ws)
-    _check(load().fmri_edge_in_wgrad(C.byref(d), ptr(i0), ptr(i1), ptr(i2), n_per_src, ptr(dy), ptr(dw),
+    _require_cuda(i0, i1, i2, dy, dw, ws, dbias)
+    _check(load().fmri_edge_in_wgrad(C.byref(d), ptr(i0), ptr(i1), ptr(i2), n_per_src, ptr(dy), ptr(dw), ptr(dbias),
                                      int(accumulate), ptr(ws), _wsb(ws), stream()))
 
 

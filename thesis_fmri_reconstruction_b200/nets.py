@@ -467,10 +467,7 @@ class DiscriminatorNet:
         L.relu_backward(c.y0, dy0, dpre)
         OH, OW = c.hw0
         if need_dw:
-            L.edge_in_wgrad(c.d0, c.imgs, c.Bs, dpre, G["conv.0.0.weight"], acc, self._ews)
-            if not acc:
-                G["conv.0.0.bias"].zero_()
-            L.colsum(dpre, c.N * OH * OW, self.C0, G["conv.0.0.bias"])
+            L.edge_in_wgrad(c.d0, c.imgs, c.Bs, dpre, G["conv.0.0.weight"], acc, self._ews, G["conv.0.0.bias"])
         if img_slices is None:
             return None
         s0, s1 = img_slices
