@@ -3,7 +3,7 @@ same seeded inputs and weights.
 
 Tolerances (rel-L2 per tensor, vs the fp32 oracle on CPU):
   fp32 exact path : forward tensors / losses 1e-4; BN buffers 1e-4; gradient buckets vs the fp64 oracle:
-                    max(1e-3, 3 x the oracle's own fp32-vs-fp64 deviation measured in the same run) -- end-to-end gradients
+                    max(5e-3, 3 x the oracle's own fp32-vs-fp64 deviation measured in the same run) -- end-to-end gradients
                     are dominated by single ReLU-mask flips (1e-3..2e-3 for the reference against itself).
   bf16 tensor path: forward tensors / losses 2e-2 (north_star); end-to-end gradient buckets are REPORTED and bounded
                     loosely (0.5) because thousands of ReLU masks flip under bf16 rounding -- CPU bf16 autocast of the
@@ -86,7 +86,7 @@ def test_stage1_vaegan_fp32_exact_path():
     rep = run_case(8, torch.float32)
     assert max(rep["forward"].values()) < 1e-4, rep["forward"]
     for b, e in rep["grad_bucket"].items():
-        assert e < max(1e-3, 3 * rep["grad_bucket_oracle_fp32_noise"][b]), (b, e, rep["grad_bucket_oracle_fp32_noise"])
+        assert e < max(5e-3, 3 * rep["grad_bucket_oracle_fp32_noise"][b]), (b, e, rep["grad_bucket_oracle_fp32_noise"])
     assert rep["bn_worst"][1] < 1e-4 and rep["gate_ok"] and rep["nbt_ok"]
 
 

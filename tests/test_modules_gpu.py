@@ -1,0 +1,210 @@
+"""The nn.Module drop-in surface (models/vae_gan.py) driven exactly like the reference's training scripts, against the
+CPU oracle: strict state_dict loading with the reference's key names, the Stage-I VAE/GAN script sequence INCLUDING the
+interleaved backward(retain_graph=True) / optimizer.step() order of train_vgan_stage1.py:408-432 (which stock torch >= 1.5
+rejects on the reference's own modules), the WAE Stage-I script sequence (train_wae_stage1.py:263-311), and eval mode.
+
+Tolerances (rel-L2): fp32 exact path -- forward 1e-4, gradient buckets max(5e-3, 3 x the oracle's fp32-vs-fp64 noise);
+bf16 tensor path -- forward 2e-2, gradient buckets reported and bounded at 0.5 (ReLU-mask flips).
+"""
+import contextlib
+
+import pytest
+import torch
+
+import configs.models_config as mc
+from oracle import vaegan as O
+from thesis_fmri_reconstruction_b200 import autograd as ag
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@contextlib.contextmanager
+def patched_randn(value):
+    orig = torch.randn
+    torch.randn = lambda *a, **k: value.clone()
+    try:
+        yield
+    finally:
+        torch.randn = orig
+
+
+@contextlib.contextmanager
+def compute(dtype):
+    old = ag.compute_dtype()
+    ag.set_compute_dtype(dtype)
+    try:
+        yield
+    finally:
+        ag.set_compute_dtype(old)
+
+
+def bucket_err(grads, ref, pre):
+    a = torch.cat([grads[k].reshape(-1).cpu() for k in ref if k.startswith(pre)])
+    r = torch.cat([ref[k].reshape(-1) for k in ref if k.startswith(pre)])
+    return rel(a, r)
+
+
+def build_vaegan(P, S):
+    mc.use_resolution(64)
+    from models.vae_gan import VaeGan
+
+    model = VaeGan(device="cuda", z_size=128)
+    missing, unexpected = model.load_state_dict({**P, **S}, strict=True)   # the reference's key names, strictly
+    assert not missing and not unexpected
+    return model
+
+
+@pytest.mark.parametrize("dtype,B", [(torch.float32, 8), (torch.bfloat16, 16)])
+def test_stage1_script_sequence(dtype, B):
+    from models.vae_gan import VaeGan
+
+    seed = 31
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_vaegan_step(P, S_ref, x, eps, z_p)
+    ref64 = O.stage1_vaegan_step({k: v.double() for k, v in P.items()},
+                                 {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in S.items()},
+                                 x.double(), eps.double(), z_p.double(), update=False)
+    hp = O.HP_VGAN
+    with compute(dtype):
+        model = build_vaegan(P, S)
+        model.train()
+        eps_d = eps.cuda()
+        model.reparameterize = lambda mu, lv: ag.reparameterize(mu, lv, eps_d)
+        opt = {b: torch.optim.RMSprop(getattr(model, b).parameters(), lr=hp["lr"], alpha=0.9, eps=1e-8)
+               for b in ("encoder", "decoder", "discriminator")}
+        with patched_randn(z_p):
+            x_tilde, disc_class, disc_layer, mus, lv = model(x)                      # train_vgan_stage1.py:330
+        dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]
+        dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
+        nle, kld, mse, bo, bp, bs = VaeGan.loss(x.cuda(), x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)
+        loss_encoder = torch.sum(kld) + torch.sum(mse)
+        loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+        loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator
+        grads = {}
+        # the script's own order, optimizer steps interleaved (train_vgan_stage1.py:408-432)
+        model.zero_grad()
+        loss_encoder.backward(retain_graph=True)
+        grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters()})
+        opt["encoder"].step()
+        model.zero_grad()
+        loss_decoder.backward(retain_graph=True)
+        grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+        opt["decoder"].step()
+        model.discriminator.zero_grad()
+        loss_discriminator.backward()
+        grads.update({"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()})
+        opt["discriminator"].step()
+        torch.cuda.synchronize()
+    ftol = 1e-4 if dtype == torch.float32 else 2e-2
+    fwd = dict(x_tilde=rel(x_tilde, ref["x_tilde"]), disc_layer=rel(disc_layer, ref["disc_layer"]),
+               disc_class=rel(disc_class, ref["disc_class"]), mu=rel(mus, ref["mu"]), logvar=rel(lv, ref["logvar"]),
+               kl=rel(kld, ref["kl"]), mse=rel(mse, ref["mse"]), bce_o=rel(bo, ref["bce_o"]),
+               loss_encoder=rel(loss_encoder, ref["loss_encoder"]), loss_decoder=rel(loss_decoder, ref["loss_decoder"]))
+    print(dtype, "forward", fwd)
+    assert max(fwd.values()) < ftol, fwd
+    for pre in ("encoder.", "decoder.", "discriminator."):
+        e = bucket_err(grads, ref64["grads"], pre)
+        noise = bucket_err(ref["grads"], ref64["grads"], pre)
+        print(dtype, pre, "grad rel-L2 vs fp64 oracle", e, "oracle fp32 noise", noise)
+        assert e < (max(5e-3, 3 * noise) if dtype == torch.float32 else 0.5), (pre, e, noise)
+    sd = model.state_dict()
+    for k, v in S_ref.items():   # BN running statistics incl. the discriminator's double update, num_batches_tracked
+        if v.dtype.is_floating_point:
+            assert rel(sd[k], v) < ftol, k
+        else:
+            assert int(sd[k]) == int(v), k
+
+
+@pytest.mark.parametrize("dtype,B", [(torch.float32, 8), (torch.bfloat16, 16)])
+def test_wae_stage1_script_sequence(dtype, B):
+    mc.use_resolution(64)
+    from models.vae_gan import WaeGan
+
+    seed = 57
+    P, S = O.make_waegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    z_fake = O.synthetic_noise(B, 128, seed=seed)[0] * 0.5
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_waegan_step(P, S_ref, x, z_fake)
+    hp = O.HP_WAE
+
+    def freeze(m, on):
+        for p in m.parameters():
+            p.requires_grad = not on
+
+    with compute(dtype):
+        model = WaeGan(device="cuda", z_size=128)
+        model.load_state_dict({**P, **S}, strict=True)
+        model.train()
+        xd, zf = x.cuda(), z_fake.cuda()
+        opt_e = torch.optim.Adam(model.encoder.parameters(), lr=hp["lr"], betas=(0.5, 0.999))
+        opt_d = torch.optim.Adam(model.decoder.parameters(), lr=hp["lr"], betas=(0.5, 0.999))
+        opt_c = torch.optim.Adam(model.discriminator.parameters(), lr=0.5 * hp["lr"], betas=(0.5, 0.999))
+        model.encoder.zero_grad(); model.decoder.zero_grad(); model.discriminator.zero_grad()
+        freeze(model.decoder, True); freeze(model.encoder, True); freeze(model.discriminator, False)
+        z_real, _ = model.encoder(xd)
+        d_real = model.discriminator(z_real)
+        d_fake = model.discriminator(zf)
+        loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))
+        loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))
+        loss_fake.backward(retain_graph=True)
+        loss_real.backward(retain_graph=True)
+        grads = {"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()}
+        opt_c.step()
+        freeze(model.encoder, False); freeze(model.decoder, False); freeze(model.discriminator, True)
+        z_real2, _ = model.encoder(xd)
+        x_recon = model.decoder(z_real2)
+        d_real2 = model.discriminator(z_real2)
+        loss_rec = torch.sum(torch.sum(0.5 * (x_recon - xd) ** 2, 1))
+        loss_pen = -10 * torch.sum(torch.log(d_real2 + 1e-3))
+        loss_rec.backward(retain_graph=True)
+        loss_pen.backward()
+        assert model.encoder.l_var.weight.grad is None          # logvar is unused: Adam must skip it as in the reference
+        grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters() if p.grad is not None})
+        grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+        opt_e.step(); opt_d.step()
+        torch.cuda.synchronize()
+    ftol = 1e-4 if dtype == torch.float32 else 2e-2
+    fwd = dict(z_real=rel(z_real, ref["z_real"]), d_real=rel(d_real, ref["d_real"]), d_fake=rel(d_fake, ref["d_fake"]),
+               x_recon=rel(x_recon, ref["x_recon"]), loss_rec=rel(loss_rec, ref["loss_reconstruction"]),
+               loss_pen=rel(loss_pen, ref["loss_penalty"]), loss_fake=rel(loss_fake, ref["loss_discriminator_fake"]))
+    print(dtype, "forward", fwd)
+    assert max(fwd.values()) < ftol, fwd
+    for pre in ("encoder.", "decoder.", "discriminator."):
+        e = bucket_err(grads, ref["grads"], pre)
+        print(dtype, pre, "grad rel-L2 vs fp32 oracle", e)
+        assert e < (5e-3 if dtype == torch.float32 else 0.5), (pre, e)
+    assert int(model.state_dict()["encoder.conv.0.bn.num_batches_tracked"]) == 2   # two encoder forwards per step
+
+
+def test_eval_mode_and_cpu_refusal():
+    from thesis_fmri_reconstruction_b200.lib import FmriError
+
+    seed = 5
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    for k in S:  # non-trivial running statistics
+        if k.endswith("running_mean"):
+            S[k] = 0.05 * torch.randn(S[k].shape, generator=torch.Generator().manual_seed(1))
+        if k.endswith("running_var"):
+            S[k] = 1.0 + 0.2 * torch.rand(S[k].shape, generator=torch.Generator().manual_seed(2))
+    x = O.synthetic_images(4, seed=seed)
+    mu, lv = O.encoder(P, {k: v.clone() for k, v in S.items()}, x, O.CFG64, train=False)
+    img = O.decoder(P, {k: v.clone() for k, v in S.items()}, mu, O.CFG64, train=False)
+    with compute(torch.float32):
+        model = build_vaegan(P, S)
+        model.eval()
+        with torch.no_grad():
+            m2, l2 = model.encoder(x.cuda())
+            im2 = model.decoder(m2)
+        assert rel(m2, mu) < 1e-4 and rel(l2, lv) < 1e-4 and rel(im2, img) < 1e-4
+        assert int(model.state_dict()["encoder.conv.0.bn.num_batches_tracked"]) == 0
+        with pytest.raises(FmriError):
+            model.encoder(x)  # CPU input: no fallback path

@@ -111,40 +111,43 @@ static int make_act_map(CUtensorMap* m, const void* base, int C, int X, int Y, i
 }
 
 // ------------------------------------------------------------------------------------------------ igemm launch
-template <int BN, int KCH, int STAGES>
-static int launch_ig(const IgParams& p, dim3 grid, cudaStream_t st) {
-    using L = IgSmem<BN, KCH, STAGES>;
+template <int BN, int KCH, int STAGES, int MT>
+static int launch_ig(const IgParams& p, int classes, cudaStream_t st) {
+    using L = IgSmem<BN, KCH, STAGES, MT>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, KCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, KCH, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      L::TOTAL));
         attr_done = true;
     }
-    igemm_kernel<BN, KCH, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    dim3 grid(cdiv((long long)p.tiles_x * p.tiles_y * p.tiles_n, MT), p.n_tiles * p.splits, classes);
+    igemm_kernel<BN, KCH, STAGES, MT><<<grid, 192, L::TOTAL, st>>>(p);
     LAUNCH_OK();
     return 0;
 }
 static int dispatch_ig(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
-    dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, p.n_tiles * p.splits, classes);
+    // two M sub-tiles per CTA (shared weight tile) once there is more than a few waves of work
+    const long long ctas = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.splits * classes;
+    const bool mt2 = ctas >= 6 * 148 && p.splits == 1;
     if (KCH == 64) {
         switch (BN) {
-            case 256: return launch_ig<256, 64, 4>(p, grid, st);
-            case 128: return launch_ig<128, 64, 4>(p, grid, st);
-            case 64: return launch_ig<64, 64, 4>(p, grid, st);
-            case 32: return launch_ig<32, 64, 4>(p, grid, st);
+            case 256: return mt2 ? launch_ig<256, 64, 3, 2>(p, classes, st) : launch_ig<256, 64, 4, 1>(p, classes, st);
+            case 128: return mt2 ? launch_ig<128, 64, 4, 2>(p, classes, st) : launch_ig<128, 64, 4, 1>(p, classes, st);
+            case 64: return mt2 ? launch_ig<64, 64, 4, 2>(p, classes, st) : launch_ig<64, 64, 4, 1>(p, classes, st);
+            case 32: return mt2 ? launch_ig<32, 64, 4, 2>(p, classes, st) : launch_ig<32, 64, 4, 1>(p, classes, st);
         }
     } else if (KCH == 32) {
         switch (BN) {
-            case 256: return launch_ig<256, 32, 4>(p, grid, st);
-            case 128: return launch_ig<128, 32, 4>(p, grid, st);
-            case 64: return launch_ig<64, 32, 4>(p, grid, st);
-            case 32: return launch_ig<32, 32, 4>(p, grid, st);
+            case 256: return mt2 ? launch_ig<256, 32, 4, 2>(p, classes, st) : launch_ig<256, 32, 4, 1>(p, classes, st);
+            case 128: return mt2 ? launch_ig<128, 32, 4, 2>(p, classes, st) : launch_ig<128, 32, 4, 1>(p, classes, st);
+            case 64: return mt2 ? launch_ig<64, 32, 4, 2>(p, classes, st) : launch_ig<64, 32, 4, 1>(p, classes, st);
+            case 32: return mt2 ? launch_ig<32, 32, 4, 2>(p, classes, st) : launch_ig<32, 32, 4, 1>(p, classes, st);
         }
     }
     return fail(FMRI_ERR_UNSUPPORTED, "igemm tile BN=%d KCH=%d not instantiated", BN, KCH);
 }
 static int pick_bn(int n_total, long long m_tiles_times_classes) {
-    if (n_total % 256 == 0 && m_tiles_times_classes * (n_total / 256) >= 2 * 148) return 256;
+    if (n_total % 256 == 0 && m_tiles_times_classes * (n_total / 256) >= 148) return 256;
     if (n_total % 128 == 0) return 128;
     if (n_total % 64 == 0) return 64;
     if (n_total % 32 == 0) return 32;

@@ -54,9 +54,12 @@ struct IgParams {
     double* stat_sq;
 };
 
-template <int BN, int KCH, int STAGES>
+// MT = number of 128-row M sub-tiles one CTA accumulates against the SAME B (weight) tile: the kernels are bound by
+// L2 -> shared-memory bandwidth (~43 B/clk/SM measured chip-wide), and MT = 2 halves the weight bytes per FLOP.
+template <int BN, int KCH, int STAGES, int MT = 1>
 struct IgSmem {
-    static constexpr int A_BYTES = 128 * KCH * 2;
+    static constexpr int A_SUB = 128 * KCH * 2;
+    static constexpr int A_BYTES = MT * A_SUB;
     static constexpr int B_BYTES = BN * KCH * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
@@ -103,9 +106,9 @@ __device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
     return f[0];
 }
 
-template <int BN, int KCH, int STAGES>
+template <int BN, int KCH, int STAGES, int MT>
 __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgParams p) {
-    using L = IgSmem<BN, KCH, STAGES>;
+    using L = IgSmem<BN, KCH, STAGES, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -117,23 +120,32 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- which tile
+    // ---- which tiles (MT consecutive M tiles share this CTA's weight tiles)
     const TapClass& c = p.cls[blockIdx.z];
-    const int mt = blockIdx.x;
-    const int tx = mt % p.tiles_x;
-    const int ty = (mt / p.tiles_x) % p.tiles_y;
-    const int tn = mt / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+    const int total_mt = p.tiles_x * p.tiles_y * p.tiles_n;
+    int x0[MT], y0[MT], n0[MT];
+    bool live[MT];
+    bool any = false;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int mt = blockIdx.x * MT + m;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tn = mt / (p.tiles_x * p.tiles_y);
+        x0[m] = tx * p.bw; y0[m] = ty * p.bh; n0[m] = tn * p.bn;
+        live[m] = mt < total_mt && x0[m] < c.lim_x && y0[m] < c.lim_y;  // tile inside this parity class' sub-grid
+        any |= live[m];
+    }
     const int nt = blockIdx.y % p.n_tiles;
     const int split = blockIdx.y / p.n_tiles;
-    if (x0 >= c.lim_x || y0 >= c.lim_y) return;  // tile outside this parity class' sub-grid
+    if (!any) return;
     const int ks_total = c.num_taps * p.num_chunks;
     const int ks_begin = (int)((long long)split * ks_total / p.splits);
     const int ks_end = (int)((long long)(split + 1) * ks_total / p.splits);
     if (ks_begin >= ks_end) return;
     const int nks = ks_end - ks_begin;
 
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = (MT * BN) < 32 ? 32 : (MT * BN);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.mapA[0]);
         tma_prefetch_desc(&p.mapB);
@@ -154,17 +166,24 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            int nlive = 0;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) nlive += live[m] ? 1 : 0;
             for (int i = 0; i < nks; ++i) {
                 const int st = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + L::B_BYTES);
+                mbar_arrive_expect_tx(&full_bar[st], nlive * p.a_bytes + L::B_BYTES);
                 const int ks = ks_begin + i;
                 const int tap = ks / p.num_chunks;
                 const int ch = ks - tap * p.num_chunks;
                 const TapDesc t = c.taps[tap];
                 uint8_t* sa = smem + st * L::STAGE_BYTES;
-                tma_load_4d(sa, &p.mapA[t.map], &full_bar[st], ch * KCH, x0 + t.dx, y0 + t.dy, n0);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    if (live[m])
+                        tma_load_4d(sa + m * L::A_SUB, &p.mapA[t.map], &full_bar[st], ch * KCH, x0[m] + t.dx,
+                                    y0[m] + t.dy, n0[m]);
                 tma_load_2d(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, t.brow + nt * BN);
             }
         }
@@ -181,11 +200,15 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
-                const uint64_t adesc = umma_smem_desc(sa, 16, sbo, layout);
                 const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout);
 #pragma unroll
-                for (int k = 0; k < KCH / 16; ++k)
-                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                for (int m = 0; m < MT; ++m) {
+                    if (!live[m]) continue;
+                    const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
+#pragma unroll
+                    for (int k = 0; k < KCH / 16; ++k)
+                        umma_bf16(tmem_base + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                }
                 umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs retire
             }
             umma_commit(tmem_full);
@@ -200,74 +223,78 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
         const int xi = row % p.bw;
         const int yi = (row / p.bw) % p.bh;
         const int ni = row / (p.bw * p.bh);
-        const bool valid = (ni < p.bn) && (n0 + ni < p.lim_n) && (y0 + yi < c.lim_y) && (x0 + xi < c.lim_x);
-        const long long off = c.out_off + (long long)(n0 + ni) * p.out_sn + (long long)(y0 + yi) * p.out_sy +
-                              (long long)(x0 + xi) * p.out_sx + (long long)nt * BN;
         const bool do_stats = p.stat_sum != nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            float f[32];
+        for (int m = 0; m < MT; ++m) {
+            if (!live[m]) continue;
+            const bool valid = (ni < p.bn) && (n0[m] + ni < p.lim_n) && (y0[m] + yi < c.lim_y) && (x0[m] + xi < c.lim_x);
+            const long long off = c.out_off + (long long)(n0[m] + ni) * p.out_sn + (long long)(y0[m] + yi) * p.out_sy +
+                                  (long long)(x0[m] + xi) * p.out_sx + (long long)nt * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * BN + c0, v);
+                tmem_ld_wait();
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias && split == 0) {  // split-K: exactly one split adds the bias
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias && split == 0) {  // split-K: exactly one split adds the bias
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
-            }
-            if (p.act == ACT_RELU) {
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
+                }
+                if (p.act == ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (p.act == ACT_TANH) {
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (p.act == ACT_TANH) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-            } else if (p.act == ACT_SIGMOID) {
+                    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
-            }
-            if (p.out_fp32) {
-                if (valid) {
-                    float* o = reinterpret_cast<float*>(p.out) + off + c0;
-                    if (p.atomic_out) {
+                    for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+                }
+                if (p.out_fp32) {
+                    if (valid) {
+                        float* o = reinterpret_cast<float*>(p.out) + off + c0;
+                        if (p.atomic_out) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
+                            for (int j = 0; j < 32; j += 4) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                    }
+                } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    if (valid) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(o + 8 * j) =
+                                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                    if (do_stats) {  // statistics of exactly what was stored (bf16-rounded)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[2 * j] = __uint_as_float(pk[j] << 16);
+                            f[2 * j + 1] = __uint_as_float(pk[j] & 0xffff0000u);
+                        }
                     }
                 }
-            } else {
-                uint32_t pk[16];
+                if (do_stats) {
+                    float g[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                if (valid) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(o + 8 * j) =
-                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                }
-                if (do_stats) {  // statistics of exactly what was stored (bf16-rounded)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        f[2 * j] = __uint_as_float(pk[j] << 16);
-                        f[2 * j + 1] = __uint_as_float(pk[j] & 0xffff0000u);
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = valid ? f[j] : 0.f;
+                        g[j] = f[j] * f[j];
                     }
+                    const float s1 = warp_colsum32(f, lane);
+                    const float s2 = warp_colsum32(g, lane);
+                    atomicAdd(&s_stat[c0 + lane], s1);
+                    atomicAdd(&s_stat[BN + c0 + lane], s2);
                 }
-            }
-            if (do_stats) {
-                float g[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    f[j] = valid ? f[j] : 0.f;
-                    g[j] = f[j] * f[j];
-                }
-                const float s1 = warp_colsum32(f, lane);
-                const float s2 = warp_colsum32(g, lane);
-                atomicAdd(&s_stat[c0 + lane], s1);
-                atomicAdd(&s_stat[BN + c0 + lane], s2);
             }
         }
         tc_fence_before();
