@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 # algorithmic MFLOP per sample per optimisation step (2 x MACs of the necessary GEMMs only)
 ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8}
-METRIC = "stage1_vaegan_train_samples_per_sec_64x64"
+METRIC = "stage1_vaegan_train_samples_per_sec_64x64"  # BASELINE.json metric; other workloads rename it below
 
 
 def parse():
@@ -325,7 +325,9 @@ def run_ours(args):
 
 
 def main():
+    global METRIC
     args = parse()
+    METRIC = f"{args.workload}_train_samples_per_sec_64x64"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -95,3 +95,54 @@ def test_stage1_vaegan_bf16_tensor_path():
     assert max(rep["forward"].values()) < 2e-2, rep["forward"]
     assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
     assert rep["bn_worst"][1] < 2e-2 and rep["gate_ok"] and rep["nbt_ok"]
+
+
+def run_wae_case(B, adt, seed=777):
+    P, S = O.make_waegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    z_fake = O.synthetic_noise(B, 128, seed=seed)[0] * 0.5
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_waegan_step(P, S_ref, x, z_fake)
+    tr = engine.WaeGanStage1(P, S, hp.CFG64, 128, adt)
+    out = tr.step(x.cuda(), z_fake.cuda())
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = dict(z_real=rel(out["z_real"], ref["z_real"]), x_recon=rel(out["x_recon"], ref["x_recon"]),
+               d_real=rel(out["d_real"], ref["d_real"].reshape(-1)), d_fake=rel(out["d_fake"], ref["d_fake"].reshape(-1)),
+               d_real_g=rel(out["d_real_g"], ref["d_real_g"].reshape(-1)))
+    for k in ("loss_discriminator_fake", "loss_discriminator_real", "loss_reconstruction", "loss_penalty"):
+        fwd[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    grads = tr.named_grads()
+    gerr = {}
+    for b in ("encoder.", "decoder."):   # the discriminator's flat_g holds the D-phase gradient, also checked
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    ks = [k for k in ref["grads"] if k.startswith("discriminator.")]
+    gerr["discriminator."] = rel(torch.cat([grads[k].reshape(-1) for k in ks]),
+                                 torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    newP = tr.named_parameters()
+    # Adam's first step is lr * sign(g): compare the updated discriminator through its effect (d_real_g above) and the
+    # untouched l_var head exactly
+    lvar_same = all(torch.equal(newP[k].cpu(), P[k]) for k in ("encoder.l_var.weight", "encoder.l_var.bias"))
+    nbt = int(tr.named_buffers()["encoder.conv.0.bn.num_batches_tracked"])
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    rep = dict(B=B, dtype=str(adt), forward=fwd, grad_bucket=gerr, lvar_same=lvar_same, nbt=nbt,
+               bn_worst=max(berr.items(), key=lambda t: t[1]))
+    with open(f"gpurun_out/parity_wae1_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+def test_stage1_waegan_fp32_exact_path():
+    rep = run_wae_case(8, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert rep["lvar_same"] and rep["nbt"] == 2 and rep["bn_worst"][1] < 1e-4
+
+
+def test_stage1_waegan_bf16_tensor_path():
+    rep = run_wae_case(16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["lvar_same"] and rep["nbt"] == 2 and rep["bn_worst"][1] < 2e-2

@@ -213,3 +213,114 @@ class VaeGanStage1(_TrainerBase):
         return dict(loss_encoder=s[3] + s[4], loss_discriminator=loss_dis, loss_decoder=lam * s[4] - (1 - lam) * loss_dis,
                     nle=s[5], bce_o=s[0], bce_p=s[1], bce_s=s[2], kl=s[3], mse=s[4], train_dis=s[8] != 0,
                     train_dec=s[9] != 0)
+
+
+class WaeGanStage1(_TrainerBase):
+    """Stage-I WAE/GAN trainer (/root/reference/train/train_wae_stage1.py:259-311): visual Encoder, Decoder, latent
+    WaeDiscriminator, three Adam(betas=(0.5, 0.999)) optimizers (the discriminator at lr / 2).
+
+    D-phase: z_real = encoder(x) (encoder / decoder frozen), L_fake = -10 sum log(d(z_fake) + 1e-3),
+    L_real = -10 sum log(1 - d(z_real) + 1e-3), Adam step on the discriminator. G-phase: the reference runs the encoder a
+    second time on unchanged weights (:296) -- same z_real, so it is computed once and the BN running statistics are
+    updated twice; x_recon = decoder(z_real), d(z_real) with the UPDATED discriminator, L_rec = sum 0.5 (x_recon - x)^2,
+    L_pen = -10 sum log(d + 1e-3); Adam on the encoder (grad of L_rec + L_pen; l_var gets none) and the decoder (L_rec).
+    """
+
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None):
+        from .hp import HP_WAE
+
+        self.cfg, self.z, self.adt = cfg, z, adt
+        self.hp = dict(HP_WAE if hp is None else hp)
+        self.enc = NN.EncoderNet(cfg, z, adt)
+        self.dec = NN.DecoderNet(cfg, z, adt)
+        self.dis = NN.WaeDiscriminatorNet(z, adt)
+        dev = torch.device("cuda")
+        self.buckets = OrderedDict()
+        self.nets = OrderedDict((("encoder.", self.enc), ("decoder.", self.dec), ("discriminator.", self.dis)))
+        for pre, net in self.nets.items():
+            named = _split(params, pre)
+            diff = set(net.param_names()) ^ set(named)
+            if diff:
+                raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(diff)}")
+            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named), 2)
+        self.S = OrderedDict((k, v.to(dev).clone()) for k, v in buffers.items())
+        self.Ssub = {pre: _split(self.S, pre) for pre in self.buckets}
+        self.nbt = {}
+        self.sc = Z(16)  # [0..3] = L_fake, L_real, L_rec, L_pen (sums)
+        self.lr = {"encoder.": float(self.hp["lr"]), "decoder.": float(self.hp["lr"]),
+                   "discriminator.": 0.5 * float(self.hp["lr"])}
+        self.t = 0
+        self._ones_buf = None
+        self._setup_dist(dist_group)
+        for pre, net in self.nets.items():
+            net.refresh(self.buckets[pre].P, inplace=True)
+
+    def _ones(self, n):
+        if self._ones_buf is None or self._ones_buf.numel() < n:
+            self._ones_buf = torch.ones(n, device="cuda")
+        return self._ones_buf
+
+    def _adam(self, pre):
+        b, hp = self.buckets[pre], self.hp
+        L.multi_tensor_adam([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], self.lr[pre], hp["beta1"], hp["beta2"],
+                            hp["eps"], self.t)
+        self.nets[pre].refresh(b.P, inplace=True)
+
+    def step(self, x, z_fake):
+        """x [B,3,H,W] fp32 NCHW, z_fake [B,z] fp32 (= 0.5 * N(0,1), train_wae_stage1.py:276), device resident."""
+        B, z = x.shape[0], self.z
+        be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
+        self.t += 1
+        sc, ones = self.sc, self._ones(B)
+        nbe, nbd = {}, {}
+        # ---------------- discriminator phase (:271-288)
+        ycat, ce = self.enc.forward(be.P, self.Ssub["encoder."], x, True, 2, nbe)
+        z_real = ycat[:, :z]
+        p_real, cr = self.dis.forward(bc.P, z_real)
+        p_fake, cf = self.dis.forward(bc.P, z_fake)
+        l = E(2 * B)
+        L.bce_fwd(p_fake, l[:B], B, True, 10.0)
+        L.bce_fwd(p_real, l[B:], B, False, 10.0)
+        L.vecsum(l[:B], B, 1.0, sc[0:1])
+        L.vecsum(l[B:], B, 1.0, sc[1:2])
+        gp = E(2 * B)
+        L.bce_bwd(p_fake, ones, gp[:B], B, True, 10.0)
+        L.bce_bwd(p_real, ones, gp[B:], B, False, 10.0)
+        self.dis.backward(bc.P, cf, gp[:B], bc.G, False, True, False)
+        self.dis.backward(bc.P, cr, gp[B:], bc.G, True, True, False)
+        self._allreduce_async([bc.flat_g])
+        self._wait_comm()
+        self._adam("discriminator.")
+        # ---------------- generator phase (:292-311)
+        x_recon, cd = self.dec.forward(bd.P, self.Ssub["decoder."], z_real, True, 1, nbd)
+        p_real2, cr2 = self.dis.forward(bc.P, z_real)
+        rec = E(B)
+        L.rowsqdiff_fwd(x_recon, x, rec, B, x[0].numel(), 0.5)
+        L.vecsum(rec, B, 1.0, sc[2:3])
+        L.bce_fwd(p_real2, l[:B], B, True, 10.0)
+        L.vecsum(l[:B], B, 1.0, sc[3:4])
+        dxr = torch.empty_like(x_recon)
+        L.rowsqdiff_bwd(x_recon, x, ones, dxr, None, B, x[0].numel(), 0.5)
+        L.bce_bwd(p_real2, ones, gp[:B], B, True, 10.0)
+        dz_pen = self.dis.backward(bc.P, cr2, gp[:B], None, False, False, True)
+        dz_rec = self.dec.backward(bd.P, cd, 1.0, dxr, 0.0, None, bd.G, False, True, True)
+        self._allreduce_async([bd.flat_g])
+        dmu = E(B, z)
+        L.axpby_tanh_bwd(1.0, dz_rec, 1.0, dz_pen, None, dmu)
+        dycat = Z(B, 2 * z, dtype=self.adt)
+        L.cast2d(dmu, z, dycat[:, :z], 2 * z, B, z)
+        be.flat_g.zero_()  # l_var receives no gradient (logvar unused): its slots stay zero and Adam leaves it unchanged
+        self.enc.backward(be.P, ce, dycat, be.G, False, True, False)
+        self._allreduce_async([be.flat_g, sc[:8]])
+        self._wait_comm()
+        self._adam("encoder.")
+        self._adam("decoder.")
+        for pre, d in (("encoder.", nbe), ("decoder.", nbd)):
+            for k, v in d.items():
+                self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
+        return dict(z_real=z_real, x_recon=x_recon, d_real=p_real, d_fake=p_fake, d_real_g=p_real2)
+
+    def losses(self):
+        s = self.sc.tolist()
+        return dict(loss_discriminator_fake=s[0], loss_discriminator_real=s[1], loss_reconstruction=s[2],
+                    loss_penalty=s[3])
