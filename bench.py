@@ -292,7 +292,7 @@ def run_ours(args):
         dom = max(("igemm", "wgrad"), key=lambda k: fam.get(k, dict(ms=0))["ms"])
         d = fam[dom]
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
-        top = sorted(((k, round(v["ms"] / psteps, 3)) for k, v in fam.items()), key=lambda t: -t[1])[:8]
+        top = sorted(((k, round(v["ms"] / psteps, 3)) for k, v in fam.items()), key=lambda t: -t[1])[:16]
         roof = dict(bound="tensor", kernel=("igemm_kernel (conv/convT fprop+dgrad, linear fprop+dgrad)" if dom == "igemm"
                                             else "wgrad_kernel (conv/convT/linear weight gradients)"),
                     achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None,

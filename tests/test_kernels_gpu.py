@@ -235,7 +235,8 @@ def test_edge_in(C, stride, dtype):
     N, H, W = 6, 16, 16
     g = torch.Generator(device="cpu").manual_seed(6)
     imgs = [torch.randn(N // 3, 3, H, W, generator=g).to(DEV).requires_grad_(True) for _ in range(3)]
-    w = (torch.randn(C, 3, 5, 5, generator=g) * 0.1).to(DEV).requires_grad_(True)
+    # weights pre-rounded to the compute dtype: the tensor path consumes bf16 weight packs (as in the conv tests above)
+    w = rnd((torch.randn(C, 3, 5, 5, generator=g) * 0.1).to(DEV), dtype).requires_grad_(True)
     b = torch.randn(C, generator=g).to(DEV)
     ref = torch.relu(F.conv2d(torch.cat(imgs, 0).double(), w.double(), b.double(), stride=stride, padding=2))
     d = L.edge_desc(N, H, W, C, stride, dtype)
@@ -266,7 +267,7 @@ def test_edge_out(C, dtype):
     N, H, W = 4, 16, 16
     g = torch.Generator(device="cpu").manual_seed(7)
     x = rnd(torch.randn(N, C, H, W, generator=g).to(DEV), dtype).requires_grad_(True)
-    w = (torch.randn(3, C, 5, 5, generator=g) * 0.1).to(DEV).requires_grad_(True)
+    w = rnd((torch.randn(3, C, 5, 5, generator=g) * 0.1).to(DEV), dtype).requires_grad_(True)
     b = torch.randn(3, generator=g).to(DEV)
     # fp64 reference: cuDNN may pick an FFT/Winograd algorithm for a 5x5 stride-1 fp32 conv (1e-3 noise)
     pre = F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=2)

@@ -8,6 +8,7 @@
 #include "../../include/fmri_b200.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "hconv_kernels.cuh"
 
 using namespace fmri;
 
@@ -610,7 +611,67 @@ extern "C" int fmri_conv_wgrad(const fmri_conv_desc* d, const void* x, const voi
 }
 
 // ================================================================================================ edge convs
-extern "C" size_t fmri_edge_workspace(const fmri_edge_desc* d) { return sizeof(float) * 75 * (size_t)d->C; }
+extern "C" size_t fmri_edge_workspace(const fmri_edge_desc* d) {
+    // fp32 [75][C] staging of the SIMT kernels, or the bf16 slab pack [C/8][25*16][8] of the tensor-core path
+    return std::max(sizeof(float) * 75 * (size_t)d->C, (size_t)2 * 25 * 16 * d->C);
+}
+
+// C -> 3 convolution, stride 1, on the halo-tile tcgen05 kernel: img[n,co,y,x] = act(bias + sum_{taps,c} X[n,y+kh-2,x+kw-2,c] * B[tap][co][c])
+// w element (co, c, tap) at w[co*s_co + c*s_c + tap]; flip uses tap 24-tap (data gradient of a 3 -> C convolution).
+// returns 1 when the shape does not fit the halo kernel (caller falls back to the CUDA-core kernel), 0 on success, <0 on error
+static int hconv_c_to_3(const void* X, int N, int H, int W, int C, const float* w, long long s_co, long long s_c, int flip,
+                        const float* bias, int act, float* img, void* ws, cudaStream_t st) {
+    constexpr int BN = 16;
+    if ((C != 32 && C != 64) || W + 4 > 160) return 1;
+    HcParams p;
+    memset(&p, 0, sizeof(p));
+    p.X = reinterpret_cast<const __nv_bfloat16*>(X);
+    p.N = N; p.H = H; p.W = W; p.C = C;
+    p.num_planes = 1;
+    p.pl_ys[0] = p.pl_xs[0] = 1;
+    p.pl_yoff[0] = p.pl_xoff[0] = -2;
+    p.PW = W + 4;
+    p.OH = H; p.OW = W;
+    // rows per tile: as many as 5 sub-tiles of 128 virtual rows hold (fewer if shared memory is short), preferring a divisor of H
+    int tht = std::max(1, std::min(H, (5 * 128) / p.PW));
+    for (;; --tht) {
+        if (tht < 1) return 1;
+        int use = tht;
+        for (int cand = tht; cand >= std::max(1, tht - 2); --cand)
+            if (H % cand == 0) { use = cand; break; }
+        p.THt = use;
+        p.tiles_y = cdiv(H, use);
+        p.MT = cdiv((long long)use * p.PW, 128);
+        p.G = std::max(1, std::min(3, 256 / (p.MT * BN)));  // 2 buffers x G x MT x BN TMEM columns <= 512
+        p.PH = use + 4;
+        const int need = std::max(p.PH * p.PW, p.MT * 128 + 4 * p.PW + 4 + 1);
+        p.slab_rows = (need + 7) / 8 * 8;
+        p.num_taps = 25;
+        if (hc_smem_bytes(p, BN) <= 227 * 1024) break;
+    }
+    for (int kh = 0; kh < 5; ++kh)
+        for (int kw = 0; kw < 5; ++kw) {
+            p.taps[kh * 5 + kw].plane = 0;
+            p.taps[kh * 5 + kw].row_off = kh * p.PW + kw;
+        }
+    p.Bslab = reinterpret_cast<const __nv_bfloat16*>(ws);
+    p.img = img; p.bias = bias; p.act = act; p.n_out = 3; p.accumulate = 0;
+    const int smem = hc_smem_bytes(p, BN);
+    hc_pack_weights_kernel<<<cdiv((long long)C * 25 * BN, 256), 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(ws), C, BN, 3,
+                                                                            25, s_co, s_c, flip);
+    LAUNCH_OK();
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        CUDA_OK(cudaFuncSetAttribute(hconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const int total_tiles = N * p.tiles_y;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / smem));
+    const int grid = std::min(total_tiles, 148 * per_sm);
+    hconv_kernel<BN><<<grid, HC_THREADS, smem, st>>>(p);
+    LAUNCH_OK();
+    return 0;
+}
 static int check_edge(const fmri_edge_desc* d, const void* ws, size_t ws_bytes) {
     if (!d || (d->C != 32 && d->C != 64)) return fail(FMRI_ERR_UNSUPPORTED, "edge conv supports C in {32,64}");
     if (d->stride != 1 && d->stride != 2) return fail(FMRI_ERR_ARG, "edge stride");
@@ -679,6 +740,11 @@ extern "C" int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const
     rc = pack_edge_in(d, w, wk, S(stream));
     if (rc) return rc;
     const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
+    if (d->dtype == FMRI_BF16 && d->stride == 1 && fmri_tensor_path_available()) {
+        // dimg[n,ci,y,x] = sum dy[n,y+kh-2,x+kw-2,c] * w[c][ci][24-tap]  (w layout [C][3][25])
+        rc = hconv_c_to_3(dy, d->N, d->H, d->W, d->C, w, 25, 75, 1, nullptr, 0, dimg, ws, S(stream));
+        if (rc <= 0) return rc;
+    }
     // image pixel gathers from the C-side grid (OH,OW); stride 1: flipped taps, stride 2: divisibility form
     const int flip = d->stride == 1 ? 1 : 0;
     return d->C == 32 ? edge_to3_t<32>(d->dtype, dy, wk, nullptr, dimg, d->N, OH, OW, d->H, d->W, d->stride, flip, 0,
@@ -743,6 +809,11 @@ extern "C" int fmri_edge_out_fprop(const fmri_edge_desc* d, const void* x, const
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
     if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
+    if (d->dtype == FMRI_BF16 && fmri_tensor_path_available()) {
+        // w layout [3][C][25]
+        rc = hconv_c_to_3(x, d->N, d->H, d->W, d->C, w, 25LL * d->C, 25, 0, bias, act, img, ws, S(stream));
+        if (rc <= 0) return rc;
+    }
     float* wk = reinterpret_cast<float*>(ws);
     rc = pack_edge_out(d, w, wk, 0, S(stream));
     if (rc) return rc;
