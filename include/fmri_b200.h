@@ -51,8 +51,10 @@ typedef struct {
 } fmri_conv_desc;
 
 void fmri_conv_out_hw(const fmri_conv_desc* d, int* OH, int* OW);
-/* bf16 tap-major weight packs consumed by the tensor path: pack_f [25][Cout][Cin] (fprop), pack_d [25][Cin][Cout]
- * (dgrad). Each 25*Cin*Cout bf16. Refreshed after every optimizer step. Either pointer may be NULL. */
+/* bf16 weight packs consumed by the tensor path: pack_f (fprop), pack_d (dgrad); the layout is private to the library
+ * (tap-major [25][N][K], plus a parity-merged pack for layers with a 32-channel side). Each buffer holds
+ * fmri_conv_pack_elems(d) bf16 elements. Refreshed after every optimizer step. Either pointer may be NULL. */
+size_t fmri_conv_pack_elems(const fmri_conv_desc* d);
 int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, void* pack_f, void* pack_d, void* stream);
 /* y = act(conv(x, w) + bias); optionally accumulates per-output-channel sum / sum-of-squares of the stored y into
  * fp64 stat_sum/stat_sq[Cout] (BatchNorm batch statistics, vae_gan.py:21). `w` fp32 master weights (used by the fp32

@@ -49,6 +49,7 @@ CONV_CASES = [
     (2, 32, 32, 32, 128),
     (8, 8, 8, 128, 256),
     (3, 16, 16, 256, 256),
+    (3, 25, 25, 32, 128),   # 100x100 config: odd grid, 32-channel side -> parity-merged data gradient with ragged classes
 ]
 
 
@@ -65,7 +66,7 @@ def test_conv_s2_fprop_stats(case, dtype):
     d = L.conv_desc(N, H, W, Cin, Cout, 2, False, 0, dtype)
     OH, OW = L.conv_out_hw(d)
     xs = nhwc(x).to(dtype)
-    pack = torch.empty(25 * Cout * Cin, dtype=torch.bfloat16, device=DEV)
+    pack = torch.empty(L.conv_pack_elems(d), dtype=torch.bfloat16, device=DEV)
     L.conv_pack_weights(d, w, pack, None)
     y = torch.full((N, OH, OW, Cout), float("nan"), dtype=dtype, device=DEV)
     ssum = torch.zeros(Cout, dtype=torch.float64, device=DEV)
@@ -90,7 +91,7 @@ def test_conv_s2_dgrad(case, dtype):
     OH, OW = L.conv_out_hw(d)
     dy = rnd(torch.randn(N, Cout, OH, OW, generator=g).to(DEV), dtype)
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=2, padding=2)
-    pack_d = torch.empty(25 * Cout * Cin, dtype=torch.bfloat16, device=DEV)
+    pack_d = torch.empty(L.conv_pack_elems(d), dtype=torch.bfloat16, device=DEV)
     L.conv_pack_weights(d, w, None, pack_d)
     dx = torch.full((N, H, W, Cin), float("nan"), dtype=dtype, device=DEV)
     L.conv_dgrad(d, nhwc(dy).to(dtype), w, pack_d, dx)
@@ -127,6 +128,7 @@ CONVT_CASES = [
     (2, 16, 16, 256, 128, 1),
     (2, 32, 32, 128, 32, 1),
     (3, 13, 13, 64, 64, 0),
+    (3, 13, 13, 128, 32, 0),  # odd output (25x25) through the parity-merged scatter
 ]
 
 
@@ -145,8 +147,8 @@ def test_convT_fprop_dgrad_wgrad(case, dtype):
     assert (OH, OW) == tuple(ref.shape[2:])
     dyr = rnd(torch.randn(N, Cout, OH, OW, generator=g).to(DEV), dtype)
     gx, gw = torch.autograd.grad(ref, (x, w), dyr)
-    pack_f = torch.empty(25 * Cout * Cin, dtype=torch.bfloat16, device=DEV)
-    pack_d = torch.empty(25 * Cout * Cin, dtype=torch.bfloat16, device=DEV)
+    pack_f = torch.empty(L.conv_pack_elems(d), dtype=torch.bfloat16, device=DEV)
+    pack_d = torch.empty(L.conv_pack_elems(d), dtype=torch.bfloat16, device=DEV)
     wd = w.detach()
     L.conv_pack_weights(d, wd, pack_f, pack_d)
     xs = nhwc(x.detach()).to(dtype)

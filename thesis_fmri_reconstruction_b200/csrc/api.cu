@@ -160,6 +160,15 @@ static void pick_box(int X, int Y, int N, int* bw, int* bh, int* bn) {
     *bn = std::max(1, std::min(N, 128 / (*bw * *bh)));
 }
 
+// power-of-two pixel box (rows = bw*bh*bn is a power of two >= 16 whenever the problem has that many pixels): the weight-
+// gradient kernel consumes pixels in K = 16 steps; boxes wider than the grid are zero-filled by TMA on both operands.
+static void pick_box_pow2(int X, int Y, int N, int* bw, int* bh, int* bn) {
+    auto up = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
+    *bw = std::min(up(X), 128);
+    *bh = std::max(1, std::min(up(Y), 128 / *bw));
+    *bn = std::max(1, std::min(up(N), 128 / (*bw * *bh)));
+}
+
 // Gather-form plan: out[n,oy,ox,:] = sum_taps X[n, oy*s+kh-2, ox*s+kw-2, :] * pack[tap]
 // (Conv2d fprop; ConvTranspose2d dgrad). X: [N,H,W,Ck] bf16, out: [N,OH,OW,Ng].
 static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, int stride, const void* pack,
@@ -235,9 +244,12 @@ static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW
 
 // Scatter-form plan (stride 2): out[n, 2a+ph, 2b+pw, :] = sum_{kh = ph (mod 2), kw = pw (mod 2)} X[n, a+(ph+2-kh)/2, ..] * pack[tap]
 // (ConvTranspose2d fprop; Conv2d dgrad). X: [N,H,W,Ck], out: [N,OH,OW,Ng] with OH in {2H-1, 2H}.
+static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
+                              double* ssum, double* ssq, cudaStream_t st);
 static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, const void* pack, void* out,
                        double* ssum, double* ssq, cudaStream_t st) {
     if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
+    if (Ng == 32) return run_scatter_merged(X, N, H, W, Ck, OH, OW, pack, out, ssum, ssq, st);
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
     memset(&p, 0, sizeof(p));
@@ -289,6 +301,62 @@ static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int O
     p.stat_sum = ssum;
     p.stat_sq = ssq;
     return dispatch_ig(p, BN, KCH, 4, st);
+}
+
+// Parity-merged scatter plan for Ng == 32 (IgParams::merge): one gather over the 3x3 coarse neighbourhood, N = 4 x 32.
+// `pack` is the ordinary tap-major pack [25][32][Ck] followed by the merged pack [9][128][Ck] (fmri_conv_pack_elems).
+static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
+                              double* ssum, double* ssq, cudaStream_t st) {
+    const int Ng = 32;
+    const int KCH = (Ck % 64 == 0) ? 64 : 32;
+    IgParams p;
+    memset(&p, 0, sizeof(p));
+    const int GX = (OW + 1) / 2, GY = (OH + 1) / 2;
+    pick_box(GX, GY, N, &p.bw, &p.bh, &p.bn);
+    p.tiles_x = cdiv(GX, p.bw);
+    p.tiles_y = cdiv(GY, p.bh);
+    p.tiles_n = cdiv(N, p.bn);
+    p.lim_n = N;
+    const int BN = 128;
+    int rc = make_act_map(&p.mapA[0], X, Ck, W, H, N, Ck, (long long)W * Ck, (long long)H * W * Ck, KCH, p.bw, p.bh,
+                          p.bn);
+    if (rc) return rc;
+    const __nv_bfloat16* mpack = reinterpret_cast<const __nv_bfloat16*>(pack) + 25LL * Ng * Ck;
+    {
+        const long long dims[2] = {Ck, 9LL * 128};
+        const long long stv[1] = {Ck};
+        const int box[2] = {KCH, BN};
+        rc = make_map(&p.mapB, mpack, 2, dims, stv, box, KCH * 2);
+        if (rc) return rc;
+    }
+    TapClass& c = p.cls[0];
+    c.num_taps = 9;
+    c.lim_x = GX;
+    c.lim_y = GY;
+    c.out_off = 0;
+    for (int t9 = 0; t9 < 9; ++t9) {
+        c.taps[t9].map = 0;
+        c.taps[t9].dy = (int16_t)(t9 / 3 - 1);
+        c.taps[t9].dx = (int16_t)(t9 % 3 - 1);
+        c.taps[t9].brow = t9 * 128;
+    }
+    p.num_chunks = Ck / KCH;
+    p.n_total = 128;
+    p.n_tiles = 1;
+    p.splits = 1;
+    p.a_bytes = p.bw * p.bh * p.bn * KCH * 2;
+    p.out_sn = (long long)OH * OW * Ng;
+    p.out_sy = 2LL * OW * Ng;
+    p.out_sx = 2LL * Ng;
+    p.out = out;
+    p.out_fp32 = 0;
+    p.stat_sum = ssum;
+    p.stat_sq = ssq;
+    p.merge = 1;
+    p.merge_oh = OH;
+    p.merge_ow = OW;
+    p.merge_sy = (long long)OW * Ng;
+    return dispatch_ig(p, BN, KCH, 1, st);
 }
 
 // Plain GEMM plan: C[M,N] = act(A[M,K] B[N,K]^T + bias), A/B bf16 K-major with pitches, optional split-K into fp32.
@@ -386,6 +454,7 @@ static int run_wgrad_tc(const void* Dn, int N, int PH, int PW, int Cd, const voi
     WgParams p;
     memset(&p, 0, sizeof(p));
     pick_box(PW, PH, N, &p.bw, &p.bh, &p.bn);
+    if ((p.bw * p.bh * p.bn) % 16) pick_box_pow2(PW, PH, N, &p.bw, &p.bh, &p.bn);
     p.rows = p.bw * p.bh * p.bn;
     if (p.rows % 16) return fail(FMRI_ERR_UNSUPPORTED, "wgrad pixel box %d not a multiple of 16", p.rows);
     p.tiles_x = cdiv(PW, p.bw);
@@ -463,6 +532,16 @@ static int check_conv(const fmri_conv_desc* d) {
 static inline long long w_so(const fmri_conv_desc* d) { return d->transposed ? 25LL : 25LL * d->Cin; }
 static inline long long w_si(const fmri_conv_desc* d) { return d->transposed ? 25LL * d->Cout : 25LL; }
 
+// elements (bf16) of one pack buffer: the tap-major pack, plus the parity-merged pack when this layer has a 32-channel side
+// that a scatter-form launch writes (ConvTranspose2d with Cout == 32: pack_f; stride-2 Conv2d with Cin == 32: pack_d)
+extern "C" size_t fmri_conv_pack_elems(const fmri_conv_desc* d) {
+    size_t n = 25 * (size_t)d->Cin * d->Cout;
+    const int thin = d->transposed ? d->Cout : d->Cin;
+    const int other = d->transposed ? d->Cin : d->Cout;
+    if (thin == 32 && d->stride == 2) n += 9 * 128 * (size_t)other;
+    return n;
+}
+
 extern "C" int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, void* pack_f, void* pack_d,
                                       void* stream) {
     int rc = check_conv(d);
@@ -472,11 +551,21 @@ extern "C" int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, v
         permute4_kernel<float, __nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
             w, reinterpret_cast<__nv_bfloat16*>(pack_f), 1, 25, d->Cout, d->Cin, 0, 1, w_so(d), w_si(d), 0);
         LAUNCH_OK();
+        if (d->transposed && d->Cout == 32 && d->stride == 2) {  // scatter-form fprop writes the 32-channel side
+            __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(pack_f);
+            merge_pack_kernel<<<grid1d(9LL * 128 * d->Cin, 256), 256, 0, S(stream)>>>(pk, pk + n, d->Cin);
+            LAUNCH_OK();
+        }
     }
     if (pack_d) {  // [tap][ci][co]
         permute4_kernel<float, __nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
             w, reinterpret_cast<__nv_bfloat16*>(pack_d), 1, 25, d->Cin, d->Cout, 0, 1, w_si(d), w_so(d), 0);
         LAUNCH_OK();
+        if (!d->transposed && d->Cin == 32 && d->stride == 2) {  // scatter-form dgrad writes the 32-channel side
+            __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(pack_d);
+            merge_pack_kernel<<<grid1d(9LL * 128 * d->Cout, 256), 256, 0, S(stream)>>>(pk, pk + n, d->Cout);
+            LAUNCH_OK();
+        }
     }
     return 0;
 }

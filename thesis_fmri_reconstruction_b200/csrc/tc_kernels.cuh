@@ -52,6 +52,13 @@ struct IgParams {
     int act;
     double* stat_sum;  // optional per-column sum / sum of squares of the stored values
     double* stat_sq;
+    // parity-merged scatter (thin-output stride-2 transposed conv / conv data-gradient, Ng = 32): the four output-parity
+    // classes become 4 x 32 GEMM columns of ONE gather over the 3x3 neighbourhood of the coarse pixel (taps a class does not
+    // use carry zero weights: 36/25 more MACs, but N = 128 instead of 32 and the activation tile is fetched 9x, not 25x).
+    // Column group g = col / 32 -> (ph, pw) = (g >> 1, g & 1) is stored at fine pixel (2y + ph, 2x + pw).
+    int merge;              // 0 / 1
+    int merge_oh, merge_ow; // fine output extent
+    long long merge_sy;     // fine row stride (elements)
 };
 
 // MT = number of 128-row M sub-tiles one CTA accumulates against the SAME B (weight) tile: the kernels are bound by
@@ -230,8 +237,20 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
             const bool valid = (ni < p.bn) && (n0[m] + ni < p.lim_n) && (y0[m] + yi < c.lim_y) && (x0[m] + xi < c.lim_x);
             const long long off = c.out_off + (long long)(n0[m] + ni) * p.out_sn + (long long)(y0[m] + yi) * p.out_sy +
                                   (long long)(x0[m] + xi) * p.out_sx + (long long)nt * BN;
+            const bool valid_tile = valid;
+            const long long off_tile = off;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                bool valid = valid_tile;
+                long long off = off_tile;
+                int stat_col = c0;
+                if (p.merge) {  // 32-column group -> output parity class
+                    const int g = (nt * BN + c0) >> 5;
+                    const int ph = g >> 1, pw = g & 1;
+                    valid = valid_tile && (2 * (y0[m] + yi) + ph < p.merge_oh) && (2 * (x0[m] + xi) + pw < p.merge_ow);
+                    off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
+                    stat_col = 0;
+                }
                 uint32_t v[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * BN + c0, v);
                 tmem_ld_wait();
@@ -292,8 +311,8 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
                     }
                     const float s1 = warp_colsum32(f, lane);
                     const float s2 = warp_colsum32(g, lane);
-                    atomicAdd(&s_stat[c0 + lane], s1);
-                    atomicAdd(&s_stat[BN + c0 + lane], s2);
+                    atomicAdd(&s_stat[stat_col + lane], s1);
+                    atomicAdd(&s_stat[BN + stat_col + lane], s2);
                 }
             }
         }
@@ -302,9 +321,11 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
     __syncthreads();
     tc_fence_after();
     if (p.stat_sum != nullptr) {
-        for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-            atomicAdd(p.stat_sum + nt * BN + i, (double)s_stat[i]);
-            atomicAdd(p.stat_sq + nt * BN + i, (double)s_stat[BN + i]);
+        const int ncol = p.merge ? 32 : BN;
+        const int cbase = p.merge ? 0 : nt * BN;
+        for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
+            atomicAdd(p.stat_sum + cbase + i, (double)s_stat[i]);
+            atomicAdd(p.stat_sq + cbase + i, (double)s_stat[BN + i]);
         }
     }
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);

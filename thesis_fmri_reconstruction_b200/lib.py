@@ -58,7 +58,7 @@ class _Proxy:
     def __getattr__(self, name):
         f = getattr(self._c, name)
         if PROF is None or name in ("fmri_last_error", "fmri_conv_out_hw", "fmri_conv_wgrad_workspace",
-                                    "fmri_edge_workspace", "fmri_launch_count", "fmri_version"):
+                                    "fmri_edge_workspace", "fmri_launch_count", "fmri_version", "fmri_conv_pack_elems"):
             return f
 
         def timed(*a):
@@ -121,6 +121,7 @@ def load():
         c = C.CDLL(LIB_PATH)
         c.fmri_last_error.restype = C.c_char_p
         c.fmri_conv_wgrad_workspace.restype = C.c_size_t
+        c.fmri_conv_pack_elems.restype = C.c_size_t
         c.fmri_edge_workspace.restype = C.c_size_t
         c.fmri_conv_out_hw.restype = None
         c.fmri_launch_count.restype = C.c_longlong
@@ -179,6 +180,10 @@ def conv_out_hw(d):
     oh, ow = C.c_int(), C.c_int()
     load().fmri_conv_out_hw(C.byref(d), C.byref(oh), C.byref(ow))
     return oh.value, ow.value
+
+
+def conv_pack_elems(d):
+    return load().fmri_conv_pack_elems(C.byref(d))
 
 
 def conv_pack_weights(d, w, pack_f, pack_d):

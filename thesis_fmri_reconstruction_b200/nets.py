@@ -106,7 +106,7 @@ class ConvBlock:
     def refresh(self, P, inplace=True):
         if self.adt != BF16:
             return
-        n = 25 * self.Cin * self.Cout
+        n = L.conv_pack_elems(self.desc(1, 8, 8))
         if self.pack_f is None or not inplace:
             self.pack_f, self.pack_d = E(n, dtype=BF16), E(n, dtype=BF16)
         L.conv_pack_weights(self.desc(1, 8, 8), P[self.prefix + "conv.weight"], self.pack_f, self.pack_d)
