@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "../../include/fmri_b200.h"
@@ -126,7 +127,54 @@ static int launch_ig(const IgParams& p, int classes, cudaStream_t st) {
     LAUNCH_OK();
     return 0;
 }
+template <int BN, int KCH, int STAGES, int MT>
+static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
+    using L = IgSmem<BN, KCH, STAGES, MT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(igemm_persistent_kernel<BN, KCH, STAGES, MT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_done = true;
+    }
+    const long long m_groups = cdiv((long long)p.tiles_x * p.tiles_y * p.tiles_n, MT);
+    const long long tiles = m_groups * p.n_tiles * classes;
+    const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), (227 * 1024) / L::TOTAL));
+    const int grid = (int)std::min<long long>(tiles, 148LL * per_sm);
+    igemm_persistent_kernel<BN, KCH, STAGES, MT><<<grid, 192, L::TOTAL, st>>>(p, classes);
+    LAUNCH_OK();
+    return 0;
+}
+static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)
+static int dispatch_ig_persistent(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
+    if (KCH == 64) {
+        switch (BN) {
+            case 256: return launch_ig_persistent<256, 64, 4, 1>(p, classes, st);
+            case 128: return launch_ig_persistent<128, 64, 4, 2>(p, classes, st);
+            case 64: return launch_ig_persistent<64, 64, 4, 2>(p, classes, st);
+            case 32: return launch_ig_persistent<32, 64, 4, 2>(p, classes, st);
+        }
+    } else if (KCH == 32) {
+        switch (BN) {
+            case 256: return launch_ig_persistent<256, 32, 4, 1>(p, classes, st);
+            case 128: return launch_ig_persistent<128, 32, 4, 2>(p, classes, st);
+            case 64: return launch_ig_persistent<64, 32, 4, 2>(p, classes, st);
+            case 32: return launch_ig_persistent<32, 32, 4, 2>(p, classes, st);
+        }
+    }
+    return fail(FMRI_ERR_UNSUPPORTED, "persistent igemm tile BN=%d KCH=%d not instantiated", BN, KCH);
+}
 static int dispatch_ig(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
+    {
+        static bool env_done = false;
+        if (!env_done) {
+            const char* e = getenv("FMRI_IGEMM_PERSISTENT");
+            if (e) g_ig_persistent = atoi(e);
+            env_done = true;
+        }
+        const long long all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * classes;
+        if (g_ig_persistent && p.splits == 1 && (all >= 2 * 148 || g_ig_persistent == 2))  // 2: always (tests)
+            return dispatch_ig_persistent(p, BN, KCH, classes, st);
+    }
     // two M sub-tiles per CTA (shared weight tile) once there is more than a few waves of work
     const long long ctas = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.splits * classes;
     const bool mt2 = ctas >= 6 * 148 && p.splits == 1;

@@ -70,7 +70,7 @@ struct IgSmem {
     static constexpr int B_BYTES = BN * KCH * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr int TOTAL = STAT_OFF + 2 * BN * 4 + 1024;  // +1024: manual base alignment
 };
 
@@ -328,6 +328,283 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
             atomicAdd(p.stat_sq + cbase + i, (double)s_stat[BN + i]);
         }
     }
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant of igemm_kernel (split-K == 1): one CTA per SM walks a list of output tiles; the TMA ring and the MMA
+// issue run ahead across tile boundaries and the accumulators are DOUBLE BUFFERED in TMEM (2 x MT x BN <= 512 columns), so the
+// epilogue of tile i (TMEM -> registers -> bias/activation -> global, BN statistics) overlaps the main loop of tile i+1.
+// The non-persistent kernel leaves the tensor pipe idle during prologue + epilogue (56-64 % busy on the big layers,
+// profiles/r1_ncu_full_gemm_kernels_B512.md).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct IgTile {
+    int cls, nt;
+    int x0[2], y0[2], n0[2];
+    bool live[2];
+    bool any;
+};
+template <int MT>
+__device__ __forceinline__ IgTile ig_decode_tile(const IgParams& p, int t, int m_groups) {
+    IgTile r;
+    const int per_cls = m_groups * p.n_tiles;
+    r.cls = t / per_cls;
+    const int rem = t - r.cls * per_cls;
+    r.nt = rem / m_groups;
+    const int mg = rem - r.nt * m_groups;
+    const TapClass& c = p.cls[r.cls];
+    const int total_mt = p.tiles_x * p.tiles_y * p.tiles_n;
+    r.any = false;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int mt = mg * MT + m;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tn = mt / (p.tiles_x * p.tiles_y);
+        r.x0[m] = tx * p.bw; r.y0[m] = ty * p.bh; r.n0[m] = tn * p.bn;
+        r.live[m] = mt < total_mt && r.x0[m] < c.lim_x && r.y0[m] < c.lim_y;
+        r.any |= r.live[m];
+    }
+    return r;
+}
+
+template <int BN, int KCH, int STAGES, int MT>
+__global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
+    using L = IgSmem<BN, KCH, STAGES, MT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull = empty_bar + STAGES;   // [2] accumulators of buffer b complete (tcgen05.commit)
+    uint64_t* tempty = tfull + 2;           // [2] buffer b drained by the 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_stat = reinterpret_cast<float*>(smem + L::STAT_OFF);
+    static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_groups = (p.tiles_x * p.tiles_y * p.tiles_n + MT - 1) / MT;
+    const int total_tiles = m_groups * p.n_tiles * num_classes;
+    constexpr uint32_t ACC_COLS = MT * BN;
+    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : (2 * ACC_COLS);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA[0]);
+        tma_prefetch_desc(&p.mapB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
+                if (!tl.any) continue;
+                const TapClass& c = p.cls[tl.cls];
+                int nlive = 0;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) nlive += tl.live[m] ? 1 : 0;
+                const int nks = c.num_taps * p.num_chunks;
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[st], nlive * p.a_bytes + L::B_BYTES);
+                    const int tap = ks / p.num_chunks;
+                    const int ch = ks - tap * p.num_chunks;
+                    const TapDesc td = c.taps[tap];
+                    uint8_t* sa = smem + st * L::STAGE_BYTES;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        if (tl.live[m])
+                            tma_load_4d(sa + m * L::A_SUB, &p.mapA[td.map], &full_bar[st], ch * KCH, tl.x0[m] + td.dx,
+                                        tl.y0[m] + td.dy, tl.n0[m]);
+                    tma_load_2d(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, td.brow + tl.nt * BN);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+            constexpr uint64_t layout = (KCH == 64) ? UMMA_SW128 : UMMA_SW64;
+            constexpr uint32_t sbo = 8 * KCH * 2;
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
+                if (!tl.any) continue;
+                const int buf = lt & 1;
+                mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const int nks = p.cls[tl.cls].num_taps * p.num_chunks;
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
+                    const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        if (!tl.live[m]) continue;
+                        const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_bf16(tmem_base + buf * ACC_COLS + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                      (ks | k) != 0);
+                    }
+                    umma_commit(&empty_bar[st]);
+                }
+                umma_commit(&tfull[buf]);
+                ++lt;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int xi = row % p.bw;
+        const int yi = (row / p.bw) % p.bh;
+        const int ni = row / (p.bw * p.bh);
+        const bool do_stats = p.stat_sum != nullptr;
+        const int etid = threadIdx.x - 64;
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
+            if (!tl.any) continue;
+            const TapClass& c = p.cls[tl.cls];
+            const int buf = lt & 1;
+            const int nt = tl.nt;
+            mbar_wait(&tfull[buf], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+                if (!tl.live[m]) continue;
+                const bool valid_tile = (ni < p.bn) && (tl.n0[m] + ni < p.lim_n) && (tl.y0[m] + yi < c.lim_y) &&
+                                        (tl.x0[m] + xi < c.lim_x);
+                const long long off_tile = c.out_off + (long long)(tl.n0[m] + ni) * p.out_sn +
+                                           (long long)(tl.y0[m] + yi) * p.out_sy + (long long)(tl.x0[m] + xi) * p.out_sx +
+                                           (long long)nt * BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    bool valid = valid_tile;
+                    long long off = off_tile;
+                    int stat_col = c0;
+                    if (p.merge) {
+                        const int g = (nt * BN + c0) >> 5;
+                        const int ph = g >> 1, pw = g & 1;
+                        valid = valid_tile && (2 * (tl.y0[m] + yi) + ph < p.merge_oh) && (2 * (tl.x0[m] + xi) + pw < p.merge_ow);
+                        off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
+                        stat_col = 0;
+                    }
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + m * BN + c0, v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
+                    }
+                    if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (p.act == ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                    } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+                    }
+                    if (p.out_fp32) {
+                        if (valid) {
+                            float* o = reinterpret_cast<float*>(p.out) + off + c0;
+                            if (p.atomic_out) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            }
+                        }
+                    } else {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                        if (valid) {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(o + 8 * j) =
+                                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                        if (do_stats) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                f[2 * j] = __uint_as_float(pk[j] << 16);
+                                f[2 * j + 1] = __uint_as_float(pk[j] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (do_stats) {
+                        float g2[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            f[j] = valid ? f[j] : 0.f;
+                            g2[j] = f[j] * f[j];
+                        }
+                        const float s1 = warp_colsum32(f, lane);
+                        const float s2 = warp_colsum32(g2, lane);
+                        atomicAdd(&s_stat[stat_col + lane], s1);
+                        atomicAdd(&s_stat[BN + stat_col + lane], s2);
+                    }
+                }
+            }
+            // accumulators of this buffer are in registers / memory: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (do_stats) {  // flush this tile's per-channel sums (the next tile may belong to another channel block)
+                named_bar_sync(1, 128);
+                const int ncol = p.merge ? 32 : BN;
+                const int cbase = p.merge ? 0 : nt * BN;
+                for (int i = etid; i < ncol; i += 128) {
+                    atomicAdd(p.stat_sum + cbase + i, (double)s_stat[i]);
+                    atomicAdd(p.stat_sq + cbase + i, (double)s_stat[BN + i]);
+                    s_stat[i] = 0.f;
+                    s_stat[BN + i] = 0.f;
+                }
+                named_bar_sync(1, 128);
+            }
+            ++lt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
