@@ -23,7 +23,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic MFLOP per sample per optimisation step (2 x MACs of the necessary GEMMs only)
-ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8}
+ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8, "stage2_cognitive": 13866.1,
+             # Stage III proper (train_vgan_stage3.py): fwd C+2D+3S = 4359.3, bwd [3S+3(S-c0)+2c0] + [2c3+3(c2+c1)+c0] + 2(2D-fc) = 11001.2
+             "stage3_cognitive": 15360.4}
 METRIC = "stage1_vaegan_train_samples_per_sec_64x64"  # BASELINE.json metric; other workloads rename it below
 
 
@@ -33,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan"])
+    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive"])
     ap.add_argument("--batch", type=int, default=4096, help="GLOBAL batch (BASELINE.json configs[4]: 4096, strong scaling)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -115,7 +117,7 @@ def cpu_reference_steps(workload, B, steps, warmup, threads=None):
             nonlocal P, sq
             out = O.stage1_vaegan_step(P, S, x, eps, z_p, sq=sq)
             P, sq = out["params"], out["square_avg"]
-    else:
+    elif workload == "stage1_waegan":
         P, S = O.make_waegan(O.CFG64, seed=12345, jitter=False)
         x = O.synthetic_images(B)
         z_fake = O.synthetic_noise(B, 128)[0] * 0.5
@@ -125,6 +127,18 @@ def cpu_reference_steps(workload, B, steps, warmup, threads=None):
             nonlocal P
             out = O.stage1_waegan_step(P, S, x, z_fake, opt=st["opt"], step=st["t"])
             P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
+    else:
+        stage = 2 if workload == "stage2_cognitive" else 3
+        P, S = O.make_cognitive(O.CFG64, seed=12345, jitter=False)
+        fmri, x = O.synthetic_fmri(B), O.synthetic_images(B)
+        eps, z_p = O.synthetic_noise(B, 128)
+        eps_t = O.synthetic_noise(B, 128, seed=99)[0]
+        sq = None
+
+        def one():
+            nonlocal P, sq
+            out = O.cognitive_vaegan_step(P, S, fmri, x, eps, eps_t, z_p, stage, sq=sq, force_gate=(True, True))
+            P, sq = out["params"], out["square_avg"]
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
@@ -177,20 +191,35 @@ def run_ours(args):
         tr = engine.VaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group, gate=True)
         n1_host = torch.randn(B, z, generator=gen).pin_memory()
         n2_host = torch.randn(B, z, generator=gen).pin_memory()
-    else:
+    elif args.workload == "stage1_waegan":
         P, S = init.init_waegan(cfg, z, seed=12345)
         tr = engine.WaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group)
         n1_host = (torch.randn(B, z, generator=gen) * 0.5).pin_memory()
         n2_host = None
+    else:
+        stage = 2 if args.workload == "stage2_cognitive" else 3
+        P, S = init.init_cognitive(cfg, z, seed=12345, with_teacher=stage == 2)
+        tr = engine.VaeGanCognitiveStage(P, S, cfg, stage, z, torch.bfloat16, dist_group=group)
+        n1_host = torch.randn(B, z, generator=gen).pin_memory()
+        n2_host = torch.randn(B, z, generator=gen).pin_memory()
+        fmri_host = torch.randn(B, hp.NUM_VOXELS, generator=gen).pin_memory()
+        eps_t = torch.randn(B, z, generator=gen).cuda()
     x = x_host.cuda(non_blocking=True)
     n1 = n1_host.cuda(non_blocking=True)
     n2 = n2_host.cuda(non_blocking=True) if n2_host is not None else None
+    cog = args.workload in ("stage2_cognitive", "stage3_cognitive")
+    fmri = fmri_host.cuda(non_blocking=True) if cog else None
+
+    def run_step(xb, a, b2, fb=None):
+        if cog:
+            tr.step(fb if fb is not None else fmri, xb, a, eps_t, b2)
+        elif b2 is not None:
+            tr.step(xb, a, b2)
+        else:
+            tr.step(xb, a)
 
     def step_dev():
-        if n2 is not None:
-            tr.step(x, n1, n2)
-        else:
-            tr.step(x, n1)
+        run_step(x, n1, n2)
 
     def sync_all():
         if world > 1:
@@ -233,7 +262,8 @@ def run_ours(args):
         return
     # ---------------------------------------------------------------- end to end from pinned host memory (`e2e`)
     copy_stream = torch.cuda.Stream()
-    bufs = [[torch.empty_like(x), torch.empty_like(n1), torch.empty_like(n2) if n2 is not None else None] for _ in range(2)]
+    bufs = [[torch.empty_like(x), torch.empty_like(n1), torch.empty_like(n2) if n2 is not None else None,
+             torch.empty_like(fmri) if cog else None] for _ in range(2)]
     evs = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     sc_host = torch.empty(16).pin_memory()
@@ -246,6 +276,8 @@ def run_ours(args):
             bufs[slot][1].copy_(n1_host, non_blocking=True)
             if n2 is not None:
                 bufs[slot][2].copy_(n2_host, non_blocking=True)
+            if cog:
+                bufs[slot][3].copy_(fmri_host, non_blocking=True)
             evs[slot].record(copy_stream)
 
     def step_e2e():
@@ -254,10 +286,7 @@ def run_ours(args):
         torch.cuda.current_stream().wait_event(evs[slot])
         upload(slot ^ 1)  # prefetch the next batch while this step computes (the DataLoader's role in the reference)
         b = bufs[slot]
-        if n2 is not None:
-            tr.step(b[0], b[1], b[2])
-        else:
-            tr.step(b[0], b[1])
+        run_step(b[0], b[1], b[2], b[3])
         done[slot].record()
         sc_host.copy_(tr.sc, non_blocking=True)  # D2H of the step's loss sums (what train_vgan_stage1.py:391-401 reads)
         state["i"] = i + 1
@@ -268,7 +297,8 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = args.batch / (ms_e2e * 1e-3)
-    h2d = world * (x_host.numel() + n1_host.numel() + (n2_host.numel() if n2_host is not None else 0)) * 4
+    h2d = world * (x_host.numel() + n1_host.numel() + (n2_host.numel() if n2_host is not None else 0) +
+                   (fmri_host.numel() if cog else 0)) * 4
     d2h = world * 16 * 4
 
     # ---------------------------------------------------------------- per-kernel-family device times (CUDA events)

@@ -185,6 +185,96 @@ def golden_stage1_waegan(ref, B, seed):
     return fx
 
 
+def golden_cognitive(ref, B, seed, stage):
+    """train/train_vgan_stage2.py:210-232, 321-407 (stage 2) / train_vgan_stage3.py:225-262, 324-411 (stage 3)."""
+    torch.manual_seed(0)
+    P, S = O.make_cognitive(O.CFG64, seed=seed, dtype=torch.float64)
+    fmri = O.synthetic_fmri(B, seed=seed).double()
+    image = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    eps_t = O.synthetic_noise(B, 128, seed=seed + 1)[0].double()
+    teacher = ref.VaeGan(device="cpu", z_size=128).double()
+    cog = ref.CognitiveEncoder(input_size=O.NUM_VOXELS, z_size=128).double()
+    if stage == 2:   # decoder / discriminator are the teacher's own modules (train_vgan_stage2.py:216-232)
+        model = ref.VaeGanCognitive(device="cpu", encoder=cog, decoder=teacher.decoder, discriminator=teacher.discriminator,
+                                    teacher_net=teacher, stage=2, z_size=128)
+    else:            # fresh decoder / discriminator objects, teacher only carried along (train_vgan_stage3.py:230-241)
+        model = ref.VaeGanCognitive(device="cpu", encoder=cog, decoder=ref.Decoder(z_size=128, size=256).double(),
+                                    discriminator=ref.Discriminator().double(), teacher_net=teacher, stage=3, z_size=128)
+    sd = model.state_dict()
+    for k, v in {**P, **S}.items():
+        sd[k].copy_(v)
+        if stage == 2 and (k.startswith("decoder.") or k.startswith("discriminator.")):
+            assert torch.equal(sd["teacher_net." + k], sd[k])   # same tensors in stage 2
+    model.train()
+    draws = [eps, eps_t]
+    model.reparameterize = lambda mu, logvar: draws.pop(0) * torch.exp(0.5 * logvar) + mu
+    hp = O.HP_VGAN
+    opt = {b: torch.optim.RMSprop(getattr(model, b).parameters(), lr=hp["lr"], alpha=0.9, eps=1e-8)
+           for b in ("encoder", "decoder", "discriminator")}
+    if stage == 2:
+        for p_ in model.decoder.parameters():
+            p_.requires_grad = False                                                  # stage2 :328-329
+    else:
+        for p_ in model.encoder.parameters():
+            p_.requires_grad = False                                                  # stage3 :329-330
+    with patched_randn(z_p):
+        x_gt, x_tilde, disc_class, disc_layer, mus, lv = model({"fmri": fmri, "image": image})
+    dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]
+    dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
+    nle, kld, mse, bo, bp, bs = ref.VaeGanCognitive.loss(x_gt, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)
+    loss_encoder = torch.sum(kld) + torch.sum(mse)
+    loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+    loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator
+    grads = {}
+    if stage == 2:
+        train_dis, train_dec = True, False                                            # stage2 :375-376
+        model.zero_grad()
+        loss_encoder.backward(retain_graph=True)                                      # :389
+        grads.update({"encoder." + k: p_.grad.clone() for k, p_ in model.encoder.named_parameters()})
+        model.zero_grad()                                                             # :393
+        loss_discriminator.backward()                                                 # :405
+        grads.update({"discriminator." + k: p_.grad.clone() for k, p_ in model.discriminator.named_parameters()})
+        steps = [("encoder", True), ("discriminator", True)]
+    else:
+        train_dis, train_dec = True, True
+        m, e = hp["margin"], hp["equilibrium"]
+        if torch.mean(bo).item() < e - m or torch.mean(bp).item() < e - m:
+            train_dis = False
+        if torch.mean(bo).item() > e + m or torch.mean(bp).item() > e + m:
+            train_dec = False
+        if train_dec is False and train_dis is False:
+            train_dis = True
+            train_dec = True
+        model.zero_grad()                                                             # stage3 :392
+        loss_decoder.backward(retain_graph=True)                                      # :400
+        grads.update({"decoder." + k: p_.grad.clone() for k, p_ in model.decoder.named_parameters()})
+        model.discriminator.zero_grad()                                               # :405
+        loss_discriminator.backward()                                                 # :409
+        grads.update({"discriminator." + k: p_.grad.clone() for k, p_ in model.discriminator.named_parameters()})
+        steps = [("decoder", train_dec), ("discriminator", train_dis)]
+    for b, on in steps:
+        if not on:
+            continue
+        for k, p_ in getattr(model, b).named_parameters():
+            p_.grad = grads[b + "." + k].clone().clamp_(-1, 1)                        # stage2 :391,406 / stage3 :402,410
+        opt[b].step()
+    newP = {k: v.detach() for k, v in model.state_dict().items() if k in P}
+    delta = {k: newP[k] - P[k] for k in P}
+    bufs = {k: v for k, v in model.state_dict().items() if k in S}
+    fx = dict(B=np.array(B), seed=np.array(seed), stage=np.array(stage), train_dis=np.array(train_dis),
+              train_dec=np.array(train_dec), mu=mus.detach().numpy(), logvar=lv.detach().numpy(),
+              kl=kld.detach().numpy(), mse=mse.detach().numpy(), bce_o=bo.detach().numpy(), bce_p=bp.detach().numpy(),
+              bce_s=bs.detach().numpy(), disc_class=disc_class.detach().numpy(),
+              loss_encoder=loss_encoder.detach().numpy(), loss_decoder=loss_decoder.detach().numpy(),
+              loss_discriminator=loss_discriminator.detach().numpy(), x_tilde=summarize(x_tilde), gt_x=summarize(x_gt),
+              disc_layer=summarize(disc_layer))
+    fx.update(summarize_dict(grads, "grad:"))
+    fx.update(summarize_dict(delta, "delta:"))
+    fx.update(summarize_dict(bufs, "buf:"))
+    return fx
+
+
 def main():
     ref = import_reference()
     out = os.path.join(ROOT, "tests", "golden")
@@ -194,6 +284,9 @@ def main():
         np.savez_compressed(os.path.join(out, f"stage1_vaegan_B{B}_s{seed}.npz"), **golden_stage1_vaegan(ref, B, seed))
         np.savez_compressed(os.path.join(out, f"stage1_waegan_B{B}_s{seed}.npz"), **golden_stage1_waegan(ref, B, seed))
         print("wrote goldens for", B, seed)
+    for stage in (2, 3):
+        np.savez_compressed(os.path.join(out, f"stage{stage}_cognitive_B4_s4711.npz"), **golden_cognitive(ref, 4, 4711, stage))
+        print("wrote cognitive golden for stage", stage)
 
 
 if __name__ == "__main__":

@@ -400,3 +400,83 @@ def stage1_waegan_step(P, S, x, z_fake, cfg=CFG64, hp=HP_WAE, opt=None, step=1, 
     if update:
         out["params"], out["adam"] = newP, dict(m=newm, v=newv)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- Stages II / III
+def make_cognitive(cfg=CFG64, z=None, seed=12345, dtype=torch.float32, jitter=True):
+    """CognitiveEncoder + Decoder + Discriminator + teacher visual Encoder of VaeGanCognitive (models/vae_gan.py:323-345;
+    train/train_vgan_stage2.py:210-232: decoder / discriminator ARE the teacher's modules, so their teacher_net.* duplicates
+    in the state_dict are the same tensors). Keys: encoder.* (cognitive), decoder.*, discriminator.*, teacher_net.encoder.*."""
+    z = z or cfg["latent_dim"]
+    P, S = OrderedDict(), OrderedDict()
+    for i, (pre, spec) in enumerate((("encoder.", cognitive_encoder_spec(z)), ("decoder.", decoder_spec(cfg, z)),
+                                     ("discriminator.", discriminator_spec(cfg)),
+                                     ("teacher_net.encoder.", encoder_spec(cfg, z)))):
+        p, s = make_net(pre, spec, seed + 10 + i, dtype, jitter)
+        if pre == "encoder.":  # CognitiveEncoder keeps torch's default Linear init (its init_parameters is commented out,
+            g = torch.Generator().manual_seed(seed + 99)  # models/vae_gan.py:208-222): U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+            for k, v in p.items():
+                if v.dim() == 2:
+                    b = 1.0 / math.sqrt(v.shape[1])
+                    p[k] = ((torch.rand(v.shape, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
+        P.update(p)
+        S.update(s)
+    return P, S
+
+
+def cognitive_vaegan_step(P, S, fmri, image, eps, eps_t, z_p, stage, cfg=CFG64, hp=HP_VGAN, sq=None, update=True,
+                          force_gate=None):
+    """One iteration of train/train_vgan_stage2.py:321-407 (stage=2) or train/train_vgan_stage3.py:324-411 (stage=3).
+
+    Forward = VaeGanCognitive.forward, mode 'vae' (models/vae_gan.py:361-393): cognitive encoder -> reparameterize ->
+    decoder; stage 2 only: the "real" image is replaced by the teacher's reconstruction decoder(reparameterize(
+    teacher.encoder(image))) (teacher encoder in train-mode BN, its parameters frozen); decoder(z_p); discriminator REC + GAN.
+    Stage 2 trains {cognitive encoder, discriminator} (decoder frozen, no gate: train_dis=True, train_dec=False, :375-376);
+    stage 3 trains {decoder, discriminator} with the gate (:382-388), encoder frozen. Both clamp gradients to [-1, 1]
+    before the RMSprop step (stage2 :391,406; stage3 :402,410)."""
+    W = _leaf(P)
+    B = len(fmri)
+    mu, logvar = cognitive_encoder(W, S, fmri, pre="encoder.")
+    z = reparameterize(mu, logvar, eps)
+    x_tilde = decoder(W, S, z, cfg)
+    gt_x = image
+    if stage == 2:
+        mu_t, lv_t = encoder(W, S, image, cfg, pre="teacher_net.encoder.")
+        gt_x = decoder(W, S, reparameterize(mu_t, lv_t, eps_t), cfg)
+    x_p = decoder(W, S, z_p, cfg)
+    disc_layer = discriminator(W, S, gt_x, x_tilde, x_p, cfg, "REC")
+    disc_class = discriminator(W, S, gt_x, x_tilde, x_p, cfg, "GAN")
+    dl_o, dl_p = disc_layer[:B], disc_layer[B:-B]
+    dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
+    nle, kl, mse, bce_o, bce_p, bce_s = vaegan_loss(gt_x, x_tilde, dl_o, dl_p, dc_o, dc_p, dc_s, mu, logvar)
+    loss_enc = kl.sum() + mse.sum()
+    loss_dis = bce_o.sum() + bce_p.sum() + bce_s.sum()
+    loss_dec = (hp["lambda_mse"] * mse).sum() - (1.0 - hp["lambda_mse"]) * loss_dis
+    if stage == 2:
+        train_dis, train_dec = True, False
+        trained = [("encoder", loss_enc), ("discriminator", loss_dis)]
+    else:
+        train_dis, train_dec = gate(bce_o.mean().item(), bce_p.mean().item(), hp["margin"], hp["equilibrium"])
+        if force_gate is not None:
+            train_dis, train_dec = force_gate
+        trained = [("decoder", loss_dec), ("discriminator", loss_dis)]
+    names = {b: bucket(W, b + ".") for b, _ in trained}
+    grads = OrderedDict()
+    for b, loss in trained:
+        gs = torch.autograd.grad(loss, [W[n] for n in names[b]], retain_graph=True)
+        grads.update(zip(names[b], gs))
+    out = dict(gt_x=gt_x, x_tilde=x_tilde, x_p=x_p, disc_layer=disc_layer, disc_class=disc_class, mu=mu, logvar=logvar,
+               kl=kl, mse=mse, bce_o=bce_o, bce_p=bce_p, bce_s=bce_s, nle=nle, loss_encoder=loss_enc,
+               loss_decoder=loss_dec, loss_discriminator=loss_dis, train_dis=train_dis, train_dec=train_dec, grads=grads)
+    out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+    if update:
+        sq = sq if sq is not None else OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+        newP, newsq = OrderedDict(P), OrderedDict(sq)
+        active = dict(encoder=stage == 2, decoder=stage == 3 and train_dec, discriminator=train_dis)
+        for b in names:
+            if not active[b]:
+                continue
+            for n in names[b]:
+                newP[n], newsq[n] = rmsprop_update(P[n], grads[n].clamp(-1, 1), sq[n], hp["lr"], hp["alpha"], hp["eps"])
+        out["params"], out["square_avg"] = newP, newsq
+    return out

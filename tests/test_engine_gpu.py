@@ -146,3 +146,64 @@ def test_stage1_waegan_bf16_tensor_path():
     assert max(rep["forward"].values()) < 2e-2, rep["forward"]
     assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
     assert rep["lvar_same"] and rep["nbt"] == 2 and rep["bn_worst"][1] < 2e-2
+
+
+def run_cog_case(stage, B, adt, seed=901):
+    P, S = O.make_cognitive(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    eps_t = O.synthetic_noise(B, 128, seed=seed + 1)[0]
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.cognitive_vaegan_step(P, S_ref, fmri, image, eps, eps_t, z_p, stage)
+    if stage == 3:  # stage 3 carries no teacher encoder
+        P = {k: v for k, v in P.items() if not k.startswith("teacher_net.")}
+        S = {k: v for k, v in S.items() if not k.startswith("teacher_net.")}
+    tr = engine.VaeGanCognitiveStage(P, S, hp.CFG64, stage, 128, adt)
+    out = tr.forward_backward(fmri.cuda(), image.cuda(), eps.cuda(), eps_t.cuda(), z_p.cuda())
+    grads = {k: v.clone() for k, v in tr.named_grads().items()}
+    tr.update(B)
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = dict(mu=rel(out["mu"], ref["mu"]), x_tilde=rel(out["x_tilde"], ref["x_tilde"]), gt_x=rel(out["gt_x"], ref["gt_x"]),
+               disc_layer=rel(nchw_flat(out["disc_layer_nhwc"]), ref["disc_layer"]),
+               disc_class=rel(out["disc_class"], ref["disc_class"].reshape(-1)), kl=rel(out["kl"], ref["kl"]),
+               mse=rel(out["mse"], ref["mse"]))
+    for k in ("loss_encoder", "loss_decoder", "loss_discriminator"):
+        fwd[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    gerr = {}
+    for b in sorted({k.split(".")[0] + "." for k in ref["grads"]}):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    sqerr = {}
+    for pre, bk in tr.buckets.items():   # RMSprop state = 0.1 * clamp(g)^2 after one step: checks the fused clamp
+        ks = [k for k in ref["grads"] if k.startswith(pre)]
+        if ks and (lo["train_dis"] if pre == "discriminator." else True):
+            got = torch.cat([bk.state_view(0, k[len(pre):]).reshape(-1) for k in ks])
+            want = torch.cat([ref["square_avg"][k].reshape(-1) for k in ks])
+            sqerr[pre] = rel(got, want)
+    gate_ok = (lo["train_dis"], lo["train_dec"]) == (ref["train_dis"], ref["train_dec"])
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
+    rep = dict(stage=stage, B=B, dtype=str(adt), forward=fwd, grad_bucket=gerr, square_avg=sqerr, gate_ok=gate_ok,
+               nbt_ok=nbt_ok, bn_worst=max(berr.items(), key=lambda t: t[1]))
+    with open(f"gpurun_out/parity_stage{stage}_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_cognitive_stage_fp32_exact_path(stage):
+    rep = run_cog_case(stage, 8, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert max(rep["square_avg"].values()) < 1e-2, rep["square_avg"]
+    assert rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 1e-4
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_cognitive_stage_bf16_tensor_path(stage):
+    rep = run_cog_case(stage, 16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2

@@ -95,6 +95,34 @@ def test_stage1_waegan_fp64_matches_reference(path):
     assert n == len(out["grads"]) == len(P) - 2  # l_var.{weight,bias} receive no gradient in the WAE
 
 
+@pytest.mark.parametrize("stage", [2, 3])
+def test_cognitive_stages_fp64_match_reference(stage):
+    g = np.load(os.path.join(GOLD, f"stage{stage}_cognitive_B4_s4711.npz"))
+    B, seed = int(g["B"]), int(g["seed"])
+    P, S = O.make_cognitive(O.CFG64, seed=seed, dtype=torch.float64)
+    fmri = O.synthetic_fmri(B, seed=seed).double()
+    image = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    eps_t = O.synthetic_noise(B, 128, seed=seed + 1)[0].double()
+    out = O.cognitive_vaegan_step(P, S, fmri, image, eps, eps_t, z_p, stage)
+    assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
+    for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder", "loss_decoder",
+              "loss_discriminator"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-9, k
+    for k in ("x_tilde", "gt_x", "disc_layer"):
+        assert summary_error(summarize(out[k]), g[k]) < 1e-9, k
+    n = 0
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert summary_error(summarize(out["grads"][k[5:]]), g[k]) < 1e-8, k
+            n += 1
+        elif k.startswith("delta:"):
+            assert summary_error(summarize(out["params"][k[6:]] - P[k[6:]]), g[k]) < 1e-6, k
+        elif k.startswith("buf:"):
+            assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
+    assert n == len(out["grads"]) > 0
+
+
 def test_gate_table():
     # train/train_vgan_stage1.py:396-404
     assert O.gate(0.5, 0.7) == (True, True)

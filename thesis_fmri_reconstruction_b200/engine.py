@@ -324,3 +324,134 @@ class WaeGanStage1(_TrainerBase):
         s = self.sc.tolist()
         return dict(loss_discriminator_fake=s[0], loss_discriminator_real=s[1], loss_reconstruction=s[2],
                     loss_penalty=s[3])
+
+
+class VaeGanCognitiveStage(_TrainerBase):
+    """Stage-II / Stage-III cognitive VAE/GAN trainer (/root/reference/train/train_vgan_stage2.py:321-407,
+    train_vgan_stage3.py:324-411) over VaeGanCognitive (models/vae_gan.py:323-432, mode 'vae').
+
+    stage 2: trains {CognitiveEncoder, Discriminator}; the decoder is frozen; the discriminator's "real" batch is the
+             teacher's reconstruction decoder(reparameterize(teacher.encoder(image))) (train-mode BN, frozen weights);
+             no gate (train_dis=True, train_dec=False). Backward: class-score sweep (g_dis only), feature-tap data-gradient
+             sweep -> decoder data-gradient sweep -> reparam/KL -> cognitive encoder.
+    stage 3: trains {Decoder, Discriminator} with the equilibrium gate; the cognitive encoder is frozen.
+    Both clamp gradients to [-1, 1] inside the fused RMSprop launch (stage2 :391,406; stage3 :402,410).
+    Parameter keys: encoder.* (CognitiveEncoder), decoder.*, discriminator.*, teacher_net.encoder.* (stage 2 only)."""
+
+    def __init__(self, params, buffers, cfg, stage, z=128, adt=BF16, hp=None, dist_group=None, voxels=None):
+        from .hp import HP_VGAN, NUM_VOXELS
+
+        if stage not in (2, 3):
+            raise L.FmriError("stage must be 2 or 3")
+        self.cfg, self.z, self.adt, self.stage = cfg, z, adt, stage
+        self.hp = dict(HP_VGAN if hp is None else hp)
+        self.cog = NN.CognitiveEncoderNet(voxels or NUM_VOXELS, z, adt)
+        self.dec = NN.DecoderNet(cfg, z, adt)
+        self.dis = NN.DiscriminatorNet(cfg, adt)
+        self.nets = OrderedDict((("encoder.", self.cog), ("decoder.", self.dec), ("discriminator.", self.dis)))
+        if stage == 2:
+            self.tenc = NN.EncoderNet(cfg, z, adt)
+            self.nets["teacher_net.encoder."] = self.tenc
+        dev = torch.device("cuda")
+        self.buckets = OrderedDict()
+        for pre, net in self.nets.items():
+            named = _split(params, pre)
+            diff = set(net.param_names()) ^ set(named)
+            if diff:
+                raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(diff)}")
+            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named), 1)
+        self.S = OrderedDict((k, v.to(dev).clone()) for k, v in buffers.items())
+        self.Ssub = {pre: _split(self.S, pre) for pre in self.buckets}
+        self.nbt = {}
+        self.sc = Z(16)
+        self.lr = {pre: float(self.hp["lr"]) for pre in self.buckets}
+        self._ones_buf = None
+        self._setup_dist(dist_group)
+        for pre, net in self.nets.items():
+            net.refresh(self.buckets[pre].P, inplace=True)
+
+    def _ones(self, n):
+        if self._ones_buf is None or self._ones_buf.numel() < n:
+            self._ones_buf = torch.ones(n, device="cuda")
+        return self._ones_buf
+
+    def forward_backward(self, fmri, image, eps, eps_t, z_p):
+        """fmri [B,V], image [B,3,H,W], eps / eps_t / z_p [B,z]: fp32, device resident (eps_t is used in stage 2 only)."""
+        hp, B, z, stage = self.hp, fmri.shape[0], self.z, self.stage
+        lam = float(hp["lambda_mse"])
+        be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
+        nb = {pre: {} for pre in self.buckets}
+        sc = self.sc
+        ycat, ce = self.cog.forward(be.P, self.Ssub["encoder."], fmri, True, 1, nb["encoder."])
+        mu, lv = ycat[:, :z], ycat[:, z:]
+        zz, kl = E(B, z), E(B)
+        L.reparam_kl_fwd(mu, lv, eps, zz, kl, B, z, ld=2 * z)
+        x_tilde, cd1 = self.dec.forward(bd.P, self.Ssub["decoder."], zz, True, 1, nb["decoder."])
+        gt_x = image
+        if stage == 2:
+            bt = self.buckets["teacher_net.encoder."]
+            yt, _ = self.tenc.forward(bt.P, self.Ssub["teacher_net.encoder."], image, True, 1, nb["teacher_net.encoder."])
+            zt = E(B, z)
+            L.reparam_kl_fwd(yt[:, :z], yt[:, z:], eps_t, zt, None, B, z, ld=2 * z)
+            gt_x, _ = self.dec.forward(bd.P, self.Ssub["decoder."], zt, True, 1, nb["decoder."])
+        x_p, cd2 = self.dec.forward(bd.P, self.Ssub["decoder."], z_p, True, 1, nb["decoder."])
+        raw3, p, cc = self.dis.forward(bc.P, self.Ssub["discriminator."], [gt_x, x_tilde, x_p], True, 2, True,
+                                       nb["discriminator."])
+        for pre, d in nb.items():
+            for k, v in d.items():
+                self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
+        Fd = raw3[0].numel()
+        mse, nle, bce = E(B), E(B), E(3 * B)
+        L.rowsqdiff_fwd(raw3[:B], raw3[B:2 * B], mse, B, Fd, 0.5)
+        L.rowsqdiff_fwd(gt_x, x_tilde, nle, B, gt_x[0].numel(), 0.5)
+        L.bce_fwd(p[:B], bce[:B], B, True, 1.0)
+        L.bce_fwd(p[B:], bce[B:], 2 * B, False, 1.0)
+        for i, (v, n) in enumerate(((bce[:B], B), (bce[B:2 * B], B), (bce[2 * B:], B), (kl, B), (mse, B), (nle, B))):
+            L.vecsum(v, n, 1.0, sc[i:i + 1])
+        self._allreduce_async([sc[:8]])
+        ones = self._ones(3 * B)
+        gp = E(3 * B)
+        L.bce_bwd(p[:B], ones, gp[:B], B, True, 1.0)
+        L.bce_bwd(p[B:], ones, gp[B:], 2 * B, False, 1.0)
+        # discriminator class-score sweep: g_dis; image gradients only when the decoder is trained (stage 3)
+        dimg_bce = self.dis.backward_gan(bc.P, cc, gp, bc.G, False, True, (1, 3) if stage == 3 else None)
+        self._allreduce_async([bc.flat_g])
+        # feature-tap sweep (data gradient only): d sum(mse) / d x_tilde
+        draw3 = torch.empty_like(raw3)
+        draw3[2 * B:].zero_()
+        L.rowsqdiff_bwd(raw3[:B], raw3[B:2 * B], ones, draw3[:B], draw3[B:2 * B], B, Fd, 0.5)
+        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2))
+        if stage == 2:
+            dz = self.dec.backward(bd.P, cd1, 1.0, dimg_mse, 0.0, None, None, False, False, True)
+            dycat = E(B, 2 * z, dtype=self.adt)
+            L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=1.0)
+            self.cog.backward(be.P, ce, dycat, be.G, False, True, True)
+            self._allreduce_async([be.flat_g])
+        else:
+            self.dec.backward(bd.P, cd1, lam, dimg_mse, -(1.0 - lam), dimg_bce[:B], bd.G, False, True, False)
+            self.dec.backward(bd.P, cd2, -(1.0 - lam), dimg_bce[B:], 0.0, None, bd.G, True, True, False)
+            self._allreduce_async([bd.flat_g])
+        return dict(gt_x=gt_x, x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, kl=kl,
+                    mse=mse, bce=bce, nle=nle)
+
+    def update(self, B_global):
+        hp = self.hp
+        self._wait_comm()
+        gates = self.sc[8:10]
+        if self.stage == 3:
+            L.vgan_gate(self.sc, float(B_global), hp["margin"], hp["equilibrium"], gates)
+            plan = (("decoder.", gates[1:2]), ("discriminator.", gates[0:1]))
+        else:
+            gates.copy_(torch.tensor([1.0, 0.0], device="cuda"))
+            plan = (("encoder.", None), ("discriminator.", None))
+        for pre, g in plan:
+            b = self.buckets[pre]
+            L.multi_tensor_rmsprop([b.flat_p], [b.flat_g], [b.states[0]], self.lr[pre], hp["alpha"], hp["eps"], 1.0, None, g)
+            self.nets[pre].refresh(b.P, inplace=True)
+
+    def step(self, fmri, image, eps, eps_t, z_p):
+        out = self.forward_backward(fmri, image, eps, eps_t, z_p)
+        self.update(fmri.shape[0] * self.world)
+        return out
+
+    losses = VaeGanStage1.losses

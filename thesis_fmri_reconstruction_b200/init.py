@@ -108,3 +108,25 @@ def init_waegan(cfg, z, seed=12345):
         P.update(p)
         S.update(s)
     return P, S
+
+
+def init_cognitive(cfg, z, seed=12345, with_teacher=True, input_size=NUM_VOXELS):
+    """CognitiveEncoder (torch default Linear init, its init_parameters is commented out in the reference,
+    models/vae_gan.py:208-222) + Decoder + Discriminator (+ the teacher's visual Encoder for Stage II)."""
+    gen = torch.Generator().manual_seed(seed)
+    P, S = OrderedDict(), OrderedDict()
+    p, s = init_net("encoder.", cognitive_encoder_table(z, input_size), gen)
+    for k, v in p.items():
+        if v.dim() == 2:
+            b = 1.0 / math.sqrt(v.shape[1])
+            p[k] = (torch.rand(v.shape, generator=gen) * 2 - 1) * b
+    P.update(p)
+    S.update(s)
+    tabs = [("decoder.", decoder_table(cfg, z)), ("discriminator.", discriminator_table(cfg))]
+    if with_teacher:
+        tabs.append(("teacher_net.encoder.", encoder_table(cfg, z)))
+    for pre, tab in tabs:
+        p, s = init_net(pre, tab, gen)
+        P.update(p)
+        S.update(s)
+    return P, S
