@@ -130,7 +130,7 @@ int fmri_bn_finalize(const double* sum, const double* sq, long long rows, int C,
                      float* invstd, float* running_mean, float* running_var, void* stream);
 int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, const float* mean,
                   const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
-/* dx, dgamma (+)=, dbeta (+)= ; train=0 treats mean/invstd as constants (eval-mode BN). ws: 2*C doubles. */
+/* dx, dgamma (+)=, dbeta (+)= ; train=0 treats mean/invstd as constants (eval-mode BN). ws: 3*C doubles. */
 int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, int train,
                      float* dgamma, float* dbeta, int accumulate, double* ws, void* stream);

@@ -324,7 +324,7 @@ def test_batchnorm_relu(rows, C, xdtype, gdtype):
     dx = torch.empty(rows, C, dtype=gdtype, device=DEV)
     dgamma = torch.empty(C, device=DEV)
     dbeta = torch.empty(C, device=DEV)
-    ws = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    ws = torch.empty(3 * C, dtype=torch.float64, device=DEV)
     L.bn_backward(xs, dy.to(gdtype), dx, rows, C, mean, invstd, gamma.detach(), beta.detach(), True, True, dgamma,
                   dbeta, False, ws)
     torch.cuda.synchronize()

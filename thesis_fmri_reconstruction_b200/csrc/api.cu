@@ -1121,6 +1121,17 @@ extern "C" int fmri_colstats(const void* x, int dtype, long long rows, int C, do
     dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
     CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double) * C, S(stream)));
     CUDA_OK(cudaMemsetAsync(sq, 0, sizeof(double) * C, S(stream)));
+    if (C % 8 == 0 && ((C / 8) >= 256 ? (C / 8) % 256 == 0 : 256 % (C / 8) == 0)) {
+        dim3 g8(cdiv(rows, rpb), std::max(1, std::min(8, (C / 8) / 256)));
+        if (dtype == FMRI_BF16)
+            bn_reduce8_kernel<0, __nv_bfloat16, __nv_bfloat16><<<g8, 256, 0, S(stream)>>>(
+                reinterpret_cast<const __nv_bfloat16*>(x), nullptr, rows, C, nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb);
+        else
+            bn_reduce8_kernel<0, float, float><<<g8, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(x), nullptr, rows, C,
+                                                                          nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb);
+        LAUNCH_OK();
+        return 0;
+    }
     if (dtype == FMRI_BF16)
         colstats_kernel<__nv_bfloat16><<<grid, 256, 2 * 256 * 4, S(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), rows, C, sum, sq, rpb);
@@ -1141,7 +1152,8 @@ extern "C" int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, l
                              const float* invstd, const float* gamma, const float* beta, int relu, void* stream) {
     if (C % 8) return fail(FMRI_ERR_UNSUPPORTED, "bn_apply needs C %% 8 == 0");
     const long long total = rows * C;
-    const int g = grid1d((total + 7) / 8, 256, 148 * 8);
+    int g = grid1d((total + 7) / 8, 256, 148 * 8);
+    if (C > 2048 && (C % 2048) == 0 && g >= C / 2048) g = g / (C / 2048) * (C / 2048);  // grid stride a multiple of C
     cudaStream_t st = S(stream);
     if (x_dtype == FMRI_BF16 && y_dtype == FMRI_BF16)
         bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(
@@ -1166,19 +1178,25 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
     const int rpb = rows_per_block_for(rows);
     dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
     CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-    bn_bwd_reduce_kernel<Tx, Tg><<<grid, 256, 2 * 256 * 4, st>>>(reinterpret_cast<const Tx*>(x),
-                                                                reinterpret_cast<const Tg*>(dy), rows, C, mean, invstd,
-                                                                gamma, beta, relu, ws, ws + C, rpb);
+    if (C % 8 == 0 && ((C / 8) >= 256 ? (C / 8) % 256 == 0 : 256 % (C / 8) == 0)) {
+        dim3 g8(cdiv(rows, rpb), std::max(1, std::min(8, (C / 8) / 256)));
+        bn_reduce8_kernel<1, Tx, Tg><<<g8, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), rows,
+                                                       C, mean, invstd, gamma, beta, relu, ws, ws + C, rpb);
+    } else {
+        bn_bwd_reduce_kernel<Tx, Tg><<<grid, 256, 2 * 256 * 4, st>>>(reinterpret_cast<const Tx*>(x),
+                                                                    reinterpret_cast<const Tg*>(dy), rows, C, mean,
+                                                                    invstd, gamma, beta, relu, ws, ws + C, rpb);
+    }
+    LAUNCH_OK();
+    float* mean_g = reinterpret_cast<float*>(ws + 2 * C);  // third C doubles of the workspace: 2C floats
+    float* mean_gx = mean_g + C;
+    bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, (double)rows, C, mean_g, mean_gx, dgamma, dbeta, accumulate);
     LAUNCH_OK();
     if (dx) {
         if (C % 8) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward needs C %% 8 == 0");
         bn_bwd_apply_kernel<Tx, Tg><<<grid1d((rows * C + 7) / 8, 256, 148 * 8), 256, 0, st>>>(
             reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), reinterpret_cast<Tg*>(dx), rows * C, C,
-            (double)rows, mean, invstd, gamma, beta, relu, train, ws, ws + C);
-        LAUNCH_OK();
-    }
-    if (dgamma) {
-        bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, C, dgamma, dbeta, accumulate);
+            (double)rows, mean, invstd, gamma, beta, relu, train, mean_g, mean_gx);
         LAUNCH_OK();
     }
     return 0;
@@ -1201,11 +1219,11 @@ extern "C" int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void
 }
 extern "C" int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream) {
     if (dtype == FMRI_BF16)
-        relu_bwd_kernel<__nv_bfloat16><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+        relu_bwd_kernel<__nv_bfloat16><<<grid1d((n + 7) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
             reinterpret_cast<__nv_bfloat16*>(dx), n);
     else
-        relu_bwd_kernel<float><<<grid1d(n, 256), 256, 0, S(stream)>>>(
+        relu_bwd_kernel<float><<<grid1d((n + 7) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
             reinterpret_cast<const float*>(y), reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(dx), n);
     LAUNCH_OK();
     return 0;

@@ -575,35 +575,53 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
     }
 }
 
-// y = relu(gamma * (x - mean) * invstd + beta); 8 elements per thread, channels-last
+// y = relu(gamma * (x - mean) * invstd + beta); 8 elements per thread, channels-last, 128-bit loads/stores. The grid is
+// sized so that the grid stride is a multiple of C whenever possible: each thread then sees the same 8 channels in every
+// iteration and keeps their (mean, scale, beta) in registers instead of re-reading four per-channel arrays per element.
+template <typename T>
+__device__ __forceinline__ void bn_ld8(const T* p, float (&v)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[2 * j] = __uint_as_float(rr[j] << 16);
+            v[2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+        }
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const Tin* __restrict__ x, Tout* __restrict__ y,
                                                        long long total, int C, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int relu) {
-    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < total;
-         i += (long long)gridDim.x * blockDim.x * 8) {
-        const int c0 = (int)(i % C);
-        float v[8];
-        if constexpr (sizeof(Tin) == 2) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(x + i);
-            const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+    const long long step = (long long)gridDim.x * blockDim.x * 8;
+    long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+    if (i >= total) return;
+    const bool hoist = (step % C) == 0;
+    float mu[8], sc[8], be[8];
+    bool have = false;
+    for (; i < total; i += step) {
+        if (!hoist || !have) {
+            const int c0 = (int)(i % C);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[2 * j] = __uint_as_float(rr[j] << 16);
-                v[2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+            for (int j = 0; j < 8; ++j) {
+                mu[j] = __ldg(mean + c0 + j);
+                sc[j] = __ldg(gamma + c0 + j) * __ldg(invstd + c0 + j);
+                be[j] = __ldg(beta + c0 + j);
             }
-        } else {
-            const float4 a = *reinterpret_cast<const float4*>(x + i);
-            const float4 b = *reinterpret_cast<const float4*>(x + i + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            have = true;
         }
+        float v[8];
+        bn_ld8(x + i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            const float sc = __ldg(gamma + c) * __ldg(invstd + c);
-            float o = (v[j] - __ldg(mean + c)) * sc + __ldg(beta + c);
+            const float o = (v[j] - mu[j]) * sc[j] + be[j];
             v[j] = relu ? fmaxf(o, 0.f) : o;
         }
         if constexpr (sizeof(Tout) == 2) {
@@ -661,6 +679,75 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const Tx* __restrict
     }
 }
 
+// vectorised reductions over a channels-last [rows, C] matrix, C % 8 == 0: thread = 8 adjacent channels (one 128-bit load
+// per row) x row lane; per-thread fp32 partial sums over its rows, shared-memory reduction over the row lanes, fp64 atomics.
+//   MODE 0: per-channel sum(x), sum(x^2)                                            (BatchNorm batch statistics)
+//   MODE 1: per-channel sum(g), sum(g*xhat), g = dy masked by the ReLU of the forward (BatchNorm backward, pass 1)
+template <int MODE, typename Tx, typename Tg>
+__global__ void __launch_bounds__(256) bn_reduce8_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy, long long rows,
+                                                         int C, const float* __restrict__ mean,
+                                                         const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int relu,
+                                                         double* __restrict__ out_a, double* __restrict__ out_b,
+                                                         int rows_per_block) {
+    const int c8 = C >> 3;                      // 8-channel groups per row
+    const int cx = c8 >= 256 ? 256 : c8;        // groups handled side by side by one block
+    const int ry = 256 / cx;                    // row lanes
+    const int tc = threadIdx.x % cx, tr = threadIdx.x / cx;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    __shared__ float sred[2][8][256 + 1];
+    for (int gb = blockIdx.y * cx; gb < c8; gb += gridDim.y * cx) {
+        const int grp = gb + tc;
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        if (grp < c8 && tr < ry) {
+            const int c0 = grp * 8;
+            float mu[8], is[8], sc[8], be[8];
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; sc[j] = gamma[c0 + j] * is[j]; be[j] = beta[c0 + j];
+                }
+            }
+            for (long long r = r0 + tr; r < r1; r += ry) {
+                float xv[8];
+                bn_ld8(x + r * C + c0, xv);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s[j] += xv[j]; q[j] += xv[j] * xv[j]; }
+                } else {
+                    float gv[8];
+                    bn_ld8(dy + r * C + c0, gv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xc = xv[j] - mu[j];
+                        float g = gv[j];
+                        if (relu && !(xc * sc[j] + be[j] > 0.f)) g = 0.f;  // same expression as bn_apply_kernel -> same mask
+                        s[j] += g;
+                        q[j] += g * (xc * is[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sred[0][j][threadIdx.x] = s[j]; sred[1][j][threadIdx.x] = q[j]; }
+        __syncthreads();
+        if (tr == 0 && grp < c8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = s[j], b = q[j];
+                for (int l = 1; l < ry; ++l) { a += sred[0][j][l * cx + tc]; b += sred[1][j][l * cx + tc]; }
+                atomicAdd(out_a + grp * 8 + j, (double)a);
+                atomicAdd(out_b + grp * 8 + j, (double)b);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // backward pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat)). `train`=0 (eval-mode BN: statistics are
 // constants): dx = gamma*invstd*g. 8 channels-last elements per thread (C % 8 == 0), 128-bit loads/stores; the
 // per-channel means are taken once per channel in fp64 (sum/count) and rounded to fp32.
@@ -697,8 +784,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, int relu, int train,
-                                                           const double* __restrict__ sum_g,
-                                                           const double* __restrict__ sum_gx) {
+                                                           const float* __restrict__ mean_g,
+                                                           const float* __restrict__ mean_gx) {
     const long long step = (long long)gridDim.x * blockDim.x * 8;
     long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
     if (i >= total) return;
@@ -714,8 +801,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
             for (int j = 0; j < 8; ++j) {
                 const int c = cc + j;
                 mu[j] = mean[c]; is[j] = invstd[c]; sc[j] = gamma[c] * is[j]; be[j] = beta[c];
-                mg[j] = train ? (float)(sum_g[c] / count) : 0.f;
-                mgx[j] = train ? (float)(sum_gx[c] / count) : 0.f;
+                mg[j] = train ? mean_g[c] : 0.f;
+                mgx[j] = train ? mean_gx[c] : 0.f;
             }
         }
         float xv[8], gv[8], o[8];
@@ -732,18 +819,44 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
     }
 }
 
-__global__ void bn_param_grad_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, int C,
+// per channel, once: the fp32 means the apply pass needs (one fp64 division per CHANNEL instead of per thread) and the
+// parameter gradients dgamma = sum(g*xhat), dbeta = sum(g) (nullable)
+__global__ void bn_param_grad_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, double count,
+                                     int C, float* __restrict__ mean_g, float* __restrict__ mean_gx,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const float dg = (float)sum_gx[c], db = (float)sum_g[c];
-    dgamma[c] = accumulate ? dgamma[c] + dg : dg;
-    dbeta[c] = accumulate ? dbeta[c] + db : db;
+    mean_g[c] = (float)(sum_g[c] / count);
+    mean_gx[c] = (float)(sum_gx[c] / count);
+    if (dgamma) {
+        const float dg = (float)sum_gx[c], db = (float)sum_g[c];
+        dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+        dbeta[c] = accumulate ? dbeta[c] + db : db;
+    }
 }
 
-// relu backward on its own (bias+ReLU layers: discriminator conv0, WAE discriminator MLP): dx = dy * (y > 0)
+// relu backward on its own (bias+ReLU layers: discriminator conv0, WAE discriminator MLP): dx = dy * (y > 0);
+// 8 elements per thread when n % 8 == 0 (always, for channels-last tensors with C % 8 == 0)
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+    if ((n & 7) == 0) {
+        for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n;
+             i += (long long)gridDim.x * blockDim.x * 8) {
+            float a[8], g[8];
+            bn_ld8(y + i, a);
+            bn_ld8(dy + i, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+            if constexpr (sizeof(T) == 2) {
+                *reinterpret_cast<uint4*>(dx + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                               pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+            } else {
+                *reinterpret_cast<float4*>(dx + i) = make_float4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<float4*>(dx + i + 4) = make_float4(g[4], g[5], g[6], g[7]);
+            }
+        }
+        return;
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         st_f(dx + i, ld_f(y + i) > 0.f ? ld_f(dy + i) : 0.f);
 }

@@ -77,7 +77,7 @@ class BatchNorm:
         """dy has the gradient dtype; returns d(raw) in the same dtype."""
         C, pre = self.C, self.prefix
         if self._ws is None:
-            self._ws = E(2 * C, dtype=F64)
+            self._ws = E(3 * C, dtype=F64)
         draw = torch.empty(c.raw.shape, dtype=dy.dtype, device=dy.device)
         L.bn_backward(c.raw, dy, draw, c.rows, C, c.mean, c.invstd, P[pre + "weight"], P[pre + "bias"], c.relu,
                       c.train, G[pre + "weight"] if need_dw else None, G[pre + "bias"] if need_dw else None, acc,
