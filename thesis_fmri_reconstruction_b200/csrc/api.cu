@@ -474,24 +474,24 @@ static int run_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, in
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad launch
-template <int BN, int NCH, int STAGES>
-static int launch_wg(const WgParams& p, dim3 grid, cudaStream_t st) {
-    using L = WgSmem<BN, NCH, STAGES>;
+template <int BN, int NCH, int STAGES, int TG>
+static int launch_wg(const WgParams& p, cudaStream_t st) {
+    using L = WgSmem<BN, NCH, STAGES, TG>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<BN, NCH, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<BN, NCH, STAGES, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      L::TOTAL));
         attr_done = true;
     }
-    wgrad_kernel<BN, NCH, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    dim3 grid(p.num_taps / TG, p.m_tiles * p.n_tiles, p.splits);
+    wgrad_kernel<BN, NCH, STAGES, TG><<<grid, 192, L::TOTAL, st>>>(p);
     LAUNCH_OK();
     return 0;
 }
 static int dispatch_wg(const WgParams& p, int BN, int NCH, cudaStream_t st) {
-    dim3 grid(p.num_taps, p.m_tiles * p.n_tiles, p.splits);
-    if (NCH == 64 && BN == 128) return launch_wg<128, 64, 3>(p, grid, st);
-    if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4>(p, grid, st);
-    if (NCH == 32 && BN == 32) return launch_wg<32, 32, 4>(p, grid, st);
+    if (NCH == 64 && BN == 128) return launch_wg<128, 64, 3, 1>(p, st);
+    if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4, 1>(p, st);
+    if (NCH == 32 && BN == 32) return p.num_taps % 5 == 0 ? launch_wg<32, 32, 3, 5>(p, st) : launch_wg<32, 32, 4, 1>(p, st);
     return fail(FMRI_ERR_UNSUPPORTED, "wgrad tile BN=%d NCH=%d not instantiated", BN, NCH);
 }
 // ws[tap][m][n] += sum_pixels Dn[pixel][m] * Sh[pixel*stride + tap - 2][n]
@@ -550,7 +550,8 @@ static int run_wgrad_tc(const void* Dn, int N, int PH, int PW, int Cd, const voi
     p.m_tiles = cdiv(Cd, 128);
     p.n_tiles = Cs / BN;
     const long long pt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
-    const long long base = (long long)num_taps * p.m_tiles * p.n_tiles;
+    const int tap_groups = (NCH == 32 && BN == 32 && num_taps % 5 == 0) ? num_taps / 5 : num_taps;
+    const long long base = (long long)tap_groups * p.m_tiles * p.n_tiles;
     long long splits = std::max<long long>(1, (2 * 148 + base - 1) / base);
     splits = std::min<long long>(splits, std::max<long long>(1, pt / 4));
     p.splits = (int)splits;

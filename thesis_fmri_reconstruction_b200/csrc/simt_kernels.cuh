@@ -578,6 +578,28 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 // y = relu(gamma * (x - mean) * invstd + beta); 8 elements per thread, channels-last, 128-bit loads/stores. The grid is
 // sized so that the grid stride is a multiple of C whenever possible: each thread then sees the same 8 channels in every
 // iteration and keeps their (mean, scale, beta) in registers instead of re-reading four per-channel arrays per element.
+// Raw 8-element vectors (one or two 128-bit registers quads) so that the NEXT iteration's loads can be issued before the
+// current iteration's arithmetic: the BN kernels carry ~50 registers of per-channel coefficients, which limits occupancy, so
+// memory-level parallelism has to come from each thread keeping two iterations of loads in flight.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_ld(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void raw_ld(const float* p, Raw8<float>& r) {
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void raw_cvt(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+    const uint32_t rr[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(rr[j] << 16);
+        v[2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void raw_cvt(const Raw8<float>& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
 template <typename T>
 __device__ __forceinline__ void bn_ld8(const T* p, float (&v)[8]) {
     if constexpr (sizeof(T) == 2) {
@@ -606,7 +628,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const Tin* __restrict__ x
     const bool hoist = (step % C) == 0;
     float mu[8], sc[8], be[8];
     bool have = false;
+    Raw8<Tin> cur, nxt;
+    raw_ld(x + i, cur);
     for (; i < total; i += step) {
+        if (i + step < total) raw_ld(x + i + step, nxt);  // next iteration's load in flight during this one's math
         if (!hoist || !have) {
             const int c0 = (int)(i % C);
 #pragma unroll
@@ -618,7 +643,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const Tin* __restrict__ x
             have = true;
         }
         float v[8];
-        bn_ld8(x + i, v);
+        raw_cvt(cur, v);
+        cur = nxt;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float o = (v[j] - mu[j]) * sc[j] + be[j];
@@ -712,15 +738,26 @@ __global__ void __launch_bounds__(256) bn_reduce8_kernel(const Tx* __restrict__ 
                     mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; sc[j] = gamma[c0 + j] * is[j]; be[j] = beta[c0 + j];
                 }
             }
-            for (long long r = r0 + tr; r < r1; r += ry) {
+            Raw8<Tx> curx;
+            Raw8<Tg> curg;
+            long long r = r0 + tr;
+            if (r < r1) {
+                raw_ld(x + r * C + c0, curx);
+                if (MODE == 1) raw_ld(dy + r * C + c0, curg);
+            }
+            for (; r < r1; r += ry) {
                 float xv[8];
-                bn_ld8(x + r * C + c0, xv);
+                raw_cvt(curx, xv);
+                float gv[8];
+                if (MODE == 1) raw_cvt(curg, gv);
+                if (r + ry < r1) {  // next row's loads in flight during this row's math
+                    raw_ld(x + (r + ry) * C + c0, curx);
+                    if (MODE == 1) raw_ld(dy + (r + ry) * C + c0, curg);
+                }
                 if (MODE == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { s[j] += xv[j]; q[j] += xv[j] * xv[j]; }
                 } else {
-                    float gv[8];
-                    bn_ld8(dy + r * C + c0, gv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float xc = xv[j] - mu[j];
@@ -793,6 +830,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
     const bool hoist = (step % C) == 0;
     float mu[8], is[8], sc[8], be[8], mg[8], mgx[8];
     int c0 = -1;
+    Raw8<Tx> curx;
+    Raw8<Tg> curg;
+    raw_ld(x + i, curx);
+    raw_ld(dy + i, curg);
     for (; i < total; i += step) {
         const int cc = (int)(i % C);
         if (!hoist || c0 < 0) {
@@ -806,8 +847,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
             }
         }
         float xv[8], gv[8], o[8];
-        ld8(x + i, xv);
-        ld8(dy + i, gv);
+        raw_cvt(curx, xv);
+        raw_cvt(curg, gv);
+        if (i + step < total) {  // next iteration's loads in flight during this one's math
+            raw_ld(x + i + step, curx);
+            raw_ld(dy + i + step, curg);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float xc = xv[j] - mu[j];

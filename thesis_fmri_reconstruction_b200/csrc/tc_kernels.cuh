@@ -625,18 +625,22 @@ struct WgParams {
     float* out;
 };
 
-template <int BN, int NCH, int STAGES>
+// TG = filter taps handled by one CTA against the SAME dense-operand tile: with a 32-channel shifted side the dense tile
+// (32 KB) dwarfs a tap's shifted tile (8 KB), and one-tap CTAs re-fetch it 25x through L2 (wgrad_kernel<32,32,4> ran at
+// 184 TFLOP/s, 12 % tensor pipe). TG = 5 (one filter row) cuts the bytes per MMA-clock 2.9x; the TG accumulators sit side
+// by side in TMEM.
+template <int BN, int NCH, int STAGES, int TG = 1>
 struct WgSmem {
     static constexpr int D_BYTES = 128 * 128 * 2;  // [2 chunks][128 pixels][64 ch]
-    static constexpr int S_BYTES = 128 * BN * 2;   // [BN/NCH chunks][128 pixels][NCH ch]
-    static constexpr int STAGE_BYTES = D_BYTES + S_BYTES;
+    static constexpr int S_BYTES = 128 * BN * 2;   // [BN/NCH chunks][128 pixels][NCH ch] per tap
+    static constexpr int STAGE_BYTES = D_BYTES + TG * S_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-template <int BN, int NCH, int STAGES>
+template <int BN, int NCH, int STAGES, int TG>
 __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgParams p) {
-    using L = WgSmem<BN, NCH, STAGES>;
+    using L = WgSmem<BN, NCH, STAGES, TG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -646,7 +650,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tap = blockIdx.x;
+    const int tap0 = blockIdx.x * TG;
     const int mtile = blockIdx.y % p.m_tiles;
     const int ntile = blockIdx.y / p.m_tiles;
     const int split = blockIdx.z;
@@ -655,17 +659,16 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
     const int pt_end = (int)((long long)(split + 1) * pt_total / p.splits);
     if (pt_begin >= pt_end) return;
     const int npt = pt_end - pt_begin;
-    const TapDesc t = p.taps[tap];
 
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr int D_CHUNKS = 2;
+    constexpr uint32_t TMEM_COLS = (TG * BN) <= 32 ? 32 : ((TG * BN) <= 64 ? 64 : ((TG * BN) <= 128 ? 128 : ((TG * BN) <= 256 ? 256 : 512)));
+    static_assert(TG * BN <= 512, "accumulators must fit TMEM");
     constexpr int S_CHUNKS = BN / NCH;
     const uint32_t d_chunk_bytes = p.rows * 128;
     const uint32_t s_chunk_bytes = p.rows * NCH * 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.mapD);
-        tma_prefetch_desc(&p.mapS[t.map]);
+        tma_prefetch_desc(&p.mapS[p.taps[tap0].map]);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -686,21 +689,25 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const int st = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + S_CHUNKS * s_chunk_bytes);
+                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + TG * S_CHUNKS * s_chunk_bytes);
                 const int pt = pt_begin + i;
                 const int tx = pt % p.tiles_x;
                 const int ty = (pt / p.tiles_x) % p.tiles_y;
                 const int tn = pt / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
                 uint8_t* sd = smem + st * L::STAGE_BYTES;
-                uint8_t* ss = sd + L::D_BYTES;
                 for (int cchunk = 0; cchunk < d_chunks_live; ++cchunk)
                     tma_load_4d(sd + cchunk * d_chunk_bytes, &p.mapD, &full_bar[st], mtile * 128 + cchunk * 64, x0,
                                 y0, n0);
 #pragma unroll
-                for (int cchunk = 0; cchunk < S_CHUNKS; ++cchunk)
-                    tma_load_4d(ss + cchunk * s_chunk_bytes, &p.mapS[t.map], &full_bar[st],
-                                ntile * BN + cchunk * NCH, x0 + t.dx, y0 + t.dy, n0);
+                for (int tg = 0; tg < TG; ++tg) {
+                    const TapDesc t = p.taps[tap0 + tg];
+                    uint8_t* ss = sd + L::D_BYTES + tg * L::S_BYTES;
+#pragma unroll
+                    for (int cchunk = 0; cchunk < S_CHUNKS; ++cchunk)
+                        tma_load_4d(ss + cchunk * s_chunk_bytes, &p.mapS[t.map], &full_bar[st],
+                                    ntile * BN + cchunk * NCH, x0 + t.dx, y0 + t.dy, n0);
+                }
             }
         }
         __syncwarp();
@@ -716,13 +723,15 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 const uint32_t sd = smem_u32(smem + st * L::STAGE_BYTES);
-                const uint32_t ss = sd + L::D_BYTES;
                 // MN-major: LBO = distance between 64(32)-channel chunks, SBO = 8 pixel rows
                 const uint64_t adesc = umma_smem_desc(sd, d_chunk_bytes, 8 * 128, UMMA_SW128);
-                const uint64_t bdesc = umma_smem_desc(ss, s_chunk_bytes, 8 * s_row, s_layout);
-                for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(tmem_base, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc,
-                              (i | k) != 0);
+#pragma unroll
+                for (int tg = 0; tg < TG; ++tg) {
+                    const uint64_t bdesc = umma_smem_desc(sd + L::D_BYTES + tg * L::S_BYTES, s_chunk_bytes, 8 * s_row, s_layout);
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16(tmem_base + tg * BN, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc,
+                                  (i | k) != 0);
+                }
                 umma_commit(&empty_bar[st]);
             }
             umma_commit(tmem_full);
@@ -734,17 +743,20 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         const int q = warp & 3;
         const int m = mtile * 128 + q * 32 + lane;
         const bool valid = m < p.m_total;
-        float* orow = p.out + ((long long)tap * p.m_total + m) * p.n_total + ntile * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            if (valid) {
+        for (int tg = 0; tg < TG; ++tg) {
+            float* orow = p.out + ((long long)(tap0 + tg) * p.m_total + m) * p.n_total + ntile * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tg * BN + c0, v);
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    red_add_v4(orow + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(orow + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
             }
         }
         tc_fence_before();
