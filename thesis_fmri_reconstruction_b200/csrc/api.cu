@@ -483,13 +483,13 @@ static int launch_wg(const WgParams& p, cudaStream_t st) {
                                      L::TOTAL));
         attr_done = true;
     }
-    dim3 grid(p.num_taps / TG, p.m_tiles * p.n_tiles, p.splits);
+    dim3 grid(cdiv(p.num_taps, TG), p.m_tiles * p.n_tiles, p.splits);
     wgrad_kernel<BN, NCH, STAGES, TG><<<grid, 192, L::TOTAL, st>>>(p);
     LAUNCH_OK();
     return 0;
 }
 static int dispatch_wg(const WgParams& p, int BN, int NCH, cudaStream_t st) {
-    if (NCH == 64 && BN == 128) return launch_wg<128, 64, 3, 1>(p, st);
+    if (NCH == 64 && BN == 128) return p.num_taps > 1 ? launch_wg<128, 64, 2, 2>(p, st) : launch_wg<128, 64, 3, 1>(p, st);
     if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4, 1>(p, st);
     if (NCH == 32 && BN == 32) return p.num_taps % 5 == 0 ? launch_wg<32, 32, 3, 5>(p, st) : launch_wg<32, 32, 4, 1>(p, st);
     return fail(FMRI_ERR_UNSUPPORTED, "wgrad tile BN=%d NCH=%d not instantiated", BN, NCH);
@@ -550,7 +550,8 @@ static int run_wgrad_tc(const void* Dn, int N, int PH, int PW, int Cd, const voi
     p.m_tiles = cdiv(Cd, 128);
     p.n_tiles = Cs / BN;
     const long long pt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
-    const int tap_groups = (NCH == 32 && BN == 32 && num_taps % 5 == 0) ? num_taps / 5 : num_taps;
+    const int tap_groups = (NCH == 32 && BN == 32 && num_taps % 5 == 0) ? num_taps / 5
+                           : ((NCH == 64 && BN == 128 && num_taps > 1) ? (num_taps + 1) / 2 : num_taps);
     const long long base = (long long)tap_groups * p.m_tiles * p.n_tiles;
     long long splits = std::max<long long>(1, (2 * 148 + base - 1) / base);
     splits = std::min<long long>(splits, std::max<long long>(1, pt / 4));

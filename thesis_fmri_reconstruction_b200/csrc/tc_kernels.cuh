@@ -651,6 +651,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tap0 = blockIdx.x * TG;
+    const int tg_live = min(TG, p.num_taps - tap0);  // the last group may be short (25 taps, TG = 2)
     const int mtile = blockIdx.y % p.m_tiles;
     const int ntile = blockIdx.y / p.m_tiles;
     const int split = blockIdx.z;
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const int st = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + TG * S_CHUNKS * s_chunk_bytes);
+                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + tg_live * S_CHUNKS * s_chunk_bytes);
                 const int pt = pt_begin + i;
                 const int tx = pt % p.tiles_x;
                 const int ty = (pt / p.tiles_x) % p.tiles_y;
@@ -701,6 +702,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                                 y0, n0);
 #pragma unroll
                 for (int tg = 0; tg < TG; ++tg) {
+                    if (tg >= tg_live) break;
                     const TapDesc t = p.taps[tap0 + tg];
                     uint8_t* ss = sd + L::D_BYTES + tg * L::S_BYTES;
 #pragma unroll
@@ -727,6 +729,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const uint64_t adesc = umma_smem_desc(sd, d_chunk_bytes, 8 * 128, UMMA_SW128);
 #pragma unroll
                 for (int tg = 0; tg < TG; ++tg) {
+                    if (tg >= tg_live) break;
                     const uint64_t bdesc = umma_smem_desc(sd + L::D_BYTES + tg * L::S_BYTES, s_chunk_bytes, 8 * s_row, s_layout);
                     for (int k = 0; k < ksteps; ++k)
                         umma_bf16(tmem_base + tg * BN, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc,
@@ -744,7 +747,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         const int m = mtile * 128 + q * 32 + lane;
         const bool valid = m < p.m_total;
 #pragma unroll 1
-        for (int tg = 0; tg < TG; ++tg) {
+        for (int tg = 0; tg < tg_live; ++tg) {
             float* orow = p.out + ((long long)(tap0 + tg) * p.m_total + m) * p.n_total + ntile * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
