@@ -750,67 +750,164 @@ extern "C" int fmri_conv_wgrad(const fmri_conv_desc* d, const void* x, const voi
 }
 
 // ================================================================================================ edge convs
+// workspace of the edge convolutions: fp32 [75][C] staging of the CUDA-core kernels, or (tensor-core path) a 64 KB region for
+// the bf16 weight slab pack followed by the 3-channel image(s) repacked as bf16 NHWC with 8 channels (16 B per pixel)
+static const size_t HC_WS_PACK = 65536;
 extern "C" size_t fmri_edge_workspace(const fmri_edge_desc* d) {
-    // fp32 [75][C] staging of the SIMT kernels, or the bf16 slab pack [C/8][25*16][8] of the tensor-core path
-    return std::max(sizeof(float) * 75 * (size_t)d->C, (size_t)2 * 25 * 16 * d->C);
+    return std::max(sizeof(float) * 75 * (size_t)d->C, HC_WS_PACK + (size_t)d->N * d->H * d->W * 16);
 }
 
-// C -> 3 convolution, stride 1, on the halo-tile tcgen05 kernel: img[n,co,y,x] = act(bias + sum_{taps,c} X[n,y+kh-2,x+kw-2,c] * B[tap][co][c])
-// w element (co, c, tap) at w[co*s_co + c*s_c + tap]; flip uses tap 24-tap (data gradient of a 3 -> C convolution).
-// returns 1 when the shape does not fit the halo kernel (caller falls back to the CUDA-core kernel), 0 on success, <0 on error
-static int hconv_c_to_3(const void* X, int N, int H, int W, int C, const float* w, long long s_co, long long s_c, int flip,
-                        const float* bias, int act, float* img, void* ws, cudaStream_t st) {
-    constexpr int BN = 16;
-    if ((C != 32 && C != 64) || W + 4 > 160) return 1;
-    HcParams p;
+// ---- halo-tile tcgen05 convolution (hconv_kernels.cuh): plan + launch -------------------------------------------------
+// Builds the tile geometry, the MMA step list and the weight-pack spec for a 5x5 convolution read in gather form from an
+// NHWC bf16 input with 8*chunks channels. stride 1: one halo plane; stride 2: four stride-parity planes.
+// chunks >= 2: one step per (tap, 16-channel pair of slabs). chunks == 1 (3-channel image padded to 8): one step per PAIR of
+// taps (the two K halves of the MMA are two different windows of the same slab).
+// Returns false when the shape does not fit (caller falls back to the CUDA-core kernels).
+static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chunks, int stride, int OH, int OW, int BN,
+                     bool flip) {
     memset(&p, 0, sizeof(p));
-    p.X = reinterpret_cast<const __nv_bfloat16*>(X);
-    p.N = N; p.H = H; p.W = W; p.C = C;
-    p.num_planes = 1;
-    p.pl_ys[0] = p.pl_xs[0] = 1;
-    p.pl_yoff[0] = p.pl_xoff[0] = -2;
-    p.PW = W + 4;
-    p.OH = H; p.OW = W;
-    // rows per tile: as many as 5 sub-tiles of 128 virtual rows hold (fewer if shared memory is short), preferring a divisor of H
-    int tht = std::max(1, std::min(H, (5 * 128) / p.PW));
+    memset(&spec, 0, sizeof(spec));
+    p.N = N; p.H = H; p.W = W; p.chunks = chunks; p.OH = OH; p.OW = OW;
+    const int hx = stride == 1 ? 4 : 2;  // halo (columns = rows)
+    if (stride == 1) {
+        p.num_planes = 1;
+        p.pl_ys[0] = p.pl_xs[0] = 1;
+        p.pl_yoff[0] = p.pl_xoff[0] = -2;
+    } else {
+        p.num_planes = 4;
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const int pl = ph * 2 + pw;
+                p.pl_ys[pl] = p.pl_xs[pl] = 2;
+                p.pl_yoff[pl] = ph - 2;   // halo row sy = 0 is output row offset -1 of this parity plane
+                p.pl_xoff[pl] = pw - 2;
+            }
+    }
+    p.PW = OW + hx;
+    if (p.PW > 200) return false;
+    const int mt_max = std::min(5, 256 / BN);  // 2 accumulator buffers x MT x BN TMEM columns <= 512
+    const int max_off = hx * p.PW + hx;
+    const int nsteps = chunks >= 2 ? 25 * (chunks / 2) : 13;
+    if (nsteps > HC_MAX_STEPS) return false;
+    p.num_steps = nsteps;
+    int tht = std::max(1, std::min(OH, (mt_max * 128) / p.PW));
     for (;; --tht) {
-        if (tht < 1) return 1;
+        if (tht < 1) return false;
         int use = tht;
         for (int cand = tht; cand >= std::max(1, tht - 2); --cand)
-            if (H % cand == 0) { use = cand; break; }
+            if (OH % cand == 0) { use = cand; break; }
         p.THt = use;
-        p.tiles_y = cdiv(H, use);
+        p.tiles_y = cdiv(OH, use);
         p.MT = cdiv((long long)use * p.PW, 128);
-        p.G = std::max(1, std::min(3, 256 / (p.MT * BN)));  // 2 buffers x G x MT x BN TMEM columns <= 512
-        p.PH = use + 4;
-        const int need = std::max(p.PH * p.PW, p.MT * 128 + 4 * p.PW + 4 + 1);
+        p.PH = use + hx;
+        const int need = std::max(p.PH * p.PW, p.MT * 128 + max_off + 1);
         p.slab_rows = (need + 7) / 8 * 8;
-        p.num_taps = 25;
         if (hc_smem_bytes(p, BN) <= 227 * 1024) break;
     }
+    // window offset of every filter tap, in 16-byte rows from the start of a halo buffer
+    int woff[25];
     for (int kh = 0; kh < 5; ++kh)
         for (int kw = 0; kw < 5; ++kw) {
-            p.taps[kh * 5 + kw].plane = 0;
-            p.taps[kh * 5 + kw].row_off = kh * p.PW + kw;
+            int plane = 0, dyr = kh, dxr = kw;
+            if (stride == 2) {
+                plane = (kh & 1) * 2 + (kw & 1);
+                dyr = (kh - 2 - (kh & 1)) / 2 + 1;
+                dxr = (kw - 2 - (kw & 1)) / 2 + 1;
+            }
+            woff[kh * 5 + kw] = plane * chunks * p.slab_rows + dyr * p.PW + dxr;
         }
-    p.Bslab = reinterpret_cast<const __nv_bfloat16*>(ws);
-    p.img = img; p.bias = bias; p.act = act; p.n_out = 3; p.accumulate = 0;
+    int s = 0;
+    if (chunks >= 2) {
+        for (int tp = 0; tp < 25; ++tp)
+            for (int j = 0; j < chunks / 2; ++j, ++s) {
+                p.steps[s].a_off = woff[tp] + 2 * j * p.slab_rows;
+                p.steps[s].a_lbo = p.slab_rows;
+                p.steps[s].b_off = s * BN;
+                spec.tap[s][0] = spec.tap[s][1] = (int16_t)(flip ? 24 - tp : tp);
+                spec.cb[s][0] = (int16_t)(16 * j);
+                spec.cb[s][1] = (int16_t)(16 * j + 8);
+            }
+    } else {
+        int order[25];
+        for (int i = 0; i < 25; ++i) order[i] = i;
+        std::sort(order, order + 25, [&](int a, int b) { return woff[a] < woff[b]; });
+        for (int i = 0; i < 25; i += 2, ++s) {
+            const int t0 = order[i], t1 = i + 1 < 25 ? order[i + 1] : -1;
+            p.steps[s].a_off = woff[t0];
+            p.steps[s].a_lbo = t1 >= 0 ? woff[t1] - woff[t0] : 1;  // unpaired last tap: second K half gets zero weights
+            p.steps[s].b_off = s * BN;
+            spec.tap[s][0] = (int16_t)(flip ? 24 - t0 : t0);
+            spec.tap[s][1] = (int16_t)(t1 >= 0 ? (flip ? 24 - t1 : t1) : -1);
+            spec.cb[s][0] = spec.cb[s][1] = 0;
+            if (t1 >= 0 && p.steps[s].a_lbo == 0) return false;
+        }
+    }
+    return true;
+}
+
+template <int BN>
+static int hc_launch(const HcParams& p, cudaStream_t st) {
     const int smem = hc_smem_bytes(p, BN);
-    hc_pack_weights_kernel<<<cdiv((long long)C * 25 * BN, 256), 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(ws), C, BN, 3,
-                                                                            25, s_co, s_c, flip);
-    LAUNCH_OK();
     static int attr_smem = 0;
     if (smem > attr_smem) {
         CUDA_OK(cudaFuncSetAttribute(hconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    const int total_tiles = N * p.tiles_y;
-    const int per_sm = std::max(1, std::min(2, (227 * 1024) / smem));
+    const int total_tiles = p.N * p.tiles_y;
+    int tmem = 32;
+    while (tmem < 2 * p.MT * BN) tmem <<= 1;
+    const int per_sm = std::max(1, std::min(std::min(2, 512 / tmem), (227 * 1024) / smem));
     const int grid = std::min(total_tiles, 148 * per_sm);
     hconv_kernel<BN><<<grid, HC_THREADS, smem, st>>>(p);
     LAUNCH_OK();
     return 0;
 }
+static int hc_run(HcParams& p, const HcPackSpec& spec, int BN, const float* w, int n_real, int c_real, long long s_n,
+                  long long s_c, void* ws, cudaStream_t st) {
+    p.Bslab = reinterpret_cast<const __nv_bfloat16*>(ws);
+    if ((size_t)hc_b_bytes(p, BN) > HC_WS_PACK) return fail(FMRI_ERR_WORKSPACE, "hconv weight pack exceeds its workspace region");
+    hc_pack_weights_kernel<<<cdiv(2LL * p.num_steps * BN * 8, 256), 256, 0, st>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(ws), spec, p.num_steps, BN, n_real, c_real, s_n, s_c);
+    LAUNCH_OK();
+    switch (BN) {
+        case 16: return hc_launch<16>(p, st);
+        case 32: return hc_launch<32>(p, st);
+        case 64: return hc_launch<64>(p, st);
+    }
+    return fail(FMRI_ERR_UNSUPPORTED, "hconv BN=%d", BN);
+}
+
+// C -> 3 convolution, stride 1: img[n,co,y,x] = act(bias + sum_{taps,c} X[n,y+kh-2,x+kw-2,c] * w[co*s_co + c*s_c + tap]);
+// flip uses tap 24-tap (data gradient of a 3 -> C convolution). Returns 1 when the shape does not fit (fall back).
+static int hconv_c_to_3(const void* X, int N, int H, int W, int C, const float* w, long long s_co, long long s_c, int flip,
+                        const float* bias, int act, float* img, void* ws, cudaStream_t st) {
+    if (C != 32 && C != 64) return 1;
+    HcParams p;
+    HcPackSpec spec;
+    if (!hc_build(p, spec, N, H, W, C / 8, 1, H, W, 16, flip != 0)) return 1;
+    p.X = reinterpret_cast<const __nv_bfloat16*>(X);
+    p.epi = 0; p.out = img; p.bias = bias; p.act = act; p.n_out = 3;
+    return hc_run(p, spec, 16, w, 3, C, s_co, s_c, ws, st);
+}
+
+// 3 -> C convolution (stride 1 or 2) from up to three fp32 NCHW image sources: y[n,oy,ox,c] = act(bias[c] + sum_{taps,ci<3}
+// img[n,ci,oy*s+kh-2,ox*s+kw-2] * w[c*s_c + ci*s_ci + tap]); the images are first repacked to bf16 NHWC-8 in the workspace.
+static int hconv_3_to_c(const float* i0, const float* i1, const float* i2, int nps, int N, int H, int W, int C, int stride,
+                        const float* w, long long s_c, long long s_ci, int flip, const float* bias, int act, void* y,
+                        void* ws, cudaStream_t st) {
+    if (C != 32 && C != 64) return 1;
+    const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    HcParams p;
+    HcPackSpec spec;
+    if (!hc_build(p, spec, N, H, W, 1, stride, OH, OW, C, flip != 0)) return 1;
+    __nv_bfloat16* img8 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ws) + HC_WS_PACK);
+    img8_pack_kernel<<<grid1d((long long)N * H * W, 256), 256, 0, st>>>(i0, i1, i2, nps, N, (long long)H * W, img8);
+    LAUNCH_OK();
+    p.X = img8;
+    p.epi = 1; p.out = y; p.bias = bias; p.act = act; p.n_out = C;
+    return hc_run(p, spec, C, w, C, 3, s_c, s_ci, ws, st);
+}
+
 static int check_edge(const fmri_edge_desc* d, const void* ws, size_t ws_bytes) {
     if (!d || (d->C != 32 && d->C != 64)) return fail(FMRI_ERR_UNSUPPORTED, "edge conv supports C in {32,64}");
     if (d->stride != 1 && d->stride != 2) return fail(FMRI_ERR_ARG, "edge stride");
@@ -849,12 +946,18 @@ extern "C" int fmri_edge_in_fprop(const fmri_edge_desc* d, const float* img0, co
                                   size_t ws_bytes, void* stream) {
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
+    if (!img1) img1 = img0;
+    if (!img2) img2 = img0;
+    if (d->dtype == FMRI_BF16 && fmri_tensor_path_available()) {
+        // w layout [C][3][25]: y[.., c] = sum img[ci] * w[c*75 + ci*25 + tap]
+        rc = hconv_3_to_c(img0, img1, img2, n_per_src, d->N, d->H, d->W, d->C, d->stride, w, 75, 25, 0, bias, act, y, ws,
+                          S(stream));
+        if (rc <= 0) return rc;
+    }
     float* wk = reinterpret_cast<float*>(ws);
     rc = pack_edge_in(d, w, wk, S(stream));
     if (rc) return rc;
     const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
-    if (!img1) img1 = img0;
-    if (!img2) img2 = img0;
     return d->C == 32 ? edge_in_fprop_t<32>(d, img0, img1, img2, n_per_src, wk, bias, act, y, OH, OW, S(stream))
                       : edge_in_fprop_t<64>(d, img0, img1, img2, n_per_src, wk, bias, act, y, OH, OW, S(stream));
 }
@@ -875,15 +978,15 @@ extern "C" int fmri_edge_in_dgrad(const fmri_edge_desc* d, const void* dy, const
                                   size_t ws_bytes, void* stream) {
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
-    float* wk = reinterpret_cast<float*>(ws);
-    rc = pack_edge_in(d, w, wk, S(stream));
-    if (rc) return rc;
     const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
     if (d->dtype == FMRI_BF16 && d->stride == 1 && fmri_tensor_path_available()) {
         // dimg[n,ci,y,x] = sum dy[n,y+kh-2,x+kw-2,c] * w[c][ci][24-tap]  (w layout [C][3][25])
         rc = hconv_c_to_3(dy, d->N, d->H, d->W, d->C, w, 25, 75, 1, nullptr, 0, dimg, ws, S(stream));
         if (rc <= 0) return rc;
     }
+    float* wk = reinterpret_cast<float*>(ws);
+    rc = pack_edge_in(d, w, wk, S(stream));
+    if (rc) return rc;
     // image pixel gathers from the C-side grid (OH,OW); stride 1: flipped taps, stride 2: divisibility form
     const int flip = d->stride == 1 ? 1 : 0;
     return d->C == 32 ? edge_to3_t<32>(d->dtype, dy, wk, nullptr, dimg, d->N, OH, OW, d->H, d->W, d->stride, flip, 0,
@@ -927,7 +1030,7 @@ extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, co
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
     float* dwk = reinterpret_cast<float*>(ws);
-    CUDA_OK(cudaMemsetAsync(dwk, 0, fmri_edge_workspace(d), S(stream)));
+    CUDA_OK(cudaMemsetAsync(dwk, 0, sizeof(float) * 75 * (size_t)d->C, S(stream)));
     const int OH = (d->H - 1) / d->stride + 1, OW = (d->W - 1) / d->stride + 1;
     if (!img1) img1 = img0;
     if (!img2) img2 = img0;
@@ -965,6 +1068,12 @@ extern "C" int fmri_edge_out_dgrad(const fmri_edge_desc* d, const float* dimg, c
     int rc = check_edge(d, ws, ws_bytes);
     if (rc) return rc;
     if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
+    if (d->dtype == FMRI_BF16 && fmri_tensor_path_available()) {
+        // w layout [3][C][25]: dx[p][c] = sum_{co,tap'} dimg[co][p + tap' - 2] * w[co*25C + c*25 + 24 - tap']
+        rc = hconv_3_to_c(dimg, dimg, dimg, d->N, d->N, d->H, d->W, d->C, 1, w, 25, 25LL * d->C, 1, nullptr, 0, dx, ws,
+                          S(stream));
+        if (rc <= 0) return rc;
+    }
     float* wk = reinterpret_cast<float*>(ws);
     // dx[p][c] = sum_{co,tap'} dimg[co][p + tap' - 2] * w[co][c][24 - tap']  -> "3 -> C" form with a flipped pack
     rc = pack_edge_out(d, w, wk, 1, S(stream));
@@ -979,7 +1088,7 @@ extern "C" int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const
     if (rc) return rc;
     if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
     float* dwk = reinterpret_cast<float*>(ws);
-    CUDA_OK(cudaMemsetAsync(dwk, 0, fmri_edge_workspace(d), S(stream)));
+    CUDA_OK(cudaMemsetAsync(dwk, 0, sizeof(float) * 75 * (size_t)d->C, S(stream)));
     rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
                                        1, -1, S(stream))
                     : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,

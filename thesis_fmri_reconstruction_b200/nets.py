@@ -41,6 +41,19 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+class _EdgeWs:
+    """Grow-only workspace of the edge convolutions (sized by fmri_edge_workspace of the largest descriptor seen)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, d):
+        need = L.edge_workspace(d)
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = E(need, dtype=torch.uint8)
+        return self.buf
+
+
 # ====================================================================================================== BatchNorm
 class BatchNorm:
     """nn.BatchNorm{1,2}d(momentum=0.9) + optional ReLU over a channels-last [rows, C] matrix."""
@@ -277,6 +290,7 @@ class EncoderNet:
         self.heads = LatentHeads(z, cfg["fc_output"], adt)
         self.Clast = ch[2]
         self._ews = None
+        self._ewsm = _EdgeWs()
 
     def param_names(self):
         n = ["conv.0.conv.weight"] + self.bn0.names()
@@ -290,8 +304,7 @@ class EncoderNet:
 
     def _edge(self, N, H, W):
         d = L.edge_desc(N, H, W, self.C0, 2, self.adt)
-        if self._ews is None:
-            self._ews = E(L.edge_workspace(d), dtype=torch.uint8)
+        self._ews = self._ewsm.get(d)
         return d
 
     def forward(self, P, S, x, train=True, n_updates=1, nbt=None):
@@ -343,6 +356,7 @@ class DecoderNet:
                        for i, (ci, co) in enumerate(chans)]
         self.Cl = dc[2]
         self._ews = None
+        self._ewsm = _EdgeWs()
 
     def param_names(self):
         n = self.fc.names()
@@ -377,8 +391,7 @@ class DecoderNet:
             cs.append(c)
             h, w = c.OH, c.OW
         d3 = L.edge_desc(B, h, w, self.Cl, 1, self.adt)
-        if self._ews is None:
-            self._ews = E(L.edge_workspace(d3), dtype=torch.uint8)
+        self._ews = self._ewsm.get(d3)
         img = E(B, 3, h, w)
         L.edge_out_fprop(d3, y, P["conv.3.0.weight"], P["conv.3.0.bias"], L.ACT_TANH, img, self._ews)
         return img, Ctx(fc=cfc, blocks=cs, d3=d3, a3=y, img=img, B=B, hw=(h, w))
@@ -420,6 +433,7 @@ class DiscriminatorNet:
         self.fc = LinearBlock("fc.0.weight", "fc.1.", cfg["fc_output_gan"], self.fg ** 2 * ch[3], adt)
         self.F = cfg["fc_output_gan"]
         self._ews = None
+        self._ewsm = _EdgeWs()
 
     def param_names(self):
         n = ["conv.0.0.weight", "conv.0.0.bias"]
@@ -438,8 +452,7 @@ class DiscriminatorNet:
         Bs, _, H, W = imgs[0].shape
         N = Bs * len(imgs)
         d0 = L.edge_desc(N, H, W, self.C0, self.stride0, self.adt)
-        if self._ews is None:
-            self._ews = E(L.edge_workspace(d0), dtype=torch.uint8)
+        self._ews = self._ewsm.get(d0)
         OH, OW = (H - 1) // self.stride0 + 1, (W - 1) // self.stride0 + 1
         y0 = E(N, OH, OW, self.C0, dtype=self.adt)
         L.edge_in_fprop(d0, imgs, Bs, P["conv.0.0.weight"], P["conv.0.0.bias"], L.ACT_RELU, y0, self._ews)
