@@ -207,3 +207,30 @@ def test_cognitive_stage_bf16_tensor_path(stage):
     assert max(rep["forward"].values()) < 2e-2, rep["forward"]
     assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
     assert rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2
+
+
+@pytest.mark.parametrize("adt,B", [(torch.float32, 4), (torch.bfloat16, 16)])
+def test_stage1_vaegan_100x100_config(adt, B):
+    """The reference's ACTIVE configuration (configs/models_config.py:13-21): 100x100 images, latent 512, stride_gan 2,
+    output_pad [False, True, True], odd feature maps 13/25/50 -- every kernel's ragged-tile / odd-parity path."""
+    seed = 100
+    P, S = O.make_vaegan(O.CFG100, seed=seed)
+    x = O.synthetic_images(B, size=100, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 512, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_vaegan_step(P, S_ref, x, eps, z_p, cfg=O.CFG100, update=False)
+    tr = engine.VaeGanStage1(P, S, hp.CFG100, 512, adt)
+    out = tr.forward_backward(x.cuda(), eps.cuda(), z_p.cuda())
+    torch.cuda.synchronize()
+    grads = tr.named_grads()
+    fwd = dict(mu=rel(out["mu"], ref["mu"]), x_tilde=rel(out["x_tilde"], ref["x_tilde"]),
+               disc_layer=rel(nchw_flat(out["disc_layer_nhwc"]), ref["disc_layer"]),
+               disc_class=rel(out["disc_class"], ref["disc_class"].reshape(-1)), kl=rel(out["kl"], ref["kl"]),
+               mse=rel(out["mse"], ref["mse"]))
+    gerr = {}
+    for b in ("encoder.", "decoder.", "discriminator."):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    print(adt, "100x100 forward", fwd, "grad buckets", gerr)
+    assert max(fwd.values()) < (1e-4 if adt == torch.float32 else 2e-2), fwd
+    assert max(gerr.values()) < (5e-3 if adt == torch.float32 else 0.5), gerr
