@@ -445,10 +445,14 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs the loop converged with warp-uniform operands; one ELECTED lane issues each tcgen05
+        // instruction (umma_bf16_elect). Issuing from inside `if (lane == 0)` costs ~15 extra instructions per MMA (an
+        // ELECT / R2UR / branch waterfall), which made every N <= 128 launch issue-bound (64-clock MMAs).
+        {
             constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
             constexpr uint64_t layout = (KCH == 64) ? UMMA_SW128 : UMMA_SW64;
             constexpr uint32_t sbo = 8 * KCH * 2;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
@@ -470,12 +474,12 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
                         const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
-                            umma_bf16(tmem_base + buf * ACC_COLS + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                      (ks | k) != 0);
+                            umma_bf16_elect(tmem_u + buf * ACC_COLS + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                            (ks | k) != 0);
                     }
-                    umma_commit(&empty_bar[st]);
+                    umma_commit_elect(&empty_bar[st]);
                 }
-                umma_commit(&tfull[buf]);
+                umma_commit_elect(&tfull[buf]);
                 ++lt;
             }
         }
@@ -714,10 +718,11 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // warp-converged issue loop, one elected lane per tcgen05 instruction (see igemm_persistent_kernel)
             constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
             constexpr uint64_t s_layout = (NCH == 64) ? UMMA_SW128 : UMMA_SW64;
             constexpr uint32_t s_row = NCH * 2;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const int ksteps = p.rows / 16;
             for (int i = 0; i < npt; ++i) {
                 const int st = i % STAGES;
@@ -732,12 +737,12 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                     if (tg >= tg_live) break;
                     const uint64_t bdesc = umma_smem_desc(sd + L::D_BYTES + tg * L::S_BYTES, s_chunk_bytes, 8 * s_row, s_layout);
                     for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(tmem_base + tg * BN, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc,
-                                  (i | k) != 0);
+                        umma_bf16_elect(tmem_u + tg * BN, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4),
+                                        idesc, (i | k) != 0);
                 }
-                umma_commit(&empty_bar[st]);
+                umma_commit_elect(&empty_bar[st]);
             }
-            umma_commit(tmem_full);
+            umma_commit_elect(tmem_full);
         }
         __syncwarp();
     } else {
