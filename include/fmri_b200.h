@@ -61,9 +61,19 @@ int fmri_conv_pack_weights(const fmri_conv_desc* d, const float* w, void* pack_f
  * path), `pack_f` bf16 pack (used by the bf16 path). */
 int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const float* w, const void* pack_f, const float* bias,
                     int act, void* y, double* stat_sum, double* stat_sq, void* stream);
-/* dx = conv data-gradient of dy (replaces aten::convolution_backward input-grad) */
+/* Optional fusion for fmri_conv_dgrad: when dx is the upstream gradient of a BatchNorm(+ReLU) layer whose pre-BN input is
+ * `x` (same [N,H,W,Cin] layout and dtype as dx), the call also leaves that layer's backward sums in `sums`:
+ * sums[c] = sum g, sums[Cin + c] = sum g * xhat, g = dx masked by the forward ReLU. Pass the same buffer as the `ws` of
+ * fmri_bn_backward with sums_ready = 1 (the separate reduction pass, 2 of BN-backward's 5 tensor passes, disappears). */
+typedef struct {
+    const void* x;
+    const float *mean, *invstd, *gamma, *beta;
+    int relu;
+    double* sums; /* >= 3 * Cin doubles (fmri_bn_backward workspace) */
+} fmri_bn_fuse;
+/* dx = conv data-gradient of dy (replaces aten::convolution_backward input-grad); fuse nullable */
 int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const float* w, const void* pack_d, void* dx,
-                    void* stream);
+                    const fmri_bn_fuse* fuse, void* stream);
 /* dw (+)= conv weight-gradient, reference layout fp32. Workspace: fmri_conv_wgrad_workspace() bytes. */
 size_t fmri_conv_wgrad_workspace(const fmri_conv_desc* d);
 int fmri_conv_wgrad(const fmri_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
@@ -133,7 +143,7 @@ int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long ro
 /* dx, dgamma (+)=, dbeta (+)= ; train=0 treats mean/invstd as constants (eval-mode BN). ws: 3*C doubles. */
 int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, int train,
-                     float* dgamma, float* dbeta, int accumulate, double* ws, void* stream);
+                     float* dgamma, float* dbeta, int accumulate, double* ws, int sums_ready, void* stream);
 int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream);
 int fmri_colsum(const void* x, int dtype, long long rows, int C, float* out /* += */, void* stream);
 

@@ -440,3 +440,37 @@ def test_layout_converters():
     L.cast2d(src, 3620, dst, 3624, 10, 3620)
     torch.cuda.synchronize()
     assert torch.equal(dst[:, :3620], src.to(torch.bfloat16)) and float(dst[:, 3620:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("case", [(4, 16, 16, 64, 128), (2, 32, 32, 32, 128), (3, 25, 25, 32, 128), (8, 8, 8, 128, 256)])
+def test_conv_dgrad_fused_bn_backward_sums(case):
+    """fmri_conv_dgrad with fmri_bn_fuse: the data gradient also leaves sum(g), sum(g*xhat) of the BN(+ReLU) layer it feeds
+    (g = stored dx masked by the forward ReLU). Checked against torch on the kernel's own bf16 dx; run once normally (small
+    launches fall back to the explicit reduction) and once with FMRI_IGEMM_PERSISTENT=2 (fused epilogue). Tolerance 2e-3."""
+    N, H, W, Cin, Cout = case
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(21)
+    w = rnd((torch.randn(Cout, Cin, 5, 5, generator=g) * 0.05).to(DEV), dtype)
+    d = L.conv_desc(N, H, W, Cin, Cout, 2, False, 0, dtype)
+    OH, OW = L.conv_out_hw(d)
+    dy = rnd(torch.randn(N, Cout, OH, OW, generator=g).to(DEV), dtype)
+    xlow = rnd(torch.randn(N, H, W, Cin, generator=g).to(DEV), dtype).to(dtype)        # pre-BN tensor of the layer below (NHWC)
+    mean = (torch.randn(Cin, generator=g) * 0.1).to(DEV)
+    invstd = (torch.rand(Cin, generator=g) + 0.5).to(DEV)
+    gamma = (torch.rand(Cin, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(Cin, generator=g) * 0.2).to(DEV)
+    pack_d = torch.empty(L.conv_pack_elems(d), dtype=torch.bfloat16, device=DEV)
+    L.conv_pack_weights(d, w, None, pack_d)
+    dx = torch.full((N, H, W, Cin), float("nan"), dtype=dtype, device=DEV)
+    sums = torch.full((3 * Cin,), float("nan"), dtype=torch.float64, device=DEV)
+    L.conv_dgrad(d, nhwc(dy).to(dtype), w, pack_d, dx, (xlow, mean, invstd, gamma, beta, True, sums))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=2, padding=2)
+    assert rel(nchw(dx), ref) < tol(dtype)
+    xc = xlow.float() - mean
+    mask = (xc * (gamma * invstd) + beta) > 0
+    gm = torch.where(mask, dx.float(), torch.zeros((), device=DEV)).double()
+    want_g = gm.reshape(-1, Cin).sum(0)
+    want_gx = (gm * (xc * invstd).double()).reshape(-1, Cin).sum(0)
+    assert rel(sums[:Cin], want_g) < 2e-3
+    assert rel(sums[Cin:2 * Cin], want_gx) < 2e-3

@@ -144,6 +144,7 @@ static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st)
     LAUNCH_OK();
     return 0;
 }
+static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
 static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)
 static int dispatch_ig_persistent(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
     if (KCH == 64) {
@@ -172,8 +173,11 @@ static int dispatch_ig(const IgParams& p, int BN, int KCH, int classes, cudaStre
             env_done = true;
         }
         const long long all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * classes;
-        if (g_ig_persistent && p.splits == 1 && (all >= 2 * 148 || g_ig_persistent == 2))  // 2: always (tests)
+        g_last_ig_was_persistent = false;
+        if (g_ig_persistent && p.splits == 1 && (all >= 2 * 148 || g_ig_persistent == 2)) {  // 2: always (tests)
+            g_last_ig_was_persistent = true;
             return dispatch_ig_persistent(p, BN, KCH, classes, st);
+        }
     }
     // two M sub-tiles per CTA (shared weight tile) once there is more than a few waves of work
     const long long ctas = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.splits * classes;
@@ -219,9 +223,19 @@ static void pick_box_pow2(int X, int Y, int N, int* bw, int* bh, int* bn) {
 
 // Gather-form plan: out[n,oy,ox,:] = sum_taps X[n, oy*s+kh-2, ox*s+kw-2, :] * pack[tap]
 // (Conv2d fprop; ConvTranspose2d dgrad). X: [N,H,W,Ck] bf16, out: [N,OH,OW,Ng].
+struct BnbFuse {  // fused BatchNorm-backward statistics of the layer whose dy this data gradient produces
+    const void* x;
+    const float *mean, *invstd, *gamma, *beta;
+    int relu;
+};
+static void apply_fuse(IgParams& p, const BnbFuse* f) {
+    if (!f) return;
+    p.bnb_x = f->x; p.bnb_mean = f->mean; p.bnb_invstd = f->invstd; p.bnb_gamma = f->gamma; p.bnb_beta = f->beta;
+    p.bnb_relu = f->relu;
+}
 static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, int stride, const void* pack,
                       const float* bias, int act, void* out, int out_fp32, double* ssum, double* ssq,
-                      cudaStream_t st) {
+                      cudaStream_t st, const BnbFuse* fuse = nullptr) {
     if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
@@ -287,17 +301,18 @@ static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW
     p.act = act;
     p.stat_sum = ssum;
     p.stat_sq = ssq;
+    apply_fuse(p, fuse);
     return dispatch_ig(p, BN, KCH, 1, st);
 }
 
 // Scatter-form plan (stride 2): out[n, 2a+ph, 2b+pw, :] = sum_{kh = ph (mod 2), kw = pw (mod 2)} X[n, a+(ph+2-kh)/2, ..] * pack[tap]
 // (ConvTranspose2d fprop; Conv2d dgrad). X: [N,H,W,Ck], out: [N,OH,OW,Ng] with OH in {2H-1, 2H}.
 static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
-                              double* ssum, double* ssq, cudaStream_t st);
+                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse);
 static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, const void* pack, void* out,
-                       double* ssum, double* ssq, cudaStream_t st) {
+                       double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse = nullptr) {
     if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
-    if (Ng == 32) return run_scatter_merged(X, N, H, W, Ck, OH, OW, pack, out, ssum, ssq, st);
+    if (Ng == 32) return run_scatter_merged(X, N, H, W, Ck, OH, OW, pack, out, ssum, ssq, st, fuse);
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
     memset(&p, 0, sizeof(p));
@@ -348,13 +363,14 @@ static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int O
     p.out_fp32 = 0;
     p.stat_sum = ssum;
     p.stat_sq = ssq;
+    apply_fuse(p, fuse);
     return dispatch_ig(p, BN, KCH, 4, st);
 }
 
 // Parity-merged scatter plan for Ng == 32 (IgParams::merge): one gather over the 3x3 coarse neighbourhood, N = 4 x 32.
 // `pack` is the ordinary tap-major pack [25][32][Ck] followed by the merged pack [9][128][Ck] (fmri_conv_pack_elems).
 static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
-                              double* ssum, double* ssq, cudaStream_t st) {
+                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse) {
     const int Ng = 32;
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
@@ -404,6 +420,7 @@ static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH
     p.merge_oh = OH;
     p.merge_ow = OW;
     p.merge_sy = (long long)OW * Ng;
+    apply_fuse(p, fuse);
     return dispatch_ig(p, BN, KCH, 1, st);
 }
 
@@ -676,23 +693,51 @@ extern "C" int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const flo
     return 0;
 }
 
+static int bn_bwd_sums(const void* x, int x_dtype, const void* dy, int g_dtype, long long rows, int C, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, int relu, double* ws, cudaStream_t st);
+
 extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const float* w, const void* pack_d, void* dx,
-                               void* stream) {
+                               const fmri_bn_fuse* fuse, void* stream) {
     int rc = check_conv(d);
     if (rc) return rc;
     int OH, OW;
     fmri_conv_out_hw(d, &OH, &OW);
+    const long long rows_in = (long long)d->N * d->H * d->W;
     if (d->dtype == FMRI_BF16) {
         if (!pack_d) return fail(FMRI_ERR_ARG, "bf16 conv dgrad needs the packed weights");
+        BnbFuse bf;
+        double *sg = nullptr, *sgx = nullptr;
+        if (fuse) {
+            if (d->Cin > 256) return fail(FMRI_ERR_UNSUPPORTED, "fused BN-backward statistics need <= 256 channels");
+            bf.x = fuse->x; bf.mean = fuse->mean; bf.invstd = fuse->invstd; bf.gamma = fuse->gamma; bf.beta = fuse->beta;
+            bf.relu = fuse->relu;
+            sg = fuse->sums;
+            sgx = fuse->sums + d->Cin;
+            CUDA_OK(cudaMemsetAsync(fuse->sums, 0, sizeof(double) * 2 * d->Cin, S(stream)));
+        }
         if (d->transposed)  // gather over dy at stride 2
-            return run_gather(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, 2, pack_d, nullptr, 0, dx, 0, nullptr,
-                              nullptr, S(stream));
-        if (d->stride == 2)
-            return run_scatter(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, pack_d, dx, nullptr, nullptr, S(stream));
-        return fail(FMRI_ERR_UNSUPPORTED, "stride-1 conv dgrad on the tensor path");
+            rc = run_gather(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, 2, pack_d, nullptr, 0, dx, 0, sg, sgx, S(stream),
+                            fuse ? &bf : nullptr);
+        else if (d->stride == 2)
+            rc = run_scatter(dy, d->N, OH, OW, d->Cout, d->H, d->W, d->Cin, pack_d, dx, sg, sgx, S(stream),
+                             fuse ? &bf : nullptr);
+        else
+            return fail(FMRI_ERR_UNSUPPORTED, "stride-1 conv dgrad on the tensor path");
+        if (rc) return rc;
+        if (fuse && !g_last_ig_was_persistent) {
+            // small launch (one tile per CTA kernel): that epilogue produced plain sum(dx) / sum(dx^2); redo the sums properly
+            return bn_bwd_sums(fuse->x, FMRI_BF16, dx, FMRI_BF16, rows_in, d->Cin, fuse->mean, fuse->invstd, fuse->gamma,
+                               fuse->beta, fuse->relu, fuse->sums, S(stream));
+        }
+        return 0;
     }
-    return direct_conv<float>(d, true, reinterpret_cast<const float*>(dy), w, nullptr, 0, reinterpret_cast<float*>(dx),
-                              S(stream));
+    rc = direct_conv<float>(d, true, reinterpret_cast<const float*>(dy), w, nullptr, 0, reinterpret_cast<float*>(dx),
+                            S(stream));
+    if (rc) return rc;
+    if (fuse)
+        return bn_bwd_sums(fuse->x, FMRI_F32, dx, FMRI_F32, rows_in, d->Cin, fuse->mean, fuse->invstd, fuse->gamma, fuse->beta,
+                           fuse->relu, fuse->sums, S(stream));
+    return 0;
 }
 
 extern "C" size_t fmri_conv_wgrad_workspace(const fmri_conv_desc* d) {
@@ -1283,9 +1328,8 @@ extern "C" int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, l
     return 0;
 }
 template <typename Tx, typename Tg>
-static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int C, const float* mean,
-                    const float* invstd, const float* gamma, const float* beta, int relu, int train, float* dgamma,
-                    float* dbeta, int accumulate, double* ws, cudaStream_t st) {
+static int bn_bwd_reduce_t(const void* x, const void* dy, long long rows, int C, const float* mean, const float* invstd,
+                           const float* gamma, const float* beta, int relu, double* ws, cudaStream_t st) {
     const int rpb = rows_per_block_for(rows);
     dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
     CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
@@ -1299,6 +1343,27 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
                                                                     invstd, gamma, beta, relu, ws, ws + C, rpb);
     }
     LAUNCH_OK();
+    return 0;
+}
+static int bn_bwd_sums(const void* x, int x_dtype, const void* dy, int g_dtype, long long rows, int C, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, int relu, double* ws, cudaStream_t st) {
+    if (C < 256 && (256 % C)) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward C=%d", C);
+    if (x_dtype == FMRI_BF16 && g_dtype == FMRI_BF16)
+        return bn_bwd_reduce_t<__nv_bfloat16, __nv_bfloat16>(x, dy, rows, C, mean, invstd, gamma, beta, relu, ws, st);
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_BF16)
+        return bn_bwd_reduce_t<float, __nv_bfloat16>(x, dy, rows, C, mean, invstd, gamma, beta, relu, ws, st);
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_F32)
+        return bn_bwd_reduce_t<float, float>(x, dy, rows, C, mean, invstd, gamma, beta, relu, ws, st);
+    return fail(FMRI_ERR_UNSUPPORTED, "bn_backward dtype combination");
+}
+template <typename Tx, typename Tg>
+static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int C, const float* mean,
+                    const float* invstd, const float* gamma, const float* beta, int relu, int train, float* dgamma,
+                    float* dbeta, int accumulate, double* ws, int sums_ready, cudaStream_t st) {
+    if (!sums_ready) {
+        int rc = bn_bwd_reduce_t<Tx, Tg>(x, dy, rows, C, mean, invstd, gamma, beta, relu, ws, st);
+        if (rc) return rc;
+    }
     float* mean_g = reinterpret_cast<float*>(ws + 2 * C);  // third C doubles of the workspace: 2C floats
     float* mean_gx = mean_g + C;
     bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, (double)rows, C, mean_g, mean_gx, dgamma, dbeta, accumulate);
@@ -1315,17 +1380,17 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
 extern "C" int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
                                 const float* mean, const float* invstd, const float* gamma, const float* beta,
                                 int relu, int train, float* dgamma, float* dbeta, int accumulate, double* ws,
-                                void* stream) {
+                                int sums_ready, void* stream) {
     if (C < 256 && (256 % C)) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward C=%d", C);
     if (x_dtype == FMRI_BF16 && g_dtype == FMRI_BF16)
         return bn_bwd_t<__nv_bfloat16, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train,
-                                                      dgamma, dbeta, accumulate, ws, S(stream));
+                                                      dgamma, dbeta, accumulate, ws, sums_ready, S(stream));
     if (x_dtype == FMRI_F32 && g_dtype == FMRI_BF16)
         return bn_bwd_t<float, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
-                                              accumulate, ws, S(stream));
+                                              accumulate, ws, sums_ready, S(stream));
     if (x_dtype == FMRI_F32 && g_dtype == FMRI_F32)
         return bn_bwd_t<float, float>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
-                                      accumulate, ws, S(stream));
+                                      accumulate, ws, sums_ready, S(stream));
     return fail(FMRI_ERR_UNSUPPORTED, "bn_backward dtype combination");
 }
 extern "C" int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream) {

@@ -59,6 +59,16 @@ struct IgParams {
     int merge;              // 0 / 1
     int merge_oh, merge_ow; // fine output extent
     long long merge_sy;     // fine row stride (elements)
+    // Fused BatchNorm-backward statistics (persistent kernel, bf16 output): when this launch is the data gradient that
+    // produces dy for a BN(+ReLU) layer, the epilogue also accumulates, per channel, sum(g) and sum(g * xhat) into
+    // stat_sum / stat_sq, with g = the stored dy masked by the forward ReLU and xhat from that layer's pre-BN tensor bnb_x
+    // (same layout as `out`). This removes the separate reduction pass of BN backward (2 of its 5 tensor passes).
+    const void* bnb_x;
+    const float* bnb_mean;
+    const float* bnb_invstd;
+    const float* bnb_gamma;
+    const float* bnb_beta;
+    int bnb_relu;
 };
 
 // MT = number of 128-row M sub-tiles one CTA accumulates against the SAME B (weight) tile: the kernels are bound by
@@ -71,7 +81,8 @@ struct IgSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = STAT_OFF + 2 * BN * 4 + 1024;  // +1024: manual base alignment
+    static constexpr int BNP_OFF = STAT_OFF + 2 * BN * 4;       // [4][256] BN-backward coefficients (mean, scale, beta, invstd)
+    static constexpr int TOTAL = BNP_OFF + 4 * 256 * 4 + 1024;  // +1024: manual base alignment
 };
 
 // transposing butterfly: on exit lane l holds the sum over the 32 lanes of f[l]
@@ -407,6 +418,17 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+    float* s_bnp = reinterpret_cast<float*>(smem + L::BNP_OFF);
+    if (p.bnb_x) {
+        const int nch = p.merge ? 32 : p.n_total;  // channels of the BN layer (<= 256)
+        for (int i = threadIdx.x; i < nch; i += blockDim.x) {
+            const float is = p.bnb_invstd[i];
+            s_bnp[i] = p.bnb_mean[i];
+            s_bnp[256 + i] = p.bnb_gamma[i] * is;
+            s_bnp[512 + i] = p.bnb_beta[i];
+            s_bnp[768 + i] = is;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -575,10 +597,36 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
                     }
                     if (do_stats) {
                         float g2[32];
+                        if (p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
+                            const int cb = (p.merge ? 0 : nt * BN) + stat_col;
+                            float xv[32];
+                            if (valid) {
+                                const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(p.bnb_x) + off + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            f[j] = valid ? f[j] : 0.f;
-                            g2[j] = f[j] * f[j];
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xp + 8 * j4));
+                                    const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        xv[8 * j4 + 2 * j] = __uint_as_float(rr[j] << 16);
+                                        xv[8 * j4 + 2 * j + 1] = __uint_as_float(rr[j] & 0xffff0000u);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float xc = (valid ? xv[j] : 0.f) - s_bnp[cb + j];
+                                float g = valid ? f[j] : 0.f;
+                                if (p.bnb_relu && !(xc * s_bnp[256 + cb + j] + s_bnp[512 + cb + j] > 0.f)) g = 0.f;
+                                f[j] = g;
+                                g2[j] = g * (xc * s_bnp[768 + cb + j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                f[j] = valid ? f[j] : 0.f;
+                                g2[j] = f[j] * f[j];
+                            }
                         }
                         const float s1 = warp_colsum32(f, lane);
                         const float s2 = warp_colsum32(g2, lane);

@@ -32,6 +32,11 @@ class EdgeDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("N", "H", "W", "C", "stride", "dtype")]
 
 
+class BnFuse(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("relu", C.c_int), ("sums", C.c_void_p)]
+
+
 class LinearDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("M", "N", "K", "dtype")]
 
@@ -198,10 +203,17 @@ def conv_fprop(d, x, w, pack_f, bias, act, y, stat_sum=None, stat_sq=None):
                                   ptr(stat_sq), stream()))
 
 
-def conv_dgrad(d, dy, w, pack_d, dx):
+def conv_dgrad(d, dy, w, pack_d, dx, fuse=None):
+    """fuse = (x, mean, invstd, gamma, beta, relu, sums): also produce the BN-backward sums of the layer dx feeds."""
     _require_cuda(dy, w, pack_d, dx)
     _note_flops(_conv_flops(d))
-    _check(load().fmri_conv_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(pack_d), ptr(dx), stream()))
+    f = None
+    if fuse is not None:
+        x, mean, invstd, gamma, beta, relu, sums = fuse
+        _require_cuda(x, mean, invstd, gamma, beta, sums)
+        f = BnFuse(x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(relu),
+                   sums.data_ptr())
+    _check(load().fmri_conv_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(pack_d), ptr(dx), C.byref(f) if f else None, stream()))
 
 
 def conv_wgrad_workspace(d):
@@ -311,11 +323,12 @@ def bn_apply(x, y, rows, Cc, mean, invstd, gamma, beta, relu):
                                 ptr(beta), int(relu), stream()))
 
 
-def bn_backward(x, dy, dx, rows, Cc, mean, invstd, gamma, beta, relu, train, dgamma, dbeta, accumulate, ws):
+def bn_backward(x, dy, dx, rows, Cc, mean, invstd, gamma, beta, relu, train, dgamma, dbeta, accumulate, ws,
+                sums_ready=False):
     _require_cuda(x, dy, dx, mean, invstd, gamma, beta, dgamma, dbeta, ws)
     _check(load().fmri_bn_backward(ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), _ll(rows), Cc, ptr(mean), ptr(invstd),
                                    ptr(gamma), ptr(beta), int(relu), int(train), ptr(dgamma), ptr(dbeta),
-                                   int(accumulate), ptr(ws), stream()))
+                                   int(accumulate), ptr(ws), int(sums_ready), stream()))
 
 
 def relu_backward(y, dy, dx):

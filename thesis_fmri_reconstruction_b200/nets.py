@@ -86,7 +86,17 @@ class BatchNorm:
         L.bn_apply(raw, y, rows, C, mean, invstd, P[pre + "weight"], P[pre + "bias"], relu)
         return y, Ctx(raw=raw, mean=mean, invstd=invstd, rows=rows, relu=relu, train=train)
 
-    def backward(self, P, c, dy, G, acc, need_dw):
+    def fuse_spec(self, P, c):
+        """Arguments that let the data-gradient kernel producing this layer's dy also compute its backward sums
+        (fmri_bn_fuse); only for train-mode BN over at most 256 channels stored in bf16."""
+        if not c.train or self.C > 256 or c.raw.dtype != BF16:
+            return None
+        if self._ws is None:
+            self._ws = E(3 * self.C, dtype=F64)
+        pre = self.prefix
+        return (c.raw, c.mean, c.invstd, P[pre + "weight"], P[pre + "bias"], c.relu, self._ws)
+
+    def backward(self, P, c, dy, G, acc, need_dw, sums_ready=False):
         """dy has the gradient dtype; returns d(raw) in the same dtype."""
         C, pre = self.C, self.prefix
         if self._ws is None:
@@ -94,7 +104,7 @@ class BatchNorm:
         draw = torch.empty(c.raw.shape, dtype=dy.dtype, device=dy.device)
         L.bn_backward(c.raw, dy, draw, c.rows, C, c.mean, c.invstd, P[pre + "weight"], P[pre + "bias"], c.relu,
                       c.train, G[pre + "weight"] if need_dw else None, G[pre + "bias"] if need_dw else None, acc,
-                      self._ws)
+                      self._ws, sums_ready)
         return draw
 
 
@@ -134,11 +144,13 @@ class ConvBlock:
                                 stats if train else None, nbt)
         return y, Ctx(d=d, x=x, bn=cb, pack_f=self.pack_f, pack_d=self.pack_d, OH=OH, OW=OW)
 
-    def backward(self, P, c, dy, G, acc, need_dw, need_dx):
-        draw = self.bn.backward(P, c.bn, dy, G, acc, need_dw)
-        return self.backward_raw(P, c, draw, G, acc, need_dw, need_dx)
+    def backward(self, P, c, dy, G, acc, need_dw, need_dx, sums_ready=False, fuse=None):
+        """sums_ready: the kernel that produced dy already left this BN's backward sums (see fuse_spec).
+        fuse: fuse_spec of the layer BELOW, handed to this layer's data-gradient kernel."""
+        draw = self.bn.backward(P, c.bn, dy, G, acc, need_dw, sums_ready)
+        return self.backward_raw(P, c, draw, G, acc, need_dw, need_dx, fuse)
 
-    def backward_raw(self, P, c, draw, G, acc, need_dw, need_dx):
+    def backward_raw(self, P, c, draw, G, acc, need_dw, need_dx, fuse=None):
         """Backward from a gradient on the raw (pre-BN) conv output -- the discriminator's feature tap (vae_gan.py:169-173)."""
         w = P[self.prefix + "conv.weight"]
         if need_dw:
@@ -148,8 +160,31 @@ class ConvBlock:
         dx = None
         if need_dx:
             dx = torch.empty(c.x.shape, dtype=self.adt, device=draw.device)
-            L.conv_dgrad(c.d, draw, w, c.pack_d, dx)
+            L.conv_dgrad(c.d, draw, w, c.pack_d, dx, fuse)
         return dx
+
+
+# Fusing the BN-backward reduction into the data-gradient epilogue (fmri_bn_fuse) removes 2 of BN-backward's 5 tensor passes
+# (-8.5 ms/step at B = 4096) but the heavier epilogue stops hiding behind the next tile's main loop in the persistent kernel
+# (+15.6 ms/step on the data-gradient launches), so it is OFF by default until the epilogue is spread over more warps.
+FUSE_BN_BWD = False
+
+
+def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_ready=False):
+    """Backward through a stack of ConvBlocks (last block first). Each block's data-gradient kernel also produces the
+    BatchNorm-backward sums of the block below it (fmri_bn_fuse), so that block's BN backward skips its reduction pass.
+    lower = (BatchNorm, ctx) of the BN below blocks[0], if any. Returns (dx of blocks[0], sums_ready for `lower`)."""
+    ready = first_ready
+    for i in range(len(blocks) - 1, -1, -1):
+        if not FUSE_BN_BWD:
+            fuse = None
+        elif i > 0:
+            fuse = blocks[i - 1].bn.fuse_spec(P, ctxs[i - 1].bn)
+        else:
+            fuse = lower[0].fuse_spec(P, lower[1]) if lower is not None else None
+        dy = blocks[i].backward(P, ctxs[i], dy, G, acc, need_dw, True, ready, fuse)
+        ready = fuse is not None
+    return dy, ready
 
 
 # ====================================================================================================== linear pieces
@@ -335,9 +370,8 @@ class EncoderNet:
         h, w = c.hw
         dy = E(B, h, w, self.Clast, dtype=self.adt)
         L.nchw_to_nhwc(dflat, dy, B, self.Clast, h, w)
-        for b, cb in zip(reversed(self.blocks), reversed(c.blocks)):
-            dy = b.backward(P, cb, dy, G, acc, need_dw, True)
-        draw0 = self.bn0.backward(P, c.c0, dy, G, acc, need_dw)
+        dy, ready = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, (self.bn0, c.c0))
+        draw0 = self.bn0.backward(P, c.c0, dy, G, acc, need_dw, ready)
         if need_dw:
             L.edge_in_wgrad(c.d0, [c.x], B, draw0, G["conv.0.conv.weight"], acc, self._ews)
 
@@ -407,8 +441,7 @@ class DecoderNet:
             L.edge_out_wgrad(c.d3, c.a3, dpre, G["conv.3.0.weight"], acc, self._ews)
         dy = torch.empty(c.a3.shape, dtype=self.adt, device=dpre.device)
         L.edge_out_dgrad(c.d3, dpre, P["conv.3.0.weight"], dy, self._ews)
-        for blk, cb in zip(reversed(self.blocks), reversed(c.blocks)):
-            dy = blk.backward(P, cb, dy, G, acc, need_dw, True)
+        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw)
         f = self.fi
         dflat = E(B, self.size * f * f, dtype=self.adt)
         L.nhwc_to_nchw(dy, dflat, B, self.size, f, f)
@@ -503,15 +536,14 @@ class DiscriminatorNet:
         h, w = c.hw
         dy = E(N, h, w, self.Cl, dtype=self.adt)
         L.nchw_to_nhwc(dflat, dy, N, self.Cl, h, w)
-        for b, cb in zip(reversed(self.blocks), reversed(c.blocks)):
-            dy = b.backward(P, cb, dy, G, acc, need_dw, True)
+        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw)
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
     def backward_rec(self, P, c, draw3, G=None, acc=False, need_dw=False, img_slices=None):
         """Backward of the feature-tap path from a gradient on the raw conv output of block 3 [N,h,w,C] (adt)."""
-        dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True)
-        for b, cb in zip(reversed(self.blocks[:2]), reversed(c.blocks[:2])):
-            dy = b.backward(P, cb, dy, G, acc, need_dw, True)
+        fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if FUSE_BN_BWD else None
+        dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True, fuse)
+        dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None)
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
 
