@@ -236,7 +236,8 @@ def test_linear(case, dtype):
 def test_edge_in(C, stride, dtype):
     N, H, W = 6, 16, 16
     g = torch.Generator(device="cpu").manual_seed(6)
-    imgs = [torch.randn(N // 3, 3, H, W, generator=g).to(DEV).requires_grad_(True) for _ in range(3)]
+    # the tensor path repacks the 3-channel side to bf16 (NHWC-8): pre-round it like every other bf16 operand
+    imgs = [rnd(torch.randn(N // 3, 3, H, W, generator=g).to(DEV), dtype).requires_grad_(True) for _ in range(3)]
     # weights pre-rounded to the compute dtype: the tensor path consumes bf16 weight packs (as in the conv tests above)
     w = rnd((torch.randn(C, 3, 5, 5, generator=g) * 0.1).to(DEV), dtype).requires_grad_(True)
     b = torch.randn(C, generator=g).to(DEV)
@@ -281,7 +282,7 @@ def test_edge_out(C, dtype):
     L.edge_out_fprop(d, xs, w.detach(), b, L.ACT_TANH, img, ws)
     torch.cuda.synchronize()
     assert rel(img, ref) < tol(dtype, out_bf16=False)
-    dimg = torch.randn_like(pre).float()
+    dimg = rnd(torch.randn_like(pre).float(), dtype)
     gx, gw = torch.autograd.grad(pre, (x, w), dimg.double())
     dx = torch.full((N, H, W, C), float("nan"), dtype=dtype, device=DEV)
     L.edge_out_dgrad(d, dimg, w.detach(), dx, ws)

@@ -10,6 +10,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "hconv_kernels.cuh"
+#include "hwgrad_kernels.cuh"
 
 using namespace fmri;
 
@@ -953,6 +954,50 @@ static int hconv_3_to_c(const float* i0, const float* i1, const float* i2, int n
     return hc_run(p, spec, C, w, C, 3, s_c, s_ci, ws, st);
 }
 
+// Edge-conv weight gradient on tcgen05 (hwgrad_kernels.cuh), stride 1. T: [N,PH,PW,C] bf16 NHWC; the 3-channel side comes as
+// up to three fp32 NCHW sources and is repacked to NHWC-8 in the workspace. dwk: fp32 [75][C] (zeroed by the caller).
+// Returns 1 when the shape does not fit (caller falls back to the CUDA-core kernel).
+static int g_hw_variant = -1;
+static int hwgrad_run(const void* T, const float* i0, const float* i1, const float* i2, int nps, int N, int PH, int PW, int C,
+                      float* dwk, float* dbias, int flip, void* ws, cudaStream_t st) {
+    if (g_hw_variant < 0) {
+        const char* e = getenv("FMRI_HWGRAD");   // -1/unset: default variant 0; 0/1: descriptor variant; 2: disable
+        g_hw_variant = e ? atoi(e) : 0;
+    }
+    if (g_hw_variant == 2) return 1;
+    if (C != 32 && C != 64) return 1;
+    HwParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.PH = PH; p.PW = PW; p.C = C;
+    p.PWp = (PW + 4 + 15) / 16 * 16;
+    if (p.PWp > 128) return 1;
+    p.bh = std::max(1, std::min(PH, 128 / p.PWp));
+    while (p.bh > 1 && PH % p.bh) --p.bh;
+    p.tiles_y = cdiv(PH, p.bh);
+    p.slab_rows = ((p.bh + 4) * p.PWp + 16 + 7) / 8 * 8;
+    if (hw_smem_bytes(p) > 227 * 1024) return 1;
+    const long long dims[4] = {C, PW, PH, N};
+    const long long strides[3] = {C, (long long)PW * C, (long long)PH * PW * C};
+    const int box[4] = {64, p.PWp, p.bh, 1};
+    if (make_map(&p.mapT, T, 4, dims, strides, box, 128)) return 1;  // e.g. a box the driver rejects: CUDA-core fallback
+    __nv_bfloat16* img8 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ws) + HC_WS_PACK);
+    img8_pack_kernel<<<grid1d((long long)N * PH * PW, 256), 256, 0, st>>>(i0, i1, i2, nps, N, (long long)PH * PW, img8);
+    LAUNCH_OK();
+    p.img8 = img8;
+    p.dwk = dwk; p.dbias = dbias; p.flip = flip; p.desc_variant = g_hw_variant;
+    const int smem = hw_smem_bytes(p);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        CUDA_OK(cudaFuncSetAttribute(hwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const int total = N * p.tiles_y;
+    const int per_sm = std::max(1, std::min(2, (227 * 1024) / smem));
+    hwgrad_kernel<<<std::min(total, 148 * per_sm), HW_THREADS, smem, st>>>(p);
+    LAUNCH_OK();
+    return 0;
+}
+
 static int check_edge(const fmri_edge_desc* d, const void* ws, size_t ws_bytes) {
     if (!d || (d->C != 32 && d->C != 64)) return fail(FMRI_ERR_UNSUPPORTED, "edge conv supports C in {32,64}");
     if (d->stride != 1 && d->stride != 2) return fail(FMRI_ERR_ARG, "edge stride");
@@ -1080,10 +1125,14 @@ extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, co
     if (!img1) img1 = img0;
     if (!img2) img2 = img0;
     if (dbias && !accumulate) CUDA_OK(cudaMemsetAsync(dbias, 0, sizeof(float) * d->C, S(stream)));
-    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
-                                       d->stride, 1, S(stream))
-                    : edge_wgrad_t<64>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
-                                       d->stride, 1, S(stream));
+    rc = 1;
+    if (d->dtype == FMRI_BF16 && d->stride == 1 && fmri_tensor_path_available())
+        rc = hwgrad_run(dy, img0, img1, img2, n_per_src, d->N, d->H, d->W, d->C, dwk, dbias, 0, ws, S(stream));
+    if (rc == 1)
+        rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
+                                           d->stride, 1, S(stream))
+                        : edge_wgrad_t<64>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
+                                           d->stride, 1, S(stream));
     if (rc) return rc;
     // dwk[(ci*25+tap)*C + c] -> dw[c][ci][tap]
     scatter4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, S(stream)>>>(dwk, dw, 1, 3, 25, d->C, 0, 25, 1,
@@ -1134,10 +1183,14 @@ extern "C" int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const
     if (d->stride != 1) return fail(FMRI_ERR_UNSUPPORTED, "edge out conv is stride 1");
     float* dwk = reinterpret_cast<float*>(ws);
     CUDA_OK(cudaMemsetAsync(dwk, 0, sizeof(float) * 75 * (size_t)d->C, S(stream)));
-    rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
-                                       1, -1, S(stream))
-                    : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
-                                       1, -1, S(stream));
+    rc = 1;
+    if (d->dtype == FMRI_BF16 && fmri_tensor_path_available())
+        rc = hwgrad_run(x, dimg, dimg, dimg, d->N, d->N, d->H, d->W, d->C, dwk, nullptr, 1, ws, S(stream));
+    if (rc == 1)
+        rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
+                                           1, -1, S(stream))
+                        : edge_wgrad_t<64>(d->dtype, x, dimg, dimg, dimg, d->N, dwk, nullptr, d->N, d->H, d->W, d->H, d->W,
+                                           1, -1, S(stream));
     if (rc) return rc;
     // dwk[(co*25+tap)*C + c] -> dw[co][c][tap]
     scatter4_kernel<float, float><<<grid1d(75LL * d->C, 256), 256, 0, S(stream)>>>(dwk, dw, 1, 3, 25, d->C, 0,
