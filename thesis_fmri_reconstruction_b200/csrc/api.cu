@@ -975,7 +975,13 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
     while (p.bh > 1 && PH % p.bh) --p.bh;
     p.tiles_y = cdiv(PH, p.bh);
     p.slab_rows = ((p.bh + 4) * p.PWp + 16 + 7) / 8 * 8;
+    p.d_chunk = (p.bh * p.PWp * 128 + 1023) / 1024 * 1024;
+    p.stages = 2;
     if (hw_smem_bytes(p) > 227 * 1024) return 1;
+    while (p.stages < HW_MAX_STAGES) {
+        ++p.stages;
+        if (hw_smem_bytes(p) > 200 * 1024) { --p.stages; break; }
+    }
     const long long dims[4] = {C, PW, PH, N};
     const long long strides[3] = {C, (long long)PW * C, (long long)PH * PW * C};
     const int box[4] = {64, p.PWp, p.bh, 1};
@@ -992,8 +998,7 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
         attr_smem = smem;
     }
     const int total = N * p.tiles_y;
-    const int per_sm = std::max(1, std::min(2, (227 * 1024) / smem));
-    hwgrad_kernel<<<std::min(total, 148 * per_sm), HW_THREADS, smem, st>>>(p);
+    hwgrad_kernel<<<std::min(total, 148), HW_THREADS, smem, st>>>(p);
     LAUNCH_OK();
     return 0;
 }

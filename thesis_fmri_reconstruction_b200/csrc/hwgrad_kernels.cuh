@@ -31,25 +31,27 @@ struct HwParams {
     float* dbias;                // [C] fp32 += sum_p T[p][c], nullable
     int flip;                    // write tap 24-tap (C -> 3 conv: T is the conv input, img the output gradient)
     int desc_variant;            // B descriptor stride assignment (see kernel)
+    int stages;                  // pipeline depth (<= HW_MAX_STAGES): the tiles are small, so depth hides the L2 latency
+    int d_chunk;                 // bytes between the two 64-channel chunks of an A stage (rows*128 rounded up to 1 KB)
 };
 
-constexpr int HW_STAGES = 3;
+constexpr int HW_MAX_STAGES = 8;
 constexpr int HW_THREADS = 384;
 constexpr int HW_PRODUCERS = 160;   // warps 2-6
-constexpr int HW_D_BYTES = 128 * 128;        // one A stage: up to 128 pixels x 64 channels (128 B rows)
-__host__ __device__ inline int hw_stage_bytes(const HwParams& p) { return 2 * HW_D_BYTES + ((p.slab_rows * 16 + 1023) / 1024) * 1024; }
-__host__ __device__ inline int hw_smem_bytes(const HwParams& p) { return HW_STAGES * hw_stage_bytes(p) + 2048 + 256 + 1024; }
+__host__ __device__ inline int hw_stage_bytes(const HwParams& p) { return 2 * p.d_chunk + ((p.slab_rows * 16 + 1023) / 1024) * 1024; }
+__host__ __device__ inline int hw_smem_bytes(const HwParams& p) { return p.stages * hw_stage_bytes(p) + 2048 + 256 + 1024; }
 
 __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constant__ HwParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = hw_stage_bytes(p);
+    const int HW_STAGES = p.stages;
     uint8_t* s_ones = smem + HW_STAGES * stage_bytes;                 // [128 rows][16 B] of bf16 1.0
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + 2048);
     uint64_t* full_bar = bars;                    // [STAGES] count = 1 (TMA expect_tx) + producers
-    uint64_t* empty_bar = bars + HW_STAGES;       // [STAGES] count = 1 (tcgen05.commit)
-    uint64_t* tmem_full = bars + 2 * HW_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HW_STAGES + 1);
+    uint64_t* empty_bar = bars + HW_MAX_STAGES;   // [STAGES] count = 2 (one tcgen05.commit per issuing warp)
+    uint64_t* tmem_full = bars + 2 * HW_MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HW_MAX_STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.N * p.tiles_y;
@@ -60,9 +62,9 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
         tma_prefetch_desc(&p.mapT);
         for (int s = 0; s < HW_STAGES; ++s) {
             mbar_init(&full_bar[s], 1 + HW_PRODUCERS);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);   // two issuing warps commit
         }
-        mbar_init(tmem_full, 1);
+        mbar_init(tmem_full, 2);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -93,8 +95,9 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer (warp-converged, elected lane) =================
+    } else if (warp == 1 || warp == 7) {
+        // ================= MMA issuers (warp-converged, elected lane): warp 1 issues kh 0,2,4, warp 7 kh 1,3 + bias ======
+        const int w2 = warp == 1 ? 0 : 1;
         const uint32_t idesc = umma_idesc_bf16(128, 48, true, true);
         const uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -108,17 +111,17 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             mbar_wait(&full_bar[st], ph);
             tc_fence_after();
             const uint32_t sd = smem_u32(smem + st * stage_bytes);
-            const uint32_t ss = sd + 2 * HW_D_BYTES;
-            const uint64_t adesc = umma_smem_desc(sd, HW_D_BYTES, 8 * 128, UMMA_SW128);   // as wgrad_kernel: LBO = 64-channel chunk
+            const uint32_t ss = sd + 2 * p.d_chunk;
+            const uint64_t adesc = umma_smem_desc(sd, p.d_chunk, 8 * 128, UMMA_SW128);   // as wgrad_kernel: LBO = 64-channel chunk
             const uint64_t bdesc = umma_smem_desc(ss, b_lbo, b_sbo, 0);
             const uint64_t odesc = umma_smem_desc(smem_u32(s_ones), b_lbo, b_sbo, 0);
             for (int k = 0; k < ksteps; ++k) {
                 const uint64_t ak = adesc + ((k * 16 * 128) >> 4);
                 const uint32_t acc = (it | k) != 0;
 #pragma unroll
-                for (int kh = 0; kh < 5; ++kh)
+                for (int kh = w2; kh < 5; kh += 2)
                     umma_bf16_elect(tmem_u + kh * 48, ak, bdesc + (uint32_t)(k * 16 + kh * p.PWp), idesc, acc);
-                if (p.dbias) umma_bf16_elect(tmem_u + 240, ak, odesc + (uint32_t)(k * 16), idesc1, acc);
+                if (p.dbias && w2 == 1) umma_bf16_elect(tmem_u + 240, ak, odesc + (uint32_t)(k * 16), idesc1, acc);
             }
             umma_commit_elect(&empty_bar[st]);
         }
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             const uint32_t ph = (it / HW_STAGES) & 1;
             const int n = t / p.tiles_y, y0 = (t - n * p.tiles_y) * p.bh;
             mbar_wait(&empty_bar[st], ph ^ 1);
-            const uint32_t ss = smem_u32(smem + st * stage_bytes) + 2 * HW_D_BYTES;
+            const uint32_t ss = smem_u32(smem + st * stage_bytes) + 2 * p.d_chunk;
             const __nv_bfloat16* In = p.img8 + (size_t)n * p.PH * p.PW * 8;
             int row = ptid;
             int sy = row / p.PWp, sx = row - sy * p.PWp;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
     }
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);  // the allocating warp
 }
 
 }  // namespace fmri
