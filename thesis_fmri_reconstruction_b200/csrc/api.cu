@@ -831,14 +831,24 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
     }
     p.PW = OW + hx;
     if (p.PW > 200) return false;
-    const int mt_max = std::min(5, 256 / BN);  // 2 accumulator buffers x MT x BN TMEM columns <= 512
+    // Every role of the kernel is a latency-bound single-warp chain (ncu: ~11 cycles per issued instruction per warp), so two
+    // co-resident CTAs per SM nearly double the throughput: prefer a plan with <= 256 TMEM columns and <= 110 KB of shared
+    // memory; fall back to one big CTA per SM.
     const int max_off = hx * p.PW + hx;
     const int nsteps = chunks >= 2 ? 25 * (chunks / 2) : 13;
     if (nsteps > HC_MAX_STEPS) return false;
     p.num_steps = nsteps;
-    int tht = std::max(1, std::min(OH, (mt_max * 128) / p.PW));
+    int mt_max = std::min(5, 128 / BN);         // 2 buffers x MT x BN <= 256 columns
+    size_t smem_cap = 110 * 1024;
+    int tht = mt_max >= 1 ? std::max(1, std::min(OH, (mt_max * 128) / p.PW)) : 0;
     for (;; --tht) {
-        if (tht < 1) return false;
+        if (tht < 1) {
+            if (smem_cap == 227 * 1024) return false;
+            mt_max = std::min(5, 256 / BN);     // one CTA per SM: 2 buffers x MT x BN <= 512 columns
+            smem_cap = 227 * 1024;
+            tht = std::max(1, std::min(OH, (mt_max * 128) / p.PW)) + 1;
+            continue;
+        }
         int use = tht;
         for (int cand = tht; cand >= std::max(1, tht - 2); --cand)
             if (OH % cand == 0) { use = cand; break; }
@@ -848,7 +858,7 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
         p.PH = use + hx;
         const int need = std::max(p.PH * p.PW, p.MT * 128 + max_off + 1);
         p.slab_rows = (need + 7) / 8 * 8;
-        if (hc_smem_bytes(p, BN) <= 227 * 1024) break;
+        if ((size_t)hc_smem_bytes(p, BN) <= smem_cap) break;
     }
     // window offset of every filter tap, in 16-byte rows from the start of a halo buffer
     int woff[25];
@@ -978,9 +988,9 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
     p.d_chunk = (p.bh * p.PWp * 128 + 1023) / 1024 * 1024;
     p.stages = 2;
     if (hw_smem_bytes(p) > 227 * 1024) return 1;
-    while (p.stages < HW_MAX_STAGES) {
+    while (p.stages < HW_MAX_STAGES) {  // two co-resident CTAs per SM (each role is a latency-bound single-warp chain)
         ++p.stages;
-        if (hw_smem_bytes(p) > 200 * 1024) { --p.stages; break; }
+        if (hw_smem_bytes(p) > 110 * 1024) { --p.stages; break; }
     }
     const long long dims[4] = {C, PW, PH, N};
     const long long strides[3] = {C, (long long)PW * C, (long long)PH * PW * C};
@@ -998,7 +1008,7 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
         attr_smem = smem;
     }
     const int total = N * p.tiles_y;
-    hwgrad_kernel<<<std::min(total, 148), HW_THREADS, smem, st>>>(p);
+    hwgrad_kernel<<<std::min(total, 148 * (smem <= 110 * 1024 ? 2 : 1)), HW_THREADS, smem, st>>>(p);
     LAUNCH_OK();
     return 0;
 }
