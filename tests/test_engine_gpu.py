@@ -234,3 +234,23 @@ def test_stage1_vaegan_100x100_config(adt, B):
     print(adt, "100x100 forward", fwd, "grad buckets", gerr)
     assert max(fwd.values()) < (1e-4 if adt == torch.float32 else 2e-2), fwd
     assert max(gerr.values()) < (5e-3 if adt == torch.float32 else 0.5), gerr
+
+
+def test_stage1_multi_step_stays_finite():
+    """Regression: at batch sizes where CTAs walk many tiles (persistent kernels, halo double buffering) no kernel may
+    manufacture a NaN (an unpaired filter tap once multiplied zero weights with uninitialised shared memory)."""
+    B = 96
+    P, S = O.make_vaegan(O.CFG64, seed=5, jitter=False)
+    tr = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
+    x = O.synthetic_images(B, seed=5).cuda()
+    eps, z_p = [t.cuda() for t in O.synthetic_noise(B, 128, seed=5)]
+    for step in range(3):
+        out = tr.forward_backward(x, eps, z_p)
+        torch.cuda.synchronize()
+        for k, v in out.items():
+            assert torch.isfinite(v.float()).all(), (step, k)
+        for k, v in tr.named_grads().items():
+            assert torch.isfinite(v).all(), (step, k)
+        tr.update(B)
+        for k, v in tr.named_parameters().items():
+            assert torch.isfinite(v).all(), (step, k)

@@ -887,15 +887,28 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
         int order[25];
         for (int i = 0; i < 25; ++i) order[i] = i;
         std::sort(order, order + 25, [&](int a, int b) { return woff[a] < woff[b]; });
-        for (int i = 0; i < 25; i += 2, ++s) {
-            const int t0 = order[i], t1 = i + 1 < 25 ? order[i + 1] : -1;
+        // 25 taps = 1 single + 12 pairs. The single is the tap with the SMALLEST window offset: its zero-weight second K half
+        // reads the window one row further, which is still inside the halo. (Pairing it at the far end would read one row
+        // past the initialised halo, and 0-weight x NaN-garbage = NaN.)
+        {
+            const int t0 = order[0];
             p.steps[s].a_off = woff[t0];
-            p.steps[s].a_lbo = t1 >= 0 ? woff[t1] - woff[t0] : 1;  // unpaired last tap: second K half gets zero weights
+            p.steps[s].a_lbo = 1;
             p.steps[s].b_off = s * BN;
             spec.tap[s][0] = (int16_t)(flip ? 24 - t0 : t0);
-            spec.tap[s][1] = (int16_t)(t1 >= 0 ? (flip ? 24 - t1 : t1) : -1);
+            spec.tap[s][1] = -1;
             spec.cb[s][0] = spec.cb[s][1] = 0;
-            if (t1 >= 0 && p.steps[s].a_lbo == 0) return false;
+            ++s;
+        }
+        for (int i = 1; i < 25; i += 2, ++s) {
+            const int t0 = order[i], t1 = order[i + 1];
+            p.steps[s].a_off = woff[t0];
+            p.steps[s].a_lbo = woff[t1] - woff[t0];
+            p.steps[s].b_off = s * BN;
+            spec.tap[s][0] = (int16_t)(flip ? 24 - t0 : t0);
+            spec.tap[s][1] = (int16_t)(flip ? 24 - t1 : t1);
+            spec.cb[s][0] = spec.cb[s][1] = 0;
+            if (p.steps[s].a_lbo == 0) return false;
         }
     }
     return true;

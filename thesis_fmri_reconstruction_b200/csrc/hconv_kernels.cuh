@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    // zero both halo buffers once: rows past the halo are never written by the producers, and although only dropped output
+    // rows (or zero-weight K halves) ever read them, an uninitialised NaN pattern must not meet a zero of the other operand
+    for (int i = threadIdx.x; i < (2 * a_buf) / 16; i += HC_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
