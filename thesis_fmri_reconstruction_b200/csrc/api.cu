@@ -838,28 +838,31 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
     const int nsteps = chunks >= 2 ? 25 * (chunks / 2) : 13;
     if (nsteps > HC_MAX_STEPS) return false;
     p.num_steps = nsteps;
-    int mt_max = std::min(5, 128 / BN);         // 2 buffers x MT x BN <= 256 columns
-    size_t smem_cap = 110 * 1024;
-    int tht = mt_max >= 1 ? std::max(1, std::min(OH, (mt_max * 128) / p.PW)) : 0;
-    for (;; --tht) {
-        if (tht < 1) {
-            if (smem_cap == 227 * 1024) return false;
-            mt_max = std::min(5, 256 / BN);     // one CTA per SM: 2 buffers x MT x BN <= 512 columns
-            smem_cap = 227 * 1024;
-            tht = std::max(1, std::min(OH, (mt_max * 128) / p.PW)) + 1;
-            continue;
+    // Plan search: rows per tile THt (any value, ragged last tile allowed) maximising the useful fraction of the computed
+    // 128-row sub-tiles, first among plans that keep two CTAs per SM (<= 256 TMEM columns, <= 110 KB smem), else one CTA.
+    // Windows of dropped rows may run past the last slab into whatever shared memory follows (weights, barriers): those rows
+    // only produce dropped outputs, so the slab is allocated for the halo alone.
+    bool found = false;
+    for (int pass = 0; pass < 2 && !found; ++pass) {
+        const int mt_max = std::min(5, (pass == 0 ? 128 : 256) / BN);
+        const size_t smem_cap = pass == 0 ? 110 * 1024 : 227 * 1024;
+        double best = 0.0;
+        for (int tht = std::min(OH, (mt_max * 128) / p.PW); tht >= 1; --tht) {
+            HcParams q = p;
+            q.THt = tht;
+            q.tiles_y = cdiv(OH, tht);
+            q.MT = cdiv((long long)tht * q.PW, 128);
+            q.PH = tht + hx;
+            q.slab_rows = (q.PH * q.PW + 7) / 8 * 8;
+            // the overshoot of the last sub-tile's windows must stay inside the CTA's allocation (it lands in the weight slab)
+            const long long overshoot = ((long long)q.MT * 128 + max_off + 1 - q.slab_rows) * 16;
+            if (overshoot > 0 && overshoot > hc_b_bytes(q, BN)) continue;
+            if ((size_t)hc_smem_bytes(q, BN) > smem_cap) continue;
+            const double eff = (double)OH * OW / ((double)q.tiles_y * q.MT * 128);
+            if (eff > best + 1e-9) { best = eff; p = q; found = true; }
         }
-        int use = tht;
-        for (int cand = tht; cand >= std::max(1, tht - 2); --cand)
-            if (OH % cand == 0) { use = cand; break; }
-        p.THt = use;
-        p.tiles_y = cdiv(OH, use);
-        p.MT = cdiv((long long)use * p.PW, 128);
-        p.PH = use + hx;
-        const int need = std::max(p.PH * p.PW, p.MT * 128 + max_off + 1);
-        p.slab_rows = (need + 7) / 8 * 8;
-        if ((size_t)hc_smem_bytes(p, BN) <= smem_cap) break;
     }
+    if (!found) return false;
     // window offset of every filter tap, in 16-byte rows from the start of a halo buffer
     int woff[25];
     for (int kh = 0; kh < 5; ++kh)
@@ -1519,17 +1522,33 @@ static int permute_any(const void* src, int sdt, void* dst, int ddt, int d1, int
         return permute_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, d1, d2, d3, s1, s2, s3, accumulate, st);
     return fail(FMRI_ERR_ARG, "bad dtype");
 }
+template <typename TI, typename TO>
+static int transpose_launch(const void* src, void* dst, int N, int R, int Cc, int accumulate, cudaStream_t st) {
+    dim3 grid(cdiv(Cc, 32), cdiv(R, 32), N);
+    transpose_batched_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), R, Cc,
+                                                           accumulate);
+    LAUNCH_OK();
+    return 0;
+}
+// dst[n][c][r] (+)= src[n][r][c]
+static int transpose_any(const void* src, int sdt, void* dst, int ddt, int N, int R, int Cc, int accumulate, cudaStream_t st) {
+    if (N > 65535) return fail(FMRI_ERR_UNSUPPORTED, "transpose batch %d > 65535", N);
+    if (sdt == FMRI_F32 && ddt == FMRI_F32) return transpose_launch<float, float>(src, dst, N, R, Cc, accumulate, st);
+    if (sdt == FMRI_F32 && ddt == FMRI_BF16) return transpose_launch<float, __nv_bfloat16>(src, dst, N, R, Cc, accumulate, st);
+    if (sdt == FMRI_BF16 && ddt == FMRI_F32) return transpose_launch<__nv_bfloat16, float>(src, dst, N, R, Cc, accumulate, st);
+    if (sdt == FMRI_BF16 && ddt == FMRI_BF16)
+        return transpose_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, N, R, Cc, accumulate, st);
+    return fail(FMRI_ERR_ARG, "bad dtype");
+}
 extern "C" int fmri_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
                                  void* stream) {
-    // dst[n][p][c] = src[n][c][p]
-    return permute_any(src, src_dtype, dst, dst_dtype, N, H * W, C, (long long)C * H * W, 1, (long long)H * W, 0,
-                       S(stream));
+    // dst[n][p][c] = src[n][c][p]: transpose of the [C][HW] matrix of every image
+    return transpose_any(src, src_dtype, dst, dst_dtype, N, C, H * W, 0, S(stream));
 }
 extern "C" int fmri_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
                                  int accumulate, void* stream) {
     // dst[n][c][p] = src[n][p][c]
-    return permute_any(src, src_dtype, dst, dst_dtype, N, C, H * W, (long long)C * H * W, 1, C, accumulate,
-                       S(stream));
+    return transpose_any(src, src_dtype, dst, dst_dtype, N, H * W, C, accumulate, S(stream));
 }
 extern "C" int fmri_cast2d(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows,
                            int cols, void* stream) {

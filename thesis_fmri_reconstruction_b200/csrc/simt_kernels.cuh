@@ -922,6 +922,33 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 // ------------------------------------------------------------------------------------------------
 // layout / dtype packers
 // ------------------------------------------------------------------------------------------------
+// batched 2-D transpose with dtype conversion through a padded shared-memory tile: dst[n][c][r] (+)= src[n][r][c]
+// (the NCHW <-> NHWC flatten / view conversions at the fc boundaries, vae_gan.py:89,127,180). Both sides coalesced.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int R,
+                                                                int Cc, int accumulate) {
+    __shared__ float tile[32][33];
+    const long long base = (long long)blockIdx.z * R * Cc;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < R && c < Cc) ? ld_f(src + base + (long long)r * Cc + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (c < Cc && r < R) {
+            Tout* o = dst + base + (long long)c * R + r;
+            float v = tile[tx][ty + 8 * k];
+            if (accumulate) v += ld_f(o);
+            st_f(o, v);
+        }
+    }
+}
+
 // strided gather copy with dtype conversion: dst[i0,i1,i2,i3] (dense, row-major) = src[i0*s0+i1*s1+i2*s2+i3*s3]
 template <typename Tin, typename Tout>
 __global__ void permute4_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int d0, int d1, int d2, int d3,
