@@ -325,7 +325,12 @@ def run_ours(args):
         top = sorted(((k, round(v["ms"] / psteps, 3)) for k, v in fam.items()), key=lambda t: -t[1])[:16]
         roof = dict(bound="tensor", kernel=("igemm_kernel (conv/convT fprop+dgrad, linear fprop+dgrad)" if dom == "igemm"
                                             else "wgrad_kernel (conv/convT/linear weight gradients)"),
-                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None,
+                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family, averaged over its 39
+                    # launches of one step, from the committed ncu capture of THIS configuration
+                    # (profiles/r1d_ncu_launches_time_dram_B4096.csv: Stage-I, batch 4096 on one GPU); null for any other
+                    traffic=(2.124e9 if (dom == "igemm" and args.workload == "stage1_vaegan" and B == 4096) else None),
+                    traffic_source="profiles/r1d_ncu_launches_time_dram_B4096.csv (ncu, cold cache)",
                     peak_source=pk["src"], kernel_ms_per_step=d["ms"] / psteps, kernel_launches_per_step=d["calls"] / psteps,
                     kernel_share_of_step=d["ms"] / tot_ms if tot_ms else None,
                     whole_step_achieved=ALG_MFLOP[args.workload] * 1e6 * value / 1e12,

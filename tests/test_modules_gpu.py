@@ -208,3 +208,78 @@ def test_eval_mode_and_cpu_refusal():
         assert int(model.state_dict()["encoder.conv.0.bn.num_batches_tracked"]) == 0
         with pytest.raises(FmriError):
             model.encoder(x)  # CPU input: no fallback path
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+@pytest.mark.parametrize("dtype,B", [(torch.float32, 8), (torch.bfloat16, 16)])
+def test_cognitive_stage_script_sequence(stage, dtype, B):
+    """VaeGanCognitive + CognitiveEncoder driven like train_vgan_stage2.py:321-407 / train_vgan_stage3.py:324-411 (teacher
+    distillation in stage 2, frozen nets, gradient clamp to [-1, 1], RMSprop) against the oracle."""
+    mc.use_resolution(64)
+    from models.vae_gan import CognitiveEncoder, Decoder, Discriminator, VaeGan, VaeGanCognitive
+
+    seed = 77
+    P, S = O.make_cognitive(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    eps_t = O.synthetic_noise(B, 128, seed=seed + 1)[0]
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.cognitive_vaegan_step(P, S_ref, fmri, image, eps, eps_t, z_p, stage)
+    hp = O.HP_VGAN
+    with compute(dtype):
+        teacher = VaeGan(device="cuda", z_size=128)
+        cog = CognitiveEncoder(input_size=O.NUM_VOXELS, z_size=128).cuda()
+        if stage == 2:   # decoder / discriminator are the teacher's modules (train_vgan_stage2.py:216-232)
+            model = VaeGanCognitive(device="cuda", encoder=cog, decoder=teacher.decoder,
+                                    discriminator=teacher.discriminator, teacher_net=teacher, stage=2, z_size=128)
+        else:
+            model = VaeGanCognitive(device="cuda", encoder=cog, decoder=Decoder(z_size=128, size=256).cuda(),
+                                    discriminator=Discriminator().cuda(), teacher_net=teacher, stage=3, z_size=128)
+        sd = model.state_dict()
+        for k, v in {**P, **S}.items():
+            sd[k].copy_(v)
+        model.train()
+        draws = [eps.cuda(), eps_t.cuda()]
+        model.reparameterize = lambda mu, lv: ag.reparameterize(mu, lv, draws.pop(0))
+        opt = {b: torch.optim.RMSprop(getattr(model, b).parameters(), lr=hp["lr"], alpha=0.9, eps=1e-8)
+               for b in ("encoder", "decoder", "discriminator")}
+        frozen = model.decoder if stage == 2 else model.encoder
+        for p_ in frozen.parameters():
+            p_.requires_grad = False
+        with patched_randn(z_p):
+            x_gt, x_tilde, disc_class, disc_layer, mus, lv = model({"fmri": fmri, "image": image})
+        dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]
+        dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
+        nle, kld, mse, bo, bp, bs = VaeGanCognitive.loss(x_gt, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)
+        loss_encoder = torch.sum(kld) + torch.sum(mse)
+        loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+        loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator
+        grads = {}
+        first, first_loss = ("encoder", loss_encoder) if stage == 2 else ("decoder", loss_decoder)
+        model.zero_grad()
+        first_loss.backward(retain_graph=True)
+        grads.update({first + "." + k: p_.grad.clone() for k, p_ in getattr(model, first).named_parameters()})
+        [p_.grad.data.clamp_(-1, 1) for p_ in getattr(model, first).parameters()]
+        opt[first].step()
+        model.zero_grad() if stage == 2 else model.discriminator.zero_grad()
+        loss_discriminator.backward()
+        grads.update({"discriminator." + k: p_.grad.clone() for k, p_ in model.discriminator.named_parameters()})
+        [p_.grad.data.clamp_(-1, 1) for p_ in model.discriminator.parameters()]
+        opt["discriminator"].step()
+        torch.cuda.synchronize()
+    ftol = 1e-4 if dtype == torch.float32 else 2e-2
+    fwd = dict(x_tilde=rel(x_tilde, ref["x_tilde"]), gt_x=rel(x_gt, ref["gt_x"]), disc_layer=rel(disc_layer, ref["disc_layer"]),
+               disc_class=rel(disc_class, ref["disc_class"]), mu=rel(mus, ref["mu"]), kl=rel(kld, ref["kl"]),
+               mse=rel(mse, ref["mse"]), loss_decoder=rel(loss_decoder, ref["loss_decoder"]))
+    print(stage, dtype, "forward", fwd)
+    assert max(fwd.values()) < ftol, fwd
+    for pre in (first + ".", "discriminator."):
+        e = bucket_err(grads, {k: v for k, v in ref["grads"].items()}, pre)
+        print(stage, dtype, pre, "grad rel-L2 vs fp32 oracle", e)
+        assert e < (5e-3 if dtype == torch.float32 else 0.5), (pre, e)
+    sd = model.state_dict()
+    for k, v in S_ref.items():
+        if v.dtype.is_floating_point:
+            assert rel(sd[k], v) < ftol, k
+        else:
+            assert int(sd[k]) == int(v), k   # decoder BN: 3 updates in stage 2 (x_tilde, teacher reconstruction, x_p)
