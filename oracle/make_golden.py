@@ -275,6 +275,84 @@ def golden_cognitive(ref, B, seed, stage):
     return fx
 
 
+def golden_cognitive_wae(ref, B, seed, stage):
+    """train/train_wae_stage2.py:195-203, 274-328 (stage 2) / train/train_wae_stage3.py:295-347 (stage 3)."""
+    torch.manual_seed(0)
+    P, S = O.make_cognitive_wae(O.CFG64, seed=seed, dtype=torch.float64)
+    fmri = O.synthetic_fmri(B, seed=seed).double()
+    image = O.synthetic_images(B, seed=seed).double()
+    trained_model = ref.WaeGan(device="cpu", z_size=128).double()
+    cog = ref.CognitiveEncoder(input_size=O.NUM_VOXELS, z_size=128).double()
+    model = ref.WaeGanCognitive(device="cpu", encoder=cog, decoder=trained_model.decoder, z_size=128).double()
+    msd, tsd = model.state_dict(), trained_model.state_dict()
+    for k, v in {**P, **S}.items():
+        if k.startswith("teacher_net."):
+            tsd[k[len("teacher_net."):]].copy_(v)
+        else:
+            msd[k].copy_(v)
+    hp = O.HP_WAE23
+    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=0.001, betas=(0.5, 0.999))
+    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=0.001, betas=(0.5, 0.999))
+    opt_c = torch.optim.Adam(model.discriminator.parameters(), lr=0.0005, betas=(0.5, 0.999))
+
+    def freeze(m, on):
+        for p_ in m.parameters():
+            p_.requires_grad = not on
+
+    model.train()
+    if stage == 2:
+        freeze(model.decoder, True)
+        model.encoder.zero_grad(); model.discriminator.zero_grad()
+        z, _ = trained_model.encoder(image)                                           # wae2 :284
+        x_gt = trained_model.decoder(z)                                               # :285 (unused)
+        freeze(model.encoder, True); freeze(model.discriminator, False)
+    else:
+        freeze(model.encoder, True)
+        model.decoder.zero_grad(); model.discriminator.zero_grad()
+        freeze(model.decoder, True); freeze(model.discriminator, False)
+    z_fake, _ = model.encoder(fmri)
+    z_real, _ = trained_model.encoder(image)
+    d_real = model.discriminator(z_real)
+    d_fake = model.discriminator(z_fake)
+    loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))
+    loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))
+    loss_fake.backward(retain_graph=True)
+    loss_real.backward(retain_graph=True)
+    grads = {"discriminator." + k: p_.grad.clone() for k, p_ in model.discriminator.named_parameters()}
+    opt_c.step()
+    freeze(model.discriminator, True)
+    if stage == 2:
+        freeze(model.encoder, False)
+    else:
+        freeze(model.decoder, False)
+    z2, _ = model.encoder(fmri)
+    x_recon = model.decoder(z2)
+    d2 = model.discriminator(z2)
+    loss_rec = torch.nn.MSELoss()(x_recon, image)
+    loss_pen = -10 * torch.mean(torch.log(d2 + 1e-3))
+    loss_rec.backward(retain_graph=True)
+    if stage == 2:
+        loss_pen.backward()
+        grads.update({"encoder." + k: p_.grad.clone() for k, p_ in model.encoder.named_parameters() if p_.grad is not None})
+        opt_e.step()
+    else:
+        grads.update({"decoder." + k: p_.grad.clone() for k, p_ in model.decoder.named_parameters()})
+        opt_d.step()
+    newP = {k: v.detach() for k, v in model.state_dict().items() if k in P}
+    delta = {k: newP[k] - P[k] for k in newP}
+    bufs = {k: v for k, v in model.state_dict().items() if k in S}
+    bufs.update({"teacher_net." + k: v for k, v in trained_model.state_dict().items() if "teacher_net." + k in S})
+    fx = dict(B=np.array(B), seed=np.array(seed), stage=np.array(stage), z_fake=z_fake.detach().numpy(),
+              z_real=z_real.detach().numpy(), d_real=d_real.detach().numpy(), d_fake=d_fake.detach().numpy(),
+              d_real_g=d2.detach().numpy(), loss_discriminator_fake=loss_fake.detach().numpy(),
+              loss_discriminator_real=loss_real.detach().numpy(), loss_reconstruction=loss_rec.detach().numpy(),
+              loss_penalty=loss_pen.detach().numpy(), x_recon=summarize(x_recon))
+    fx.update(summarize_dict(grads, "grad:"))
+    fx.update(summarize_dict(delta, "delta:"))
+    fx.update(summarize_dict(bufs, "buf:"))
+    return fx
+
+
 def main():
     ref = import_reference()
     out = os.path.join(ROOT, "tests", "golden")
@@ -287,6 +365,9 @@ def main():
     for stage in (2, 3):
         np.savez_compressed(os.path.join(out, f"stage{stage}_cognitive_B4_s4711.npz"), **golden_cognitive(ref, 4, 4711, stage))
         print("wrote cognitive golden for stage", stage)
+        np.savez_compressed(os.path.join(out, f"stage{stage}_cognitive_wae_B4_s3131.npz"),
+                            **golden_cognitive_wae(ref, 4, 3131, stage))
+        print("wrote cognitive WAE golden for stage", stage)
 
 
 if __name__ == "__main__":

@@ -480,3 +480,74 @@ def cognitive_vaegan_step(P, S, fmri, image, eps, eps_t, z_p, stage, cfg=CFG64, 
                 newP[n], newsq[n] = rmsprop_update(P[n], grads[n].clamp(-1, 1), sq[n], hp["lr"], hp["alpha"], hp["eps"])
         out["params"], out["square_avg"] = newP, newsq
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- WAE Stages II / III
+def make_cognitive_wae(cfg=CFG64, z=None, seed=12345, dtype=torch.float32, jitter=True):
+    """WaeGanCognitive (models/vae_gan.py:532-546) + the Stage-I WaeGan teacher's visual encoder
+    (train/train_wae_stage2.py:195-203). Keys: encoder.* (cognitive), decoder.*, discriminator.main.*, teacher_net.encoder.*."""
+    z = z or cfg["latent_dim"]
+    P, S = OrderedDict(), OrderedDict()
+    for i, (pre, spec, wd) in enumerate((("encoder.", cognitive_encoder_spec(z), False),
+                                         ("decoder.", decoder_spec(cfg, z), False),
+                                         ("discriminator.", wae_discriminator_spec(z), True),
+                                         ("teacher_net.encoder.", encoder_spec(cfg, z), False))):
+        p, s = make_net(pre, spec, seed + 20 + i, dtype, jitter, wae_disc=wd)
+        P.update(p)
+        S.update(s)
+    return P, S
+
+
+HP_WAE23 = dict(lr=1e-3, lr_dis=5e-4, beta1=0.5, beta2=0.999, eps=1e-8)  # train_wae_stage2.py:237-239 (hard-coded)
+
+
+def cognitive_wae_step(P, S, fmri, image, stage, cfg=CFG64, hp=HP_WAE23, opt=None, step=1):
+    """One iteration of train/train_wae_stage2.py:274-328 (stage=2) or train/train_wae_stage3.py:295-347 (stage=3).
+
+    stage 2: an unused teacher reconstruction forward (:284-285, BN side effects only), D-phase on z_fake = cognitive
+    encoder(fmri) vs z_real = teacher.encoder(image), Adam(5e-4) on the latent discriminator; G-phase trains the cognitive
+    encoder with nn.MSELoss(x_recon, image) + (-10 * mean log(d + 1e-3)) (:320-321), Adam(1e-3); decoder frozen.
+    stage 3: same D-phase; G-phase trains the DECODER on nn.MSELoss only (:338-347), cognitive encoder frozen."""
+    names = {b: bucket(P, b + ".") for b in ("encoder", "decoder", "discriminator")}
+    if opt is None:
+        opt = dict(m=OrderedDict((k, torch.zeros_like(v)) for k, v in P.items()),
+                   v=OrderedDict((k, torch.zeros_like(v)) for k, v in P.items()))
+    W = _leaf(P)
+    if stage == 2:
+        zt, _ = encoder(W, S, image, cfg, pre="teacher_net.encoder.")   # x_gt = decoder(teacher.encoder(image)): unused
+        decoder(W, S, zt, cfg)
+    z_fake, _ = cognitive_encoder(W, S, fmri, pre="encoder.")
+    z_real, _ = encoder(W, S, image, cfg, pre="teacher_net.encoder.")
+    d_real = wae_discriminator(W, z_real.detach())
+    d_fake = wae_discriminator(W, z_fake.detach())
+    loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))
+    loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))
+    g_dis = torch.autograd.grad(loss_fake + loss_real, [W[n] for n in names["discriminator"]])
+    grads = OrderedDict(zip(names["discriminator"], g_dis))
+    newP, newm, newv = OrderedDict(P), OrderedDict(opt["m"]), OrderedDict(opt["v"])
+    for n in names["discriminator"]:
+        newP[n], newm[n], newv[n] = adam_update(P[n], grads[n], opt["m"][n], opt["v"][n], step, hp["lr_dis"], hp["beta1"],
+                                                hp["beta2"], hp["eps"])
+    W2 = _leaf(newP)
+    z2, _ = cognitive_encoder(W2, S, fmri, pre="encoder.")
+    x_recon = decoder(W2, S, z2, cfg)
+    d2 = wae_discriminator(W2, z2)
+    loss_rec = F.mse_loss(x_recon, image)
+    loss_pen = -10 * torch.mean(torch.log(d2 + 1e-3))
+    if stage == 2:
+        g = torch.autograd.grad(loss_rec + loss_pen, [W2[n] for n in names["encoder"]], allow_unused=True)
+        trained = "encoder"
+    else:
+        g = torch.autograd.grad(loss_rec, [W2[n] for n in names["decoder"]])
+        trained = "decoder"
+    grads.update((n, gg) for n, gg in zip(names[trained], g) if gg is not None)
+    for n in names[trained]:
+        if n in grads:
+            newP[n], newm[n], newv[n] = adam_update(P[n], grads[n], opt["m"][n], opt["v"][n], step, hp["lr"], hp["beta1"],
+                                                    hp["beta2"], hp["eps"])
+    out = dict(z_fake=z_fake, z_real=z_real, d_real=d_real, d_fake=d_fake, x_recon=x_recon, d_real_g=d2,
+               loss_discriminator_fake=loss_fake, loss_discriminator_real=loss_real, loss_reconstruction=loss_rec,
+               loss_penalty=loss_pen, grads=grads, trained=trained)
+    out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+    out["params"], out["adam"] = newP, dict(m=newm, v=newv)
+    return out

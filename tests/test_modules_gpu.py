@@ -283,3 +283,87 @@ def test_cognitive_stage_script_sequence(stage, dtype, B):
             assert rel(sd[k], v) < ftol, k
         else:
             assert int(sd[k]) == int(v), k   # decoder BN: 3 updates in stage 2 (x_tilde, teacher reconstruction, x_p)
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+@pytest.mark.parametrize("dtype,B", [(torch.float32, 8), (torch.bfloat16, 16)])
+def test_cognitive_wae_script_sequence(stage, dtype, B):
+    """WaeGanCognitive + CognitiveEncoder + a WaeGan teacher driven like train_wae_stage2.py:274-328 /
+    train_wae_stage3.py:295-347 (nn.MSELoss on the module output, mean penalty, Adam) against the oracle."""
+    mc.use_resolution(64)
+    from models.vae_gan import CognitiveEncoder, WaeGan, WaeGanCognitive
+
+    seed = 91
+    P, S = O.make_cognitive_wae(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.cognitive_wae_step(P, S_ref, fmri, image, stage)
+
+    def freeze(m, on):
+        for p_ in m.parameters():
+            p_.requires_grad = not on
+
+    with compute(dtype):
+        trained_model = WaeGan(device="cuda", z_size=128)
+        cog = CognitiveEncoder(input_size=O.NUM_VOXELS, z_size=128).cuda()
+        model = WaeGanCognitive(device="cuda", encoder=cog, decoder=trained_model.decoder, z_size=128)
+        msd, tsd = model.state_dict(), trained_model.state_dict()
+        for k, v in {**P, **S}.items():
+            (tsd[k[len("teacher_net."):]] if k.startswith("teacher_net.") else msd[k]).copy_(v)
+        opt_e = torch.optim.Adam(model.encoder.parameters(), lr=0.001, betas=(0.5, 0.999))
+        opt_d = torch.optim.Adam(model.decoder.parameters(), lr=0.001, betas=(0.5, 0.999))
+        opt_c = torch.optim.Adam(model.discriminator.parameters(), lr=0.0005, betas=(0.5, 0.999))
+        x_fmri, x_image = fmri.cuda(), image.cuda()
+        model.train()
+        if stage == 2:
+            freeze(model.decoder, True)
+            model.encoder.zero_grad(); model.discriminator.zero_grad()
+            z, _ = trained_model.encoder(x_image)
+            trained_model.decoder(z)                      # the script's unused x_gt forward (BN side effects)
+            freeze(model.encoder, True); freeze(model.discriminator, False)
+        else:
+            freeze(model.encoder, True)
+            model.decoder.zero_grad(); model.discriminator.zero_grad()
+            freeze(model.decoder, True); freeze(model.discriminator, False)
+        z_fake, _ = model.encoder(x_fmri)
+        z_real, _ = trained_model.encoder(x_image)
+        d_real = model.discriminator(z_real)
+        d_fake = model.discriminator(z_fake)
+        loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))
+        loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))
+        loss_fake.backward(retain_graph=True)
+        loss_real.backward(retain_graph=True)
+        grads = {"discriminator." + k: p_.grad.clone() for k, p_ in model.discriminator.named_parameters()}
+        opt_c.step()
+        freeze(model.discriminator, True)
+        freeze(model.encoder if stage == 2 else model.decoder, False)
+        z2, _ = model.encoder(x_fmri)
+        x_recon = model.decoder(z2)
+        d2 = model.discriminator(z2)
+        loss_rec = torch.nn.MSELoss()(x_recon, x_image)
+        loss_pen = -10 * torch.mean(torch.log(d2 + 1e-3))
+        loss_rec.backward(retain_graph=True)
+        if stage == 2:
+            loss_pen.backward()
+            grads.update({"encoder." + k: p_.grad.clone() for k, p_ in model.encoder.named_parameters() if p_.grad is not None})
+            opt_e.step()
+        else:
+            grads.update({"decoder." + k: p_.grad.clone() for k, p_ in model.decoder.named_parameters()})
+            opt_d.step()
+        torch.cuda.synchronize()
+    ftol = 1e-4 if dtype == torch.float32 else 2e-2
+    fwd = dict(z_fake=rel(z_fake, ref["z_fake"]), z_real=rel(z_real, ref["z_real"]), d_real=rel(d_real, ref["d_real"]),
+               x_recon=rel(x_recon, ref["x_recon"]), loss_rec=rel(loss_rec, ref["loss_reconstruction"]),
+               loss_pen=rel(loss_pen, ref["loss_penalty"]))
+    print(stage, dtype, "forward", fwd)
+    assert max(fwd.values()) < ftol, fwd
+    for pre in (ref["trained"] + ".", "discriminator."):
+        e = bucket_err(grads, ref["grads"], pre)
+        print(stage, dtype, pre, "grad rel-L2 vs fp32 oracle", e)
+        assert e < (5e-3 if dtype == torch.float32 else 0.5), (pre, e)
+    sd = {**{("teacher_net." + k): v for k, v in trained_model.state_dict().items()}, **model.state_dict()}
+    for k, v in S_ref.items():
+        if v.dtype.is_floating_point:
+            assert rel(sd[k], v) < ftol, k
+        else:
+            assert int(sd[k]) == int(v), k

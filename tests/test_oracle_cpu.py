@@ -123,6 +123,30 @@ def test_cognitive_stages_fp64_match_reference(stage):
     assert n == len(out["grads"]) > 0
 
 
+@pytest.mark.parametrize("stage", [2, 3])
+def test_cognitive_wae_stages_fp64_match_reference(stage):
+    g = np.load(os.path.join(GOLD, f"stage{stage}_cognitive_wae_B4_s3131.npz"))
+    B, seed = int(g["B"]), int(g["seed"])
+    P, S = O.make_cognitive_wae(O.CFG64, seed=seed, dtype=torch.float64)
+    fmri = O.synthetic_fmri(B, seed=seed).double()
+    image = O.synthetic_images(B, seed=seed).double()
+    out = O.cognitive_wae_step(P, S, fmri, image, stage)
+    for k in ("z_fake", "z_real", "d_real", "d_fake", "d_real_g", "loss_discriminator_fake", "loss_discriminator_real",
+              "loss_reconstruction", "loss_penalty"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-9, k
+    assert summary_error(summarize(out["x_recon"]), g["x_recon"]) < 1e-9
+    n = 0
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert summary_error(summarize(out["grads"][k[5:]]), g[k]) < 1e-8, k
+            n += 1
+        elif k.startswith("delta:"):
+            assert summary_error(summarize(out["params"][k[6:]] - P[k[6:]]), g[k]) < 1e-6, k
+        elif k.startswith("buf:"):
+            assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
+    assert n == len(out["grads"]) > 0
+
+
 def test_gate_table():
     # train/train_vgan_stage1.py:396-404
     assert O.gate(0.5, 0.7) == (True, True)
