@@ -1417,7 +1417,14 @@ static int bn_bwd_reduce_t(const void* x, const void* dy, long long rows, int C,
     const int rpb = rows_per_block_for(rows);
     dim3 grid(cdiv(rows, rpb), std::min(8, cdiv(C, 256)));
     CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-    if (C % 8 == 0 && ((C / 8) >= 256 ? (C / 8) % 256 == 0 : 256 % (C / 8) == 0)) {
+    if (C % 2 == 0 && ((C / 2) >= 256 ? (C / 2) % 256 == 0 : 256 % (C / 2) == 0)) {
+        const int ry = std::max(1, 256 / (C / 2));
+        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * 8 - 1) / (148 * 8));
+        dim3 gcp(cdiv(rows, per), std::max(1, std::min(8, (C / 2) / 256)));
+        bn_bwd_cp_kernel<1, Tx, Tg><<<gcp, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), nullptr,
+                                                       rows, C, mean, invstd, gamma, beta, relu, 1, nullptr, nullptr, ws,
+                                                       ws + C, (int)per);
+    } else if (C % 8 == 0 && ((C / 8) >= 256 ? (C / 8) % 256 == 0 : 256 % (C / 8) == 0)) {
         dim3 g8(cdiv(rows, rpb), std::max(1, std::min(8, (C / 8) / 256)));
         bn_reduce8_kernel<1, Tx, Tg><<<g8, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), rows,
                                                        C, mean, invstd, gamma, beta, relu, ws, ws + C, rpb);
@@ -1452,7 +1459,15 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
     float* mean_gx = mean_g + C;
     bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, (double)rows, C, mean_g, mean_gx, dgamma, dbeta, accumulate);
     LAUNCH_OK();
-    if (dx) {
+    if (dx && C % 2 == 0 && ((C / 2) >= 256 ? (C / 2) % 256 == 0 : 256 % (C / 2) == 0)) {
+        const int ry = std::max(1, 256 / (C / 2));
+        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * 8 - 1) / (148 * 8));
+        dim3 gcp(cdiv(rows, per), std::max(1, std::min(8, (C / 2) / 256)));
+        bn_bwd_cp_kernel<2, Tx, Tg><<<gcp, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy),
+                                                       reinterpret_cast<Tg*>(dx), rows, C, mean, invstd, gamma, beta, relu,
+                                                       train, mean_g, mean_gx, nullptr, nullptr, (int)per);
+        LAUNCH_OK();
+    } else if (dx) {
         if (C % 8) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward needs C %% 8 == 0");
         bn_bwd_apply_kernel<Tx, Tg><<<grid1d((rows * C + 7) / 8, 256, 148 * 8), 256, 0, st>>>(
             reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), reinterpret_cast<Tg*>(dx), rows * C, C,
