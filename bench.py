@@ -158,7 +158,10 @@ def run_reference(args):
     sample = f"{steps} timed + {warm} warm-up steps of batch {B} (bounded sample of the workload), fp32, torch CPU"
     line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=f"{args.workload} 64x64 z=128, oracle port of the reference step on host CPU", global_batch=B),
+                config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json configs[4]: global batch {args.batch})",
+                            global_batch=args.batch, cpu_sample_batch=B,
+                            note="reference arm: oracle port of the reference step (two discriminator passes, three autograd "
+                                 "sweeps) on the host cores; each timed step is a batch-%d sample of the workload" % B),
                 cpu_baseline=dict(value=v, unit="samples/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
