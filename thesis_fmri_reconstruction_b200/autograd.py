@@ -84,14 +84,6 @@ def _params_of(mod):
     return names, params
 
 
-def _grad_list(names, G, needs):
-    return [G[n] if (need and n in G) else None for n, need in zip(names, needs)]
-
-
-def _alloc_grads(names, P, needs):
-    return {n: torch.empty_like(P[n]) for n, need in zip(names, needs) if need}
-
-
 # ====================================================================================================== encoders
 class _EncoderFn(torch.autograd.Function):
     """Encoder / CognitiveEncoder forward: input -> (mu, logvar)."""

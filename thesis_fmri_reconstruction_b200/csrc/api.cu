@@ -141,7 +141,7 @@ static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st)
     const long long tiles = m_groups * p.n_tiles * classes;
     const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), (227 * 1024) / L::TOTAL));
     const int grid = (int)std::min<long long>(tiles, 148LL * per_sm);
-    igemm_persistent_kernel<BN, KCH, STAGES, MT><<<grid, 192, L::TOTAL, st>>>(p, classes);
+    igemm_persistent_kernel<BN, KCH, STAGES, MT><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
     LAUNCH_OK();
     return 0;
 }
@@ -1231,6 +1231,7 @@ extern "C" int fmri_edge_out_wgrad(const fmri_edge_desc* d, const void* x, const
 }
 
 // ================================================================================================ linear
+static int transpose_any(const void* src, int sdt, void* dst, int ddt, int N, int R, int Cc, int accumulate, cudaStream_t st);
 extern "C" int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* w, void* wp, int ldw, void* wpt,
                                         int ldwt, void* stream) {
     if (!d || d->M < 0 || d->N <= 0 || d->K <= 0) return fail(FMRI_ERR_ARG, "bad linear descriptor");
@@ -1242,9 +1243,14 @@ extern "C" int fmri_linear_pack_weights(const fmri_linear_desc* d, const float* 
     if (wpt) {  // [K][N]
         if (ldwt < d->N) return fail(FMRI_ERR_ARG, "ldwt < N");
         // dst[k][n] (pitch ldwt) = w[n][k]
-        scatter4_kernel<float, __nv_bfloat16><<<grid1d((long long)d->N * d->K, 256), 256, 0, S(stream)>>>(
-            w, reinterpret_cast<__nv_bfloat16*>(wpt), 1, 1, d->N, d->K, 0, 0, 1, ldwt, 0);
-        LAUNCH_OK();
+        if (ldwt == d->N) {  // dense: tiled transpose, both sides coalesced
+            int rc = transpose_any(w, FMRI_F32, wpt, FMRI_BF16, 1, d->N, d->K, 0, S(stream));
+            if (rc) return rc;
+        } else {
+            scatter4_kernel<float, __nv_bfloat16><<<grid1d((long long)d->N * d->K, 256), 256, 0, S(stream)>>>(
+                w, reinterpret_cast<__nv_bfloat16*>(wpt), 1, 1, d->N, d->K, 0, 0, 1, ldwt, 0);
+            LAUNCH_OK();
+        }
     }
     return 0;
 }

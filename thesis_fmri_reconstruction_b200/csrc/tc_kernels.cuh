@@ -383,8 +383,11 @@ __device__ __forceinline__ IgTile ig_decode_tile(const IgParams& p, int t, int m
     return r;
 }
 
+constexpr int IGP_EPI_WARPS = 8;
+constexpr int IGP_THREADS = 64 + 32 * IGP_EPI_WARPS;
+
 template <int BN, int KCH, int STAGES, int MT>
-__global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
+__global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
     using L = IgSmem<BN, KCH, STAGES, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);
+            mbar_init(&tempty[b], IGP_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -508,7 +511,10 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
         __syncwarp();
     } else {
         // ================= epilogue =================
+        // 8 epilogue warps: two per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31); the two warps of a
+        // quarter split the tile's 32-column chunks between them (even / odd), halving the epilogue's critical path
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int xi = row % p.bw;
         const int yi = (row / p.bw) % p.bh;
@@ -534,6 +540,7 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
                                            (long long)nt * BN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if ((((m * (BN / 32)) + (c0 >> 5)) & 1) != half) continue;
                     bool valid = valid_tile;
                     long long off = off_tile;
                     int stat_col = c0;
@@ -640,16 +647,16 @@ __global__ void __launch_bounds__(192) igemm_persistent_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
             if (do_stats) {  // flush this tile's per-channel sums (the next tile may belong to another channel block)
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 32 * IGP_EPI_WARPS);
                 const int ncol = p.merge ? 32 : BN;
                 const int cbase = p.merge ? 0 : nt * BN;
-                for (int i = etid; i < ncol; i += 128) {
+                for (int i = etid; i < ncol; i += 32 * IGP_EPI_WARPS) {
                     atomicAdd(p.stat_sum + cbase + i, (double)s_stat[i]);
                     atomicAdd(p.stat_sq + cbase + i, (double)s_stat[BN + i]);
                     s_stat[i] = 0.f;
                     s_stat[BN + i] = 0.f;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 32 * IGP_EPI_WARPS);
             }
             ++lt;
         }

@@ -111,7 +111,6 @@ class VaeGanStage1(_TrainerBase):
         self.lr = {pre: float(self.hp["lr"]) for pre in self.buckets}
         self._setup_dist(dist_group)
         self.refresh()
-        self.launches = 0
 
     def refresh(self):
         """Re-derive the bf16 operand packs from the fp32 master weights (after every optimizer step)."""

@@ -167,7 +167,9 @@ class ConvBlock:
 # Fusing the BN-backward reduction into the data-gradient epilogue (fmri_bn_fuse) removes 2 of BN-backward's 5 tensor passes
 # (-8.5 ms/step at B = 4096) but the heavier epilogue stops hiding behind the next tile's main loop in the persistent kernel
 # (+15.6 ms/step on the data-gradient launches), so it is OFF by default until the epilogue is spread over more warps.
-FUSE_BN_BWD = False
+import os as _os
+
+FUSE_BN_BWD = _os.environ.get("FMRI_FUSE_BN", "0") == "1"
 
 
 def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_ready=False):
