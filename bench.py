@@ -25,7 +25,15 @@ sys.path.insert(0, ROOT)
 # algorithmic MFLOP per sample per optimisation step (2 x MACs of the necessary GEMMs only)
 ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8, "stage2_cognitive": 13866.1,
              # Stage III proper (train_vgan_stage3.py): fwd C+2D+3S = 4359.3, bwd [3S+3(S-c0)+2c0] + [2c3+3(c2+c1)+c0] + 2(2D-fc) = 11001.2
-             "stage3_cognitive": 15360.4}
+             "stage3_cognitive": 15360.4,
+             # configs[3] composite: Stage III + teacher-encoder forward + latent-discriminator D-phase
+             "stage3_dual": 15624.3,
+             # WAE-MMD extension: E + D forward, 2D + (2E - c0) backward; the pairwise kernel adds 9 * B * Z flop / sample
+             "stage1_wae_mmd": 3339.2}
+CONFIG_OF = {"stage1_vaegan": "configs[4] (configs[0] at --batch 64)", "stage1_waegan": "configs[1] (reference WAE/GAN step; "
+             "the reference has no MMD)", "stage2_cognitive": "configs[2]", "stage3_cognitive": "train_vgan_stage3.py proper",
+             "stage3_dual": "configs[3] (composite, SURVEY.md 8d C4)",
+             "stage1_wae_mmd": "configs[1] with the MMD latent loss (extension: no reference code, parity unpinned)"}
 METRIC = "stage1_vaegan_train_samples_per_sec_64x64"  # BASELINE.json metric; other workloads rename it below
 
 
@@ -35,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive"])
+    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive", "stage3_dual", "stage1_wae_mmd"])
     ap.add_argument("--batch", type=int, default=4096, help="GLOBAL batch (BASELINE.json configs[4]: 4096, strong scaling)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -127,6 +135,27 @@ def cpu_reference_steps(workload, B, steps, warmup, threads=None):
             nonlocal P
             out = O.stage1_waegan_step(P, S, x, z_fake, opt=st["opt"], step=st["t"])
             P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
+    elif workload == "stage1_wae_mmd":
+        P, S = O.make_waegan(O.CFG64, seed=12345, jitter=False)
+        x = O.synthetic_images(B)
+        z_fake = O.synthetic_noise(B, 128)[0] * 0.5
+        st = dict(opt=None, t=1)
+
+        def one():
+            nonlocal P
+            out = O.stage1_wae_mmd_step(P, S, x, z_fake, opt=st["opt"], step=st["t"])
+            P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
+    elif workload == "stage3_dual":
+        P, S = O.make_dual_stage3(O.CFG64, seed=12345, jitter=False)
+        fmri, x = O.synthetic_fmri(B), O.synthetic_images(B)
+        eps, z_p = O.synthetic_noise(B, 128)
+        st = dict(sq=None, opt=None, t=1)
+
+        def one():
+            nonlocal P
+            out = O.dual_stage3_step(P, S, fmri, x, eps, z_p, sq=st["sq"], opt=st["opt"], step=st["t"],
+                                     force_gate=(True, True))
+            P, st["sq"], st["opt"], st["t"] = out["params"], out["square_avg"], out["adam"], st["t"] + 1
     else:
         stage = 2 if workload == "stage2_cognitive" else 3
         P, S = O.make_cognitive(O.CFG64, seed=12345, jitter=False)
@@ -158,7 +187,7 @@ def run_reference(args):
     sample = f"{steps} timed + {warm} warm-up steps of batch {B} (bounded sample of the workload), fp32, torch CPU"
     line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json configs[4]: global batch {args.batch})",
+                config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})",
                             global_batch=args.batch, cpu_sample_batch=B,
                             note="reference arm: oracle port of the reference step (two discriminator passes, three autograd "
                                  "sweeps) on the host cores; each timed step is a batch-%d sample of the workload" % B),
@@ -194,15 +223,20 @@ def run_ours(args):
         tr = engine.VaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group, gate=True)
         n1_host = torch.randn(B, z, generator=gen).pin_memory()
         n2_host = torch.randn(B, z, generator=gen).pin_memory()
-    elif args.workload == "stage1_waegan":
+    elif args.workload in ("stage1_waegan", "stage1_wae_mmd"):
         P, S = init.init_waegan(cfg, z, seed=12345)
-        tr = engine.WaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group)
+        tr = engine.WaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group,
+                                 penalty="mmd" if args.workload == "stage1_wae_mmd" else "gan")
         n1_host = (torch.randn(B, z, generator=gen) * 0.5).pin_memory()
         n2_host = None
     else:
-        stage = 2 if args.workload == "stage2_cognitive" else 3
-        P, S = init.init_cognitive(cfg, z, seed=12345, with_teacher=stage == 2)
-        tr = engine.VaeGanCognitiveStage(P, S, cfg, stage, z, torch.bfloat16, dist_group=group)
+        if args.workload == "stage3_dual":
+            P, S = init.init_dual_stage3(cfg, z, seed=12345)
+            tr = engine.DualCognitiveStage3(P, S, cfg, z, torch.bfloat16, dist_group=group)
+        else:
+            stage = 2 if args.workload == "stage2_cognitive" else 3
+            P, S = init.init_cognitive(cfg, z, seed=12345, with_teacher=stage == 2)
+            tr = engine.VaeGanCognitiveStage(P, S, cfg, stage, z, torch.bfloat16, dist_group=group)
         n1_host = torch.randn(B, z, generator=gen).pin_memory()
         n2_host = torch.randn(B, z, generator=gen).pin_memory()
         fmri_host = torch.randn(B, hp.NUM_VOXELS, generator=gen).pin_memory()
@@ -210,11 +244,14 @@ def run_ours(args):
     x = x_host.cuda(non_blocking=True)
     n1 = n1_host.cuda(non_blocking=True)
     n2 = n2_host.cuda(non_blocking=True) if n2_host is not None else None
-    cog = args.workload in ("stage2_cognitive", "stage3_cognitive")
+    cog = args.workload in ("stage2_cognitive", "stage3_cognitive", "stage3_dual")
+    dual = args.workload == "stage3_dual"
     fmri = fmri_host.cuda(non_blocking=True) if cog else None
 
     def run_step(xb, a, b2, fb=None):
-        if cog:
+        if dual:
+            tr.step(fb if fb is not None else fmri, xb, a, b2)
+        elif cog:
             tr.step(fb if fb is not None else fmri, xb, a, eps_t, b2)
         elif b2 is not None:
             tr.step(xb, a, b2)
@@ -350,7 +387,7 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
                     data="synthetic", impl="ours",
-                    config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json configs[4]: global batch {args.batch})",
+                    config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})",
                                 global_batch=args.batch, per_gpu_batch=B, parallelism=f"dp{world}",
                                 l2="inputs larger than L2: per-step activation working set ~%.1f GB per GPU >> 126 MB" % act_gb,
                                 optimizer="3 x RMSprop (fused multi-tensor), equilibrium gate on device"),

@@ -181,6 +181,17 @@ int fmri_head_sigmoid_bwd(const void* x, int dtype, const float* w, const float*
 int fmri_bce_fwd(const float* p, float* out, int n, int positive, float scale, void* stream);
 int fmri_bce_bwd(const float* p, const float* g, float* dp, int n, int positive, float scale, int accumulate,
                  void* stream);
+/* WAE-MMD latent penalty, inverse-multiquadratic kernel summed over the scales {.1,.2,.5,1,2,5,10} * 2 Z sigma2
+ * (Tolstikhin et al.; the estimator of the repositories the reference's README.md:287,293 cites). EXTENSION: the
+ * reference ships no MMD code, so this pair is pinned only against oracle/mmd.py ("parity unpinned").
+ * zq = encoded latents [B, Z] (row pitch ldq floats, e.g. the mu half of a [B, 2Z] head output), zp = prior samples.
+ *   fwd: mmd[0] = lambda * { [sum_{i!=j} k(q_i,q_j) + sum_{i!=j} k(p_i,p_j)] / (B(B-1)) - 2/B^2 sum_{i,j} k(q_i,p_j) }
+ *        ws = 3 doubles of caller-owned scratch (zeroed by the call).
+ *   bwd: dzq (+)= lambda * d mmd / d zq   (fp32, row pitch ldd floats). 2 <= B, Z <= 512. */
+int fmri_mmd_imq_fwd(const float* zq, int ldq, const float* zp, int ldp, int B, int Z, float sigma2, float lambda,
+                     float* mmd, double* ws, void* stream);
+int fmri_mmd_imq_bwd(const float* zq, int ldq, const float* zp, int ldp, int B, int Z, float sigma2, float lambda,
+                     float* dzq, int ldd, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused multi-tensor optimizers over fp32 master weights (one launch per parameter bucket).

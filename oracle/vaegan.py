@@ -402,6 +402,37 @@ def stage1_waegan_step(P, S, x, z_fake, cfg=CFG64, hp=HP_WAE, opt=None, step=1, 
     return out
 
 
+def stage1_wae_mmd_step(P, S, x, z_fake, cfg=CFG64, hp=HP_WAE, opt=None, step=1, lambda_mmd=10.0, sigma2=0.25):
+    """WAE-MMD variant of the Stage-I WAE step (BASELINE.json configs[1] names an MMD latent loss). PARITY UNPINNED: the
+    reference has no MMD code; this is train/train_wae_stage1.py:292-311 with the latent-discriminator
+    penalty replaced by lambda_mmd * B * MMD_IMQ(z_real, z_fake) (oracle/mmd.py; the factor B keeps the reference's
+    batch-SUM loss convention, :301-303) and no discriminator phase: ONE encoder forward, L_rec = sum 0.5 (x_recon - x)^2,
+    Adam(lr) on the encoder (grad of L_rec + L_pen; l_var receives none) and on the decoder (grad of L_rec)."""
+    from .mmd import mmd_imq
+
+    names = {b: bucket(P, b + ".") for b in ("encoder", "decoder")}
+    if opt is None:
+        opt = dict(m=OrderedDict((k, torch.zeros_like(v)) for k, v in P.items()),
+                   v=OrderedDict((k, torch.zeros_like(v)) for k, v in P.items()))
+    W = _leaf(P)
+    z_real, _ = encoder(W, S, x, cfg)
+    x_recon = decoder(W, S, z_real, cfg)
+    loss_rec = torch.sum(torch.sum(0.5 * (x_recon - x) ** 2, 1))
+    loss_pen = lambda_mmd * len(x) * mmd_imq(z_real, z_fake, sigma2)
+    g_enc = torch.autograd.grad(loss_rec + loss_pen, [W[n] for n in names["encoder"]], retain_graph=True, allow_unused=True)
+    g_dec = torch.autograd.grad(loss_rec, [W[n] for n in names["decoder"]])
+    grads = OrderedDict((n, g) for n, g in zip(names["encoder"], g_enc) if g is not None)
+    grads.update(zip(names["decoder"], g_dec))
+    newP, newm, newv = OrderedDict(P), OrderedDict(opt["m"]), OrderedDict(opt["v"])
+    for n in grads:
+        newP[n], newm[n], newv[n] = adam_update(P[n], grads[n], opt["m"][n], opt["v"][n], step, hp["lr"], hp["beta1"],
+                                                hp["beta2"], hp["eps"])
+    out = dict(z_real=z_real, x_recon=x_recon, loss_reconstruction=loss_rec, loss_penalty=loss_pen, grads=grads)
+    out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+    out["params"], out["adam"] = newP, dict(m=newm, v=newv)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- Stages II / III
 def make_cognitive(cfg=CFG64, z=None, seed=12345, dtype=torch.float32, jitter=True):
     """CognitiveEncoder + Decoder + Discriminator + teacher visual Encoder of VaeGanCognitive (models/vae_gan.py:323-345;
@@ -550,4 +581,50 @@ def cognitive_wae_step(P, S, fmri, image, stage, cfg=CFG64, hp=HP_WAE23, opt=Non
                loss_penalty=loss_pen, grads=grads, trained=trained)
     out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
     out["params"], out["adam"] = newP, dict(m=newm, v=newv)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- Stage III "dual" composite
+def make_dual_stage3(cfg=CFG64, z=None, seed=12345, dtype=torch.float32, jitter=True):
+    """BASELINE.json configs[3] ("Stage III cognitive WAE/Dual-GAN with two discriminators and fixed cognitive encoder").
+    NOT a single reference script: make_cognitive()'s nets plus the latent WaeDiscriminator of
+    WaeGanCognitive (models/vae_gan.py:542, kept N(0, 0.0099999) init) under the prefix latent_discriminator.*."""
+    z = z or cfg["latent_dim"]
+    P, S = make_cognitive(cfg, z, seed, dtype, jitter)
+    p, s = make_net("latent_discriminator.", wae_discriminator_spec(z), seed + 40, dtype, jitter, wae_disc=True)
+    P.update(p)
+    S.update(s)
+    return P, S
+
+
+def dual_stage3_step(P, S, fmri, image, eps, z_p, cfg=CFG64, hp=HP_VGAN, hp_lat=HP_WAE23, sq=None, opt=None, step=1,
+                     force_gate=None):
+    """The composite step of configs[3]: the image-side update of train/train_vgan_stage3.py:324-411
+    (cognitive_vaegan_step(stage=3): decoder + image discriminator trained with the gate and the gradient clamp, cognitive
+    encoder fixed) PLUS the latent-discriminator phase of train/train_wae_stage3.py:308-326 on
+    z_fake = cognitive_encoder(fmri) (the same forward, so its BN statistics are updated once) and
+    z_real = teacher.encoder(image) (train-mode BN, frozen): L_fake = -10 sum log(d(z_fake) + 1e-3),
+    L_real = -10 sum log(1 - d(z_real) + 1e-3), Adam(5e-4, betas (0.5, 0.999)) on the latent discriminator.
+    Each half is pinned to the reference through its own golden fixture (stage3_cognitive_*, stage3_cognitive_wae_*)."""
+    out = cognitive_vaegan_step(P, S, fmri, image, eps, None, z_p, 3, cfg, hp, sq=sq, force_gate=force_gate)
+    names = bucket(P, "latent_discriminator.")
+    if opt is None:
+        opt = dict(m=OrderedDict((k, torch.zeros_like(P[k])) for k in names),
+                   v=OrderedDict((k, torch.zeros_like(P[k])) for k in names))
+    W = _leaf(P)
+    z_fake = out["mu"]
+    z_real, _ = encoder(W, S, image, cfg, pre="teacher_net.encoder.")
+    d_real = wae_discriminator(W, z_real.detach(), pre="latent_discriminator.")
+    d_fake = wae_discriminator(W, z_fake.detach(), pre="latent_discriminator.")
+    loss_fake = -10 * torch.sum(torch.log(d_fake + 1e-3))
+    loss_real = -10 * torch.sum(torch.log(1 - d_real + 1e-3))
+    g = torch.autograd.grad(loss_fake + loss_real, [W[n] for n in names])
+    newP, newm, newv = out["params"], OrderedDict(opt["m"]), OrderedDict(opt["v"])
+    for n, gg in zip(names, g):
+        out["grads"][n] = gg.detach()
+        newP[n], newm[n], newv[n] = adam_update(P[n], gg.detach(), opt["m"][n], opt["v"][n], step, hp_lat["lr_dis"],
+                                                hp_lat["beta1"], hp_lat["beta2"], hp_lat["eps"])
+    out.update(z_real=z_real.detach(), d_real=d_real.detach(), d_fake=d_fake.detach(),
+               loss_discriminator_fake=loss_fake.detach(), loss_discriminator_real=loss_real.detach(),
+               adam=dict(m=newm, v=newv))
     return out

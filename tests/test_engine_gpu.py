@@ -254,3 +254,95 @@ def test_stage1_multi_step_stays_finite():
         tr.update(B)
         for k, v in tr.named_parameters().items():
             assert torch.isfinite(v).all(), (step, k)
+
+
+def run_dual_case(B, adt, seed=606):
+    """BASELINE.json configs[3] composite (engine.DualCognitiveStage3) against oracle.dual_stage3_step."""
+    P, S = O.make_dual_stage3(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.dual_stage3_step(P, S_ref, fmri, image, eps, z_p)
+    tr = engine.DualCognitiveStage3(P, S, hp.CFG64, 128, adt)
+    out = tr.forward_backward(fmri.cuda(), image.cuda(), eps.cuda(), z_p.cuda())
+    grads = {k: v.clone() for k, v in tr.named_grads().items()}
+    tr.update(B)
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = dict(mu=rel(out["mu"], ref["mu"]), x_tilde=rel(out["x_tilde"], ref["x_tilde"]),
+               disc_layer=rel(nchw_flat(out["disc_layer_nhwc"]), ref["disc_layer"]),
+               disc_class=rel(out["disc_class"], ref["disc_class"].reshape(-1)), mse=rel(out["mse"], ref["mse"]),
+               z_real=rel(out["z_real"], ref["z_real"]), d_real=rel(out["d_real"], ref["d_real"].reshape(-1)),
+               d_fake=rel(out["d_fake"], ref["d_fake"].reshape(-1)))
+    for k in ("loss_decoder", "loss_discriminator", "loss_discriminator_fake", "loss_discriminator_real"):
+        fwd[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    gerr = {}
+    for b in ("decoder.", "discriminator.", "latent_discriminator."):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        assert ks
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    # Adam state of the latent discriminator after one step: exp_avg = 0.5 g, exp_avg_sq = 0.001 g^2
+    bk = tr.buckets["latent_discriminator."]
+    ks = [k for k in ref["grads"] if k.startswith("latent_discriminator.")]
+    adam = {}
+    for i, name in enumerate(("m", "v")):
+        got = torch.cat([bk.state_view(i, k[len("latent_discriminator."):]).reshape(-1) for k in ks])
+        want = torch.cat([ref["adam"][name][k].reshape(-1) for k in ks])
+        adam[name] = rel(got, want)
+    newP = tr.named_parameters()
+    frozen_same = all(torch.equal(newP[k].cpu(), P[k].float()) for k in newP
+                      if k.startswith("encoder.") or k.startswith("teacher_net."))
+    gate_ok = (lo["train_dis"], lo["train_dec"]) == (ref["train_dis"], ref["train_dec"])
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
+    rep = dict(B=B, dtype=str(adt), forward=fwd, grad_bucket=gerr, adam=adam, frozen_same=frozen_same, gate_ok=gate_ok,
+               nbt_ok=nbt_ok, bn_worst=max(berr.items(), key=lambda t: t[1]))
+    with open(f"gpurun_out/parity_stage3_dual_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+def test_stage3_dual_fp32_exact_path():
+    rep = run_dual_case(8, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert max(rep["adam"].values()) < 1e-2, rep["adam"]
+    assert rep["frozen_same"] and rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 1e-4
+
+
+def test_stage3_dual_bf16_tensor_path():
+    rep = run_dual_case(16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["frozen_same"] and rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2
+
+
+@pytest.mark.parametrize("adt,B", [(torch.float32, 8), (torch.bfloat16, 16)])
+def test_stage1_wae_mmd_variant(adt, B):
+    """WaeGanStage1(penalty="mmd") against oracle.stage1_wae_mmd_step. EXTENSION, parity unpinned: the reference has no
+    MMD; the bar is agreement with our own published-estimator statement (oracle/mmd.py)."""
+    seed = 313
+    P, S = O.make_waegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    z_fake = O.synthetic_noise(B, 128, seed=seed)[0] * 0.5
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.stage1_wae_mmd_step(P, S_ref, x, z_fake)
+    tr = engine.WaeGanStage1(P, S, hp.CFG64, 128, adt, penalty="mmd")
+    out = tr.step(x.cuda(), z_fake.cuda())
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = dict(z_real=rel(out["z_real"], ref["z_real"]), x_recon=rel(out["x_recon"], ref["x_recon"]))
+    fwd["loss_reconstruction"] = abs(lo["loss_reconstruction"] - ref["loss_reconstruction"].item()) / abs(ref["loss_reconstruction"].item())
+    # the penalty is a difference of kernel sums of magnitude ~ 7 * lambda * B: error measured against that magnitude
+    fwd["loss_penalty"] = abs(lo["loss_penalty"] - ref["loss_penalty"].item()) / (7 * 10.0 * B)
+    grads = tr.named_grads()
+    gerr = {}
+    for b in ("encoder.", "decoder."):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    nbt = int(tr.named_buffers()["encoder.conv.0.bn.num_batches_tracked"])
+    print(adt, "wae-mmd forward", fwd, "grad buckets", gerr, "penalty", lo["loss_penalty"], ref["loss_penalty"].item())
+    assert max(fwd.values()) < (1e-4 if adt == torch.float32 else 2e-2), fwd
+    assert max(gerr.values()) < (5e-3 if adt == torch.float32 else 0.5), gerr
+    assert nbt == 1

@@ -475,3 +475,33 @@ def test_conv_dgrad_fused_bn_backward_sums(case):
     want_gx = (gm * (xc * invstd).double()).reshape(-1, Cin).sum(0)
     assert rel(sums[:Cin], want_g) < 2e-3
     assert rel(sums[Cin:2 * Cin], want_gx) < 2e-3
+
+
+@pytest.mark.parametrize("B,Z", [(2, 128), (7, 128), (64, 128), (100, 96), (300, 128), (37, 512)])
+def test_mmd_imq_fwd_bwd(B, Z):
+    """fmri_mmd_imq_{fwd,bwd} against oracle/mmd.py in fp64 (extension: the reference has no MMD; parity unpinned).
+    Tolerance 1e-5 relative (fp32 pairwise sums, fp64 accumulation across tiles); ragged B / Z exercise the tile masks."""
+    from oracle.mmd import mmd_imq
+
+    g = torch.Generator().manual_seed(B * 1000 + Z)
+    ycat = torch.randn(B, 2 * Z, generator=g)          # zq is the mu half of a [B, 2Z] head output (pitched view)
+    zp = torch.randn(B, Z, generator=g) * 0.5
+    lam, sigma2 = 10.0, 0.25
+    q64 = ycat[:, :Z].double().requires_grad_(True)
+    ref = lam * mmd_imq(q64, zp.double(), sigma2)
+    ref.backward()
+    yc = ycat.cuda()
+    zq_d, zp_d = yc[:, :Z], zp.cuda()
+    out, ws = torch.empty(1, device="cuda"), torch.empty(3, device="cuda", dtype=torch.float64)
+    L.mmd_imq_fwd(zq_d, zp_d, B, Z, sigma2, lam, out, ws)
+    dq = torch.full((B, Z), 7.0, device="cuda")
+    L.mmd_imq_bwd(zq_d, zp_d, B, Z, sigma2, lam, dq)
+    base = 1e-3   # same magnitude as the gradient, so that fp32 accumulation onto it keeps the 1e-5 resolution
+    dq2 = torch.full((B, Z), base, device="cuda")
+    L.mmd_imq_bwd(zq_d, zp_d, B, Z, sigma2, lam, dq2, accumulate=True)
+    torch.cuda.synchronize()
+    # the estimate is a difference of kernel sums of magnitude ~ 7 * lam: the bound is relative to that magnitude
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 2e-6 * 7 * lam, (out.item(), ref.item())
+    gr = q64.grad.float()
+    assert rel(dq.cpu(), gr) < 1e-5, rel(dq.cpu(), gr)
+    assert rel(dq2.cpu() - base, gr) < 1e-4

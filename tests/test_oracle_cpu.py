@@ -175,3 +175,49 @@ def test_optimizer_restatements_match_torch_optim():
         opt.step()
         q, m, v = O.adam_update(q, g, m, v, t, 1e-3)
     assert _rel(q.numpy(), p.detach().numpy()) < 1e-12
+
+
+def test_dual_stage3_composite_equals_its_pinned_halves():
+    """BASELINE.json configs[3] is a composite, so the reference holds no single fixture for it; its two
+    halves are the golden-pinned steps above. The composite must reproduce each half exactly on shared weights."""
+    B, seed = 4, 77
+    Pw, Sw = O.make_cognitive_wae(O.CFG64, seed=seed, dtype=torch.float64)
+    Pd, Sd = O.make_dual_stage3(O.CFG64, seed=seed, dtype=torch.float64)
+    for k in Pw:   # share the cognitive encoder, the teacher encoder and the latent discriminator
+        if k.startswith("encoder.") or k.startswith("teacher_net.encoder."):
+            Pd[k] = Pw[k].clone()
+        elif k.startswith("discriminator."):
+            Pd["latent_" + k] = Pw[k].clone()
+    fmri, image = O.synthetic_fmri(B, seed=seed).double(), O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    wae = O.cognitive_wae_step(Pw, Sw, fmri, image, 3)
+    Sc = {k: v.clone() for k, v in Sd.items()}
+    img = O.cognitive_vaegan_step(Pd, Sc, fmri, image, eps, None, z_p, 3)
+    dual = O.dual_stage3_step(Pd, Sd, fmri, image, eps, z_p)
+    for k in ("z_real", "d_real", "d_fake", "loss_discriminator_fake", "loss_discriminator_real"):
+        assert _rel(dual[k].numpy(), wae[k].numpy()) < 1e-12, k
+    for k, g in wae["grads"].items():
+        if k.startswith("discriminator."):
+            assert _rel(dual["grads"]["latent_" + k].numpy(), g.numpy()) < 1e-12, k
+            assert _rel(dual["params"]["latent_" + k].numpy(), wae["params"][k].numpy()) < 1e-12, k
+    for k in ("x_tilde", "disc_layer", "disc_class", "loss_decoder", "loss_discriminator"):
+        assert _rel(dual[k].numpy(), img[k].numpy()) < 1e-12, k
+    for k, g in img["grads"].items():
+        assert _rel(dual["grads"][k].numpy(), g.numpy()) < 1e-12, k
+        assert _rel(dual["params"][k].numpy(), img["params"][k].numpy()) < 1e-12, k
+
+
+def test_mmd_statement_known_answers():
+    """oracle/mmd.py (parity unpinned: no reference MMD code). Closed form at B=2 and basic estimator properties."""
+    from oracle.mmd import SCALES, mmd_imq
+
+    q = torch.tensor([[0.0, 0.0], [1.0, 0.0]], dtype=torch.float64)
+    p = torch.tensor([[0.0, 1.0], [1.0, 1.0]], dtype=torch.float64)
+    # d_qq = d_pp = 1 (off-diagonal), d_qp = [[1, 2], [2, 1]], Z = 2, sigma2 = 1 -> C_s = 4 s
+    want = sum(2 * (4 * s / (4 * s + 1)) * 2 / 2 - 2 * (2 * 4 * s / (4 * s + 1) + 2 * 4 * s / (4 * s + 2)) / 4 for s in SCALES)
+    assert abs(mmd_imq(q, p, 1.0).item() - want) < 1e-12
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(256, 8, generator=g, dtype=torch.float64), torch.randn(256, 8, generator=g, dtype=torch.float64)
+    same, shifted = mmd_imq(a, b, 1.0).item(), mmd_imq(a + 2.0, b, 1.0).item()
+    assert abs(same) < 0.05 and shifted > 0.5
+    assert abs(mmd_imq(a, b, 1.0).item() - mmd_imq(b, a, 1.0).item()) < 1e-12   # symmetric in its arguments

@@ -314,6 +314,37 @@ class _BceFn(torch.autograd.Function):
         return dp, None, None
 
 
+class _MmdImqFn(torch.autograd.Function):
+    """WAE-MMD penalty with the inverse-multiquadratic kernel (fmri_mmd_imq_{fwd,bwd}). EXTENSION: the reference has no
+    MMD; pinned against oracle/mmd.py only. Differentiable in the encoded latents zq; zp are prior samples."""
+
+    @staticmethod
+    def forward(ctx, zq, zp, sigma2, lam):
+        q, p = _cuda_f32(zq, "mmd latents"), _cuda_f32(zp, "mmd prior samples")
+        if q.dim() != 2 or q.shape != p.shape:
+            raise L.FmriError("mmd_imq expects two [B, Z] tensors of the same shape")
+        B, Z = q.shape
+        out = torch.empty(1, dtype=F32, device=q.device)
+        ws = torch.empty(3, dtype=torch.float64, device=q.device)
+        L.mmd_imq_fwd(q, p, B, Z, sigma2, lam, out, ws)
+        ctx.save_for_backward(q, p)
+        ctx.sigma2, ctx.lam = sigma2, lam
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        q, p = ctx.saved_tensors
+        B, Z = q.shape
+        dq = torch.empty_like(q)
+        L.mmd_imq_bwd(q, p, B, Z, ctx.sigma2, ctx.lam, dq)
+        return dq * g.to(F32), None, None, None
+
+
+def mmd_imq(zq, zp, sigma2=1.0, lam=1.0):
+    """lam * MMD_IMQ(zq, zp): the WAE-MMD latent penalty (Tolstikhin et al.), sigma2 = the prior's variance."""
+    return _MmdImqFn.apply(zq, zp, float(sigma2), float(lam))
+
+
 def reparameterize(mu, logvar, eps):
     return _ReparamFn.apply(mu, logvar, eps)
 

@@ -11,6 +11,7 @@
 #include "tc_kernels.cuh"
 #include "hconv_kernels.cuh"
 #include "hwgrad_kernels.cuh"
+#include "mmd_kernels.cuh"
 
 using namespace fmri;
 
@@ -1635,6 +1636,59 @@ extern "C" int fmri_rowsqdiff_fwd(const void* a, const void* b, int dtype, float
         rowsqdiff_fwd_kernel<float><<<(unsigned)rows, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(a),
                                                                           reinterpret_cast<const float*>(b), out, F,
                                                                           scale);
+    LAUNCH_OK();
+    return 0;
+}
+// ------------------------------------------------------------------------------------------------ WAE-MMD (extension)
+static size_t mmd_smem() { return sizeof(float) * (size_t)(2 * MMD_T * MMD_LD + MMD_T * (MMD_T + 1)); }
+static int mmd_check(int B, int Z) {
+    if (B < 2) return fail(FMRI_ERR_ARG, "mmd: the unbiased estimator needs B >= 2 (got %d)", B);
+    if (Z < 1 || Z > MMD_KC * MMD_MAXCH) return fail(FMRI_ERR_ARG, "mmd: Z=%d outside [1, %d]", Z, MMD_KC * MMD_MAXCH);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(mmd_imq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mmd_smem());
+        cudaFuncSetAttribute(mmd_imq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mmd_smem());
+        attr = true;
+    }
+    return 0;
+}
+// j-tile slices so that the grid fills the 148 SMs twice over (2 resident CTAs per SM)
+static int mmd_splits(int base_ctas, int ntj) { return std::max(1, std::min(ntj, (2 * 148 + base_ctas - 1) / base_ctas)); }
+extern "C" int fmri_mmd_imq_fwd(const float* zq, int ldq, const float* zp, int ldp, int B, int Z, float sigma2,
+                                float lambda, float* mmd, double* ws, void* stream) {
+    if (int rc = mmd_check(B, Z)) return rc;
+    if (!zq || !zp || !mmd || !ws) return fail(FMRI_ERR_ARG, "mmd_fwd: null pointer");
+    MmdParams P{};
+    P.q = zq; P.p = zp; P.ldq = ldq; P.ldp = ldp; P.B = B; P.Z = Z;
+    P.cbase = 2.f * (float)Z * sigma2;
+    P.stat = ws;
+    const int nt = (B + MMD_T - 1) / MMD_T;
+    P.nsplit = mmd_splits(2 * nt, nt);
+    cudaMemsetAsync(ws, 0, 3 * sizeof(double), S(stream));
+    dim3 grid(nt, 2, P.nsplit);
+    mmd_imq_kernel<false><<<grid, MMD_THREADS, mmd_smem(), S(stream)>>>(P);
+    LAUNCH_OK();
+    mmd_finalize_kernel<<<1, 1, 0, S(stream)>>>(ws, B, lambda, mmd);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_mmd_imq_bwd(const float* zq, int ldq, const float* zp, int ldp, int B, int Z, float sigma2,
+                                float lambda, float* dzq, int ldd, int accumulate, void* stream) {
+    if (int rc = mmd_check(B, Z)) return rc;
+    if (!zq || !zp || !dzq) return fail(FMRI_ERR_ARG, "mmd_bwd: null pointer");
+    MmdParams P{};
+    P.q = zq; P.p = zp; P.ldq = ldq; P.ldp = ldp; P.B = B; P.Z = Z;
+    P.cbase = 2.f * (float)Z * sigma2;
+    P.dq = dzq; P.ldd = ldd; P.accumulate = accumulate;
+    const double b = (double)B;
+    P.w_same = (float)(lambda * 4.0 / (b * (b - 1.0)));
+    P.w_cross = (float)(-lambda * 4.0 / (b * b));
+    const int nt = (B + MMD_T - 1) / MMD_T, nch = (Z + MMD_KC - 1) / MMD_KC;
+    P.nsplit = mmd_splits(nt * nch, nt);
+    if (P.nsplit > 1 && !accumulate)
+        cudaMemset2DAsync(dzq, (size_t)ldd * sizeof(float), 0, (size_t)Z * sizeof(float), (size_t)B, S(stream));
+    dim3 grid(nt, 1, P.nsplit * nch);
+    mmd_imq_kernel<true><<<grid, MMD_THREADS, mmd_smem(), S(stream)>>>(P);
     LAUNCH_OK();
     return 0;
 }

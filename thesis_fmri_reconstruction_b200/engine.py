@@ -225,17 +225,23 @@ class WaeGanStage1(_TrainerBase):
     L_pen = -10 sum log(d + 1e-3); Adam on the encoder (grad of L_rec + L_pen; l_var gets none) and the decoder (L_rec).
     """
 
-    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None):
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None, penalty="gan", lambda_mmd=10.0,
+                 sigma2=0.25):
         from .hp import HP_WAE
 
+        if penalty not in ("gan", "mmd"):
+            raise L.FmriError("penalty must be 'gan' (the reference's latent discriminator) or 'mmd'")
         self.cfg, self.z, self.adt = cfg, z, adt
+        self.penalty, self.lambda_mmd, self.sigma2 = penalty, float(lambda_mmd), float(sigma2)
         self.hp = dict(HP_WAE if hp is None else hp)
         self.enc = NN.EncoderNet(cfg, z, adt)
         self.dec = NN.DecoderNet(cfg, z, adt)
-        self.dis = NN.WaeDiscriminatorNet(z, adt)
         dev = torch.device("cuda")
         self.buckets = OrderedDict()
-        self.nets = OrderedDict((("encoder.", self.enc), ("decoder.", self.dec), ("discriminator.", self.dis)))
+        self.nets = OrderedDict((("encoder.", self.enc), ("decoder.", self.dec)))
+        if penalty == "gan":
+            self.dis = NN.WaeDiscriminatorNet(z, adt)
+            self.nets["discriminator."] = self.dis
         for pre, net in self.nets.items():
             named = _split(params, pre)
             diff = set(net.param_names()) ^ set(named)
@@ -250,6 +256,7 @@ class WaeGanStage1(_TrainerBase):
                    "discriminator.": 0.5 * float(self.hp["lr"])}
         self.t = 0
         self._ones_buf = None
+        self._mmd_ws = torch.empty(3, dtype=torch.float64, device=dev)
         self._setup_dist(dist_group)
         for pre, net in self.nets.items():
             net.refresh(self.buckets[pre].P, inplace=True)
@@ -267,6 +274,8 @@ class WaeGanStage1(_TrainerBase):
 
     def step(self, x, z_fake):
         """x [B,3,H,W] fp32 NCHW, z_fake [B,z] fp32 (= 0.5 * N(0,1), train_wae_stage1.py:276), device resident."""
+        if self.penalty == "mmd":
+            return self._step_mmd(x, z_fake)
         B, z = x.shape[0], self.z
         be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
         self.t += 1
@@ -319,6 +328,42 @@ class WaeGanStage1(_TrainerBase):
                 self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
         return dict(z_real=z_real, x_recon=x_recon, d_real=p_real, d_fake=p_fake, d_real_g=p_real2)
 
+    def _step_mmd(self, x, z_fake):
+        """WAE-MMD variant (EXTENSION, parity unpinned: the reference has no MMD, SURVEY.md 0-3): no latent discriminator;
+        L_pen = lambda_mmd * B * MMD_IMQ(z_real, z_fake) over this rank's batch (per-rank, like BatchNorm), one encoder
+        forward. Everything else as train_wae_stage1.py:292-311."""
+        B, z = x.shape[0], self.z
+        be, bd = self.buckets["encoder."], self.buckets["decoder."]
+        self.t += 1
+        sc, ones = self.sc, self._ones(B)
+        nbe, nbd = {}, {}
+        ycat, ce = self.enc.forward(be.P, self.Ssub["encoder."], x, True, 1, nbe)
+        z_real = ycat[:, :z]
+        x_recon, cd = self.dec.forward(bd.P, self.Ssub["decoder."], z_real, True, 1, nbd)
+        rec = E(B)
+        L.rowsqdiff_fwd(x_recon, x, rec, B, x[0].numel(), 0.5)
+        L.vecsum(rec, B, 1.0, sc[2:3])
+        lam = self.lambda_mmd * B
+        L.mmd_imq_fwd(z_real, z_fake, B, z, self.sigma2, lam, sc[3:4], self._mmd_ws)
+        dxr = torch.empty_like(x_recon)
+        L.rowsqdiff_bwd(x_recon, x, ones, dxr, None, B, x[0].numel(), 0.5)
+        dz_rec = self.dec.backward(bd.P, cd, 1.0, dxr, 0.0, None, bd.G, False, True, True)
+        self._allreduce_async([bd.flat_g])
+        dmu = dz_rec if dz_rec.dtype == F32 and dz_rec.is_contiguous() else dz_rec.to(F32).contiguous()
+        L.mmd_imq_bwd(z_real, z_fake, B, z, self.sigma2, lam, dmu, accumulate=True)
+        dycat = Z(B, 2 * z, dtype=self.adt)
+        L.cast2d(dmu, z, dycat[:, :z], 2 * z, B, z)
+        be.flat_g.zero_()
+        self.enc.backward(be.P, ce, dycat, be.G, False, True, False)
+        self._allreduce_async([be.flat_g, sc[:8]])
+        self._wait_comm()
+        self._adam("encoder.")
+        self._adam("decoder.")
+        for pre, d in (("encoder.", nbe), ("decoder.", nbd)):
+            for k, v in d.items():
+                self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
+        return dict(z_real=z_real, x_recon=x_recon)
+
     def losses(self):
         s = self.sc.tolist()
         return dict(loss_discriminator_fake=s[0], loss_discriminator_real=s[1], loss_reconstruction=s[2],
@@ -337,6 +382,8 @@ class VaeGanCognitiveStage(_TrainerBase):
     Both clamp gradients to [-1, 1] inside the fused RMSprop launch (stage2 :391,406; stage3 :402,410).
     Parameter keys: encoder.* (CognitiveEncoder), decoder.*, discriminator.*, teacher_net.encoder.* (stage 2 only)."""
 
+    LATENT_DISCRIMINATOR = False
+
     def __init__(self, params, buffers, cfg, stage, z=128, adt=BF16, hp=None, dist_group=None, voxels=None):
         from .hp import HP_VGAN, NUM_VOXELS
 
@@ -348,9 +395,12 @@ class VaeGanCognitiveStage(_TrainerBase):
         self.dec = NN.DecoderNet(cfg, z, adt)
         self.dis = NN.DiscriminatorNet(cfg, adt)
         self.nets = OrderedDict((("encoder.", self.cog), ("decoder.", self.dec), ("discriminator.", self.dis)))
-        if stage == 2:
+        if stage == 2 or self.LATENT_DISCRIMINATOR:
             self.tenc = NN.EncoderNet(cfg, z, adt)
             self.nets["teacher_net.encoder."] = self.tenc
+        if self.LATENT_DISCRIMINATOR:
+            self.ldis = NN.WaeDiscriminatorNet(z, adt)
+            self.nets["latent_discriminator."] = self.ldis
         dev = torch.device("cuda")
         self.buckets = OrderedDict()
         for pre, net in self.nets.items():
@@ -358,11 +408,12 @@ class VaeGanCognitiveStage(_TrainerBase):
             diff = set(net.param_names()) ^ set(named)
             if diff:
                 raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(diff)}")
-            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named), 1)
+            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named),
+                                       2 if pre == "latent_discriminator." else 1)
         self.S = OrderedDict((k, v.to(dev).clone()) for k, v in buffers.items())
         self.Ssub = {pre: _split(self.S, pre) for pre in self.buckets}
         self.nbt = {}
-        self.sc = Z(16)
+        self.sc = Z(16)      # [0..5] as VaeGanStage1; [6], [7] = latent L_fake, L_real; [8], [9] = gates
         self.lr = {pre: float(self.hp["lr"]) for pre in self.buckets}
         self._ones_buf = None
         self._setup_dist(dist_group)
@@ -454,3 +505,66 @@ class VaeGanCognitiveStage(_TrainerBase):
         return out
 
     losses = VaeGanStage1.losses
+
+
+class DualCognitiveStage3(VaeGanCognitiveStage):
+    """BASELINE.json configs[3], "Stage III cognitive WAE/Dual-GAN with two discriminators and fixed cognitive encoder": a
+    composite, not a single reference script. The image side is the Stage-III VAE/GAN update
+    (/root/reference/train/train_vgan_stage3.py:324-411: decoder + image Discriminator, gate, gradient clamp, RMSprop); the
+    latent side is the discriminator phase of /root/reference/train/train_wae_stage3.py:308-326: z_fake = the cognitive
+    encoder's mu (the same forward), z_real = teacher.encoder(image) (train-mode BN, frozen weights),
+    L_fake = -10 sum log(d(z_fake) + 1e-3), L_real = -10 sum log(1 - d(z_real) + 1e-3), Adam(5e-4, betas (0.5, 0.999)) on
+    the latent WaeDiscriminator. Extra parameter keys: teacher_net.encoder.*, latent_discriminator.main.*."""
+
+    LATENT_DISCRIMINATOR = True
+
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, hp_latent=None, dist_group=None, voxels=None):
+        from .hp import HP_WAE23
+
+        super().__init__(params, buffers, cfg, 3, z, adt, hp, dist_group, voxels)
+        self.hp_lat = dict(HP_WAE23 if hp_latent is None else hp_latent)
+        self.t = 0
+        self.lsc = Z(2)  # latent L_fake, L_real (sums); all-reduced with the latent discriminator's gradient bucket
+
+    def forward_backward(self, fmri, image, eps, z_p):
+        out = super().forward_backward(fmri, image, eps, None, z_p)
+        B, z, sc = fmri.shape[0], self.z, self.sc
+        bt, bl = self.buckets["teacher_net.encoder."], self.buckets["latent_discriminator."]
+        nbt = {}
+        yt, _ = self.tenc.forward(bt.P, self.Ssub["teacher_net.encoder."], image, True, 1, nbt)
+        for k, v in nbt.items():
+            self.nbt["teacher_net.encoder." + k] = self.nbt.get("teacher_net.encoder." + k, 0) + v
+        z_fake, z_real = out["mu"], yt[:, :z]
+        p_real, cr = self.ldis.forward(bl.P, z_real)
+        p_fake, cf = self.ldis.forward(bl.P, z_fake)
+        l, gp, ones = E(2 * B), E(2 * B), self._ones(3 * B)
+        L.bce_fwd(p_fake, l[:B], B, True, 10.0)
+        L.bce_fwd(p_real, l[B:], B, False, 10.0)
+        L.vecsum(l[:B], B, 1.0, self.lsc[0:1])
+        L.vecsum(l[B:], B, 1.0, self.lsc[1:2])
+        L.bce_bwd(p_fake, ones, gp[:B], B, True, 10.0)
+        L.bce_bwd(p_real, ones, gp[B:], B, False, 10.0)
+        self.ldis.backward(bl.P, cf, gp[:B], bl.G, False, True, False)
+        self.ldis.backward(bl.P, cr, gp[B:], bl.G, True, True, False)
+        self._allreduce_async([bl.flat_g, self.lsc])
+        out.update(z_real=z_real, d_real=p_real, d_fake=p_fake)
+        return out
+
+    def update(self, B_global):
+        super().update(B_global)
+        self.t += 1
+        b, hp = self.buckets["latent_discriminator."], self.hp_lat
+        L.multi_tensor_adam([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], float(hp["lr_dis"]), hp["beta1"],
+                            hp["beta2"], hp["eps"], self.t)
+        self.ldis.refresh(b.P, inplace=True)
+
+    def step(self, fmri, image, eps, z_p):
+        out = self.forward_backward(fmri, image, eps, z_p)
+        self.update(fmri.shape[0] * self.world)
+        return out
+
+    def losses(self):
+        d = VaeGanStage1.losses(self)
+        lf, lr = self.lsc.tolist()
+        d.update(loss_discriminator_fake=lf, loss_discriminator_real=lr)
+        return d

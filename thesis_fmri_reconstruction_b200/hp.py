@@ -15,6 +15,8 @@ NUM_VOXELS = 3620
 HP_VGAN = dict(lr=1e-4, alpha=0.9, eps=1e-8, lambda_mse=1e-6, margin=0.35, equilibrium=0.68)
 # train_wae_stage1.py:221-224 (Adam betas (0.5, 0.999); the discriminator runs at lr / 2), wae_config.py:17
 HP_WAE = dict(lr=1e-4, beta1=0.5, beta2=0.999, eps=1e-8)
+# train_wae_stage2.py:237-243, train_wae_stage3.py (hard-coded: encoder / decoder 1e-3, latent discriminator 5e-4)
+HP_WAE23 = dict(lr=1e-3, lr_dis=5e-4, beta1=0.5, beta2=0.999, eps=1e-8)
 
 
 def cfg_from_module(mc):

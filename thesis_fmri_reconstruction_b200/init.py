@@ -130,3 +130,14 @@ def init_cognitive(cfg, z, seed=12345, with_teacher=True, input_size=NUM_VOXELS)
         P.update(p)
         S.update(s)
     return P, S
+
+
+def init_dual_stage3(cfg, z, seed=12345, input_size=NUM_VOXELS):
+    """init_cognitive() with the teacher's visual Encoder plus the latent WaeDiscriminator of WaeGanCognitive
+    (models/vae_gan.py:542: keeps its own N(0, 0.0099999) init, :522-525) under latent_discriminator.*."""
+    P, S = init_cognitive(cfg, z, seed, True, input_size)
+    gen = torch.Generator().manual_seed(seed + 1)
+    p, s = init_net("latent_discriminator.", wae_discriminator_table(z), gen, 0.0099999)
+    P.update(p)
+    S.update(s)
+    return P, S

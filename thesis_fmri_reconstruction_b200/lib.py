@@ -377,6 +377,19 @@ def rowsqdiff_bwd(a, b, g, da, db, rows, F, scale):
                                      stream()))
 
 
+def mmd_imq_fwd(zq, zp, B, Z, sigma2, lam, mmd, ws):
+    """zq / zp: fp32 [B, Z] views with unit column stride (row pitch taken from .stride(0)); ws: 3 float64."""
+    _require_cuda(zq, zp, mmd, ws, contiguous=False)
+    _check(load().fmri_mmd_imq_fwd(ptr(zq), zq.stride(0), ptr(zp), zp.stride(0), B, Z, _f(sigma2), _f(lam), ptr(mmd),
+                                   ptr(ws), stream()))
+
+
+def mmd_imq_bwd(zq, zp, B, Z, sigma2, lam, dzq, accumulate=False):
+    _require_cuda(zq, zp, dzq, contiguous=False)
+    _check(load().fmri_mmd_imq_bwd(ptr(zq), zq.stride(0), ptr(zp), zp.stride(0), B, Z, _f(sigma2), _f(lam), ptr(dzq),
+                                   dzq.stride(0), int(accumulate), stream()))
+
+
 def head_sigmoid_fwd(x, w, bias, p, rows, F):
     _require_cuda(x, w, bias, p)
     _check(load().fmri_head_sigmoid_fwd(ptr(x), dt(x), ptr(w), ptr(bias), ptr(p), rows, F, stream()))
