@@ -507,6 +507,22 @@ static int launch_wg(const WgParams& p, cudaStream_t st) {
     LAUNCH_OK();
     return 0;
 }
+// Split count for kernels that run ONE CTA per SM (the ~200 KB shared-memory wgrad tiles): pick s so that base * s CTAs fill
+// whole waves of 148 (an ncu capture showed 312- and 300-CTA grids = 2.1 waves, i.e. a third round that is 11 % full and
+// a 30 % longer kernel). Searches one to three waves, with a small preference for fewer, larger CTAs.
+static int wave_splits(long long base, long long max_splits) {
+    const long long lo = std::max<long long>(1, (148 + base - 1) / base);
+    if (max_splits <= lo) return (int)std::max<long long>(1, max_splits);
+    const long long hi = std::min<long long>(max_splits, std::max<long long>(lo, (3 * 148) / base));
+    long long best = lo;
+    double best_score = -1.0;
+    for (long long s = lo; s <= hi; ++s) {
+        const long long ctas = base * s, waves = (ctas + 147) / 148;
+        const double score = (double)ctas / (148.0 * waves) - 0.01 * waves;
+        if (score > best_score) { best_score = score; best = s; }
+    }
+    return (int)best;
+}
 static int dispatch_wg(const WgParams& p, int BN, int NCH, cudaStream_t st) {
     if (NCH == 64 && BN == 128) return p.num_taps > 1 ? launch_wg<128, 64, 2, 2>(p, st) : launch_wg<128, 64, 3, 1>(p, st);
     if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4, 1>(p, st);
@@ -572,9 +588,7 @@ static int run_wgrad_tc(const void* Dn, int N, int PH, int PW, int Cd, const voi
     const int tap_groups = (NCH == 32 && BN == 32 && num_taps % 5 == 0) ? num_taps / 5
                            : ((NCH == 64 && BN == 128 && num_taps > 1) ? (num_taps + 1) / 2 : num_taps);
     const long long base = (long long)tap_groups * p.m_tiles * p.n_tiles;
-    long long splits = std::max<long long>(1, (2 * 148 + base - 1) / base);
-    splits = std::min<long long>(splits, std::max<long long>(1, pt / 4));
-    p.splits = (int)splits;
+    p.splits = wave_splits(base, std::max<long long>(1, pt / 4));
     p.out = ws;
     return dispatch_wg(p, BN, NCH, st);
 }
@@ -1342,9 +1356,7 @@ extern "C" int fmri_linear_wgrad(const fmri_linear_desc* d, const void* x, int l
             p.m_tiles = d->N / 128;
             p.n_tiles = d->K / BN;
             const long long base = (long long)p.m_tiles * p.n_tiles;
-            long long splits = std::max<long long>(1, (148 + base - 1) / base);
-            splits = std::min<long long>(splits, std::max<long long>(1, p.tiles_x / 2));
-            p.splits = (int)splits;
+            p.splits = wave_splits(base, std::max<long long>(1, p.tiles_x / 2));
             p.out = dw;
             return dispatch_wg(p, BN, NCH, S(stream));
         }
@@ -1426,7 +1438,12 @@ static int bn_bwd_reduce_t(const void* x, const void* dy, long long rows, int C,
     CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
     if (C % 2 == 0 && ((C / 2) >= 256 ? (C / 2) % 256 == 0 : 256 % (C / 2) == 0)) {
         const int ry = std::max(1, 256 / (C / 2));
-        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * 8 - 1) / (148 * 8));
+        static int occ1 = 0;  // resident CTAs per SM of this instantiation: the grid is exactly one wave
+        if (!occ1) {
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, bn_bwd_cp_kernel<1, Tx, Tg>, 256, 0));
+            occ1 = std::max(1, occ1);
+        }
+        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * occ1 - 1) / (148 * occ1));
         dim3 gcp(cdiv(rows, per), std::max(1, std::min(8, (C / 2) / 256)));
         bn_bwd_cp_kernel<1, Tx, Tg><<<gcp, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy), nullptr,
                                                        rows, C, mean, invstd, gamma, beta, relu, 1, nullptr, nullptr, ws,
@@ -1468,7 +1485,12 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
     LAUNCH_OK();
     if (dx && C % 2 == 0 && ((C / 2) >= 256 ? (C / 2) % 256 == 0 : 256 % (C / 2) == 0)) {
         const int ry = std::max(1, 256 / (C / 2));
-        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * 8 - 1) / (148 * 8));
+        static int occ2 = 0;
+        if (!occ2) {
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, bn_bwd_cp_kernel<2, Tx, Tg>, 256, 0));
+            occ2 = std::max(1, occ2);
+        }
+        const long long per = std::max<long long>((long long)ry * 16, (rows + 148 * occ2 - 1) / (148 * occ2));
         dim3 gcp(cdiv(rows, per), std::max(1, std::min(8, (C / 2) / 256)));
         bn_bwd_cp_kernel<2, Tx, Tg><<<gcp, 256, 0, st>>>(reinterpret_cast<const Tx*>(x), reinterpret_cast<const Tg*>(dy),
                                                        reinterpret_cast<Tg*>(dx), rows, C, mean, invstd, gamma, beta, relu,

@@ -869,22 +869,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const Tx* __restrict_
 // stride, so it carries only 2 channels' coefficients (12 registers instead of 48) and keeps 8 independent row accesses in
 // flight; a warp's access to one row is one contiguous 128 B (bf16) segment. The 8-channels-per-thread versions above are
 // register-bound (84-87 registers, 3 CTAs/SM) and reach 3.7-4.1 TB/s; relu_bwd with the same traffic pattern reaches 6.2.
+// raw(): the untouched 32- / 64-bit word (what stays in registers while loads are in flight), cvt(): the two floats
 template <typename T> struct Pair;
 template <> struct Pair<__nv_bfloat16> {
-    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
-        const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
-        return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
-    }
+    using Raw = uint32_t;
+    static __device__ __forceinline__ Raw raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+    static __device__ __forceinline__ float2 cvt(Raw r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) { return cvt(raw(p)); }
     static __device__ __forceinline__ void st(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b); }
 };
 template <> struct Pair<float> {
-    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    using Raw = float2;
+    static __device__ __forceinline__ Raw raw(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ float2 cvt(Raw r) { return r; }
+    static __device__ __forceinline__ float2 ld(const float* p) { return raw(p); }
     static __device__ __forceinline__ void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 };
 
 // MODE 1: sums sum(g), sum(g*xhat) per channel; MODE 2: dx = scale*(g - mean_g - xhat*mean_gx)
 template <int MODE, typename Tx, typename Tg>
-__global__ void __launch_bounds__(256) bn_bwd_cp_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy, Tg* __restrict__ dx,
+__global__ void __launch_bounds__(256, 8) bn_bwd_cp_kernel(const Tx* __restrict__ x, const Tg* __restrict__ dy, Tg* __restrict__ dx,
                                                         long long rows, int C, const float* __restrict__ mean,
                                                         const float* __restrict__ invstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -915,16 +919,18 @@ __global__ void __launch_bounds__(256) bn_bwd_cp_kernel(const Tx* __restrict__ x
             long long r = r0 + ty;
 #pragma unroll 1
             for (; r + 7LL * ry < r1; r += 8LL * ry) {
-                float2 xv[8], gv[8];
+                typename Pair<Tx>::Raw xr[8];
+                typename Pair<Tg>::Raw gr[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    xv[u] = Pair<Tx>::ld(x + (r + (long long)u * ry) * C + c);
-                    gv[u] = Pair<Tg>::ld(dy + (r + (long long)u * ry) * C + c);
+                    xr[u] = Pair<Tx>::raw(x + (r + (long long)u * ry) * C + c);
+                    gr[u] = Pair<Tg>::raw(dy + (r + (long long)u * ry) * C + c);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float xc0 = xv[u].x - mu0, xc1 = xv[u].y - mu1;
-                    float g0 = gv[u].x, g1 = gv[u].y;
+                    const float2 xv = Pair<Tx>::cvt(xr[u]), gv = Pair<Tg>::cvt(gr[u]);
+                    const float xc0 = xv.x - mu0, xc1 = xv.y - mu1;
+                    float g0 = gv.x, g1 = gv.y;
                     if (relu && !(xc0 * sc0 + be0 > 0.f)) g0 = 0.f;
                     if (relu && !(xc1 * sc1 + be1 > 0.f)) g1 = 0.f;
                     if (MODE == 1) {  // q accumulates g*xc; the invstd factor is applied once at the end
