@@ -345,12 +345,17 @@ def run_ours(args):
     pk = peaks()
     roof = None
     if not args.no_profile:
+        from thesis_fmri_reconstruction_b200 import nets as _nets
+
         torch.cuda.synchronize()
+        side = _nets.WGRAD_SIDE_STREAM
+        _nets.WGRAD_SIDE_STREAM = False   # attribution pass: every kernel alone on the compute stream (no overlap)
         lib.profile_begin()
         psteps = max(1, min(3, args.steps))
         for _ in range(psteps):
             step_dev()
         agg = lib.profile_end()
+        _nets.WGRAD_SIDE_STREAM = side
         tot_ms = sum(a["ms"] for a in agg.values())
         fam = {}
         for name, a in agg.items():

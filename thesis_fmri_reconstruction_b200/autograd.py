@@ -126,6 +126,7 @@ class _EncoderFn(torch.autograd.Function):
         G = {n: torch.empty_like(ctx.P[n]) for n in ctx.names}
         if any(needs):
             net.backward(ctx.P, ctx.c, dycat, G, False, True, dlv is not None)
+            NN.join_side()   # weight gradients were produced on the side stream (nets.WGRAD_SIDE_STREAM)
         if dlv is None:  # WAE: logvar unused -> its head receives no gradient (Adam must skip it, train_wae_stage1.py:296)
             for n in ("l_var.weight", "l_var.bias"):
                 G[n] = None
@@ -152,6 +153,7 @@ class _DecoderFn(torch.autograd.Function):
         need_dz = ctx.needs_input_grad[1]
         G = {n: torch.empty_like(ctx.P[n]) for n in ctx.names} if need_dw else None
         dz = ctx.net.backward(ctx.P, ctx.c, 1.0, dimg.to(F32).contiguous(), 0.0, None, G, False, need_dw, need_dz)
+        NN.join_side()
         return (None, dz) + tuple(G[n] if need else None for n, need in zip(ctx.names, needs))
 
 
@@ -199,6 +201,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             dimg = net.backward_rec(P, c, draw3, G, False, need_dw, sl)
         else:
             dimg = net.backward_gan(P, c, g.to(F32).contiguous().view(-1), G, False, need_dw, sl)
+        NN.join_side()
         gi = [None, None, None]
         if sl is not None:
             for i in range(sl[0], sl[1]):

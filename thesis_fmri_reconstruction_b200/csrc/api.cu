@@ -148,7 +148,14 @@ static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st)
 }
 static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
 static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)
-static int dispatch_ig_persistent(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
+static int dispatch_ig_persistent(const IgParams& p_in, int BN, int KCH, int classes, cudaStream_t st) {
+    static int legacy = -1;
+    if (legacy < 0) {
+        const char* e = getenv("FMRI_IG_PRODUCER");
+        legacy = (e && atoi(e) == 0) ? 1 : 0;
+    }
+    IgParams p = p_in;
+    p.legacy_producer = legacy;
     if (KCH == 64) {
         switch (BN) {
             case 256: return launch_ig_persistent<256, 64, 4, 1>(p, classes, st);
@@ -523,7 +530,14 @@ static int wave_splits(long long base, long long max_splits) {
     }
     return (int)best;
 }
-static int dispatch_wg(const WgParams& p, int BN, int NCH, cudaStream_t st) {
+static int dispatch_wg(const WgParams& p_in, int BN, int NCH, cudaStream_t st) {
+    static int merge = -1;
+    if (merge < 0) {
+        const char* e = getenv("FMRI_WG_MERGE");
+        merge = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    WgParams p = p_in;
+    p.merge_taps = merge;
     if (NCH == 64 && BN == 128) return p.num_taps > 1 ? launch_wg<128, 64, 2, 2>(p, st) : launch_wg<128, 64, 3, 1>(p, st);
     if (NCH == 64 && BN == 64) return launch_wg<64, 64, 4, 1>(p, st);
     if (NCH == 32 && BN == 32) return p.num_taps % 5 == 0 ? launch_wg<32, 32, 3, 5>(p, st) : launch_wg<32, 32, 4, 1>(p, st);

@@ -57,6 +57,7 @@ struct IgParams {
     // use carry zero weights: 36/25 more MACs, but N = 128 instead of 32 and the activation tile is fetched 9x, not 25x).
     // Column group g = col / 32 -> (ph, pw) = (g >> 1, g & 1) is stored at fine pixel (2y + ph, 2x + pw).
     int merge;              // 0 / 1
+    int legacy_producer;    // persistent kernel: 1 = single-lane TMA producer (A/B switch), 0 = warp-converged elected issue
     int merge_oh, merge_ow; // fine output extent
     long long merge_sy;     // fine row stride (elements)
     // Fused BatchNorm-backward statistics (persistent kernel, bf16 output): when this launch is the data gradient that
@@ -81,7 +82,8 @@ struct IgSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
-    static constexpr int BNP_OFF = STAT_OFF + 2 * BN * 4;       // [4][256] BN-backward coefficients (mean, scale, beta, invstd)
+    static constexpr int STAT_SLOTS = 8;                        // persistent kernel: one private [2][BN] slot per epilogue warp
+    static constexpr int BNP_OFF = STAT_OFF + STAT_SLOTS * 2 * BN * 4;  // [4][256] BN-backward coefficients (mean, scale, beta, invstd)
     static constexpr int TOTAL = BNP_OFF + 4 * 256 * 4 + 1024;  // +1024: manual base alignment
 };
 
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < L::STAT_SLOTS * 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
     float* s_bnp = reinterpret_cast<float*>(smem + L::BNP_OFF);
     if (p.bnb_x) {
         const int nch = p.merge ? 32 : p.n_total;  // channels of the BN layer (<= 256)
@@ -439,7 +441,41 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // The whole warp runs the loop converged (warp-uniform operands, elected issue, see ptx.cuh); tap and channel-chunk
+        // counters are nested loops instead of a per-stage integer division. A stage of the 32-channel K-chunk layers is
+        // only 128-256 tensor-pipe cycles, which the previous single-lane producer (~130 dependent instructions per
+        // stage) could not keep up with.
+        if (p.legacy_producer) {   // single-lane producer (A/B switch FMRI_IG_PRODUCER=0)
+            if (lane == 0) {
+                int it = 0;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
+                    if (!tl.any) continue;
+                    const TapClass& c = p.cls[tl.cls];
+                    int nlive = 0;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) nlive += tl.live[m] ? 1 : 0;
+                    const int nks = c.num_taps * p.num_chunks;
+                    for (int ks = 0; ks < nks; ++ks, ++it) {
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[st], nlive * p.a_bytes + L::B_BYTES);
+                        const int tap = ks / p.num_chunks;
+                        const int ch = ks - tap * p.num_chunks;
+                        const TapDesc td = c.taps[tap];
+                        uint8_t* sa = smem + st * L::STAGE_BYTES;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            if (tl.live[m])
+                                tma_load_4d(sa + m * L::A_SUB, &p.mapA[td.map], &full_bar[st], ch * KCH, tl.x0[m] + td.dx,
+                                            tl.y0[m] + td.dy, tl.n0[m]);
+                        tma_load_2d(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, td.brow + tl.nt * BN);
+                    }
+                }
+            }
+        } else
+        {
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
@@ -448,22 +484,24 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                 int nlive = 0;
 #pragma unroll
                 for (int m = 0; m < MT; ++m) nlive += tl.live[m] ? 1 : 0;
-                const int nks = c.num_taps * p.num_chunks;
-                for (int ks = 0; ks < nks; ++ks, ++it) {
-                    const int st = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[st], nlive * p.a_bytes + L::B_BYTES);
-                    const int tap = ks / p.num_chunks;
-                    const int ch = ks - tap * p.num_chunks;
+                const uint32_t tx_bytes = nlive * p.a_bytes + L::B_BYTES;
+                const int brow0 = tl.nt * BN;
+                for (int tap = 0; tap < c.num_taps; ++tap) {
                     const TapDesc td = c.taps[tap];
-                    uint8_t* sa = smem + st * L::STAGE_BYTES;
+                    const CUtensorMap* mapA = &p.mapA[td.map];
+                    for (int ch = 0; ch < p.num_chunks; ++ch, ++it) {
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        mbar_arrive_expect_tx_elect(&full_bar[st], tx_bytes);
+                        uint8_t* sa = smem + st * L::STAGE_BYTES;
 #pragma unroll
-                    for (int m = 0; m < MT; ++m)
-                        if (tl.live[m])
-                            tma_load_4d(sa + m * L::A_SUB, &p.mapA[td.map], &full_bar[st], ch * KCH, tl.x0[m] + td.dx,
-                                        tl.y0[m] + td.dy, tl.n0[m]);
-                    tma_load_2d(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, td.brow + tl.nt * BN);
+                        for (int m = 0; m < MT; ++m)
+                            if (tl.live[m])
+                                tma_load_4d_elect(sa + m * L::A_SUB, mapA, &full_bar[st], ch * KCH, tl.x0[m] + td.dx,
+                                                  tl.y0[m] + td.dy, tl.n0[m]);
+                        tma_load_2d_elect(sa + L::A_BYTES, &p.mapB, &full_bar[st], ch * KCH, td.brow + brow0);
+                    }
                 }
             }
         }
@@ -530,17 +568,28 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
             const int nt = tl.nt;
             mbar_wait(&tfull[buf], (lt >> 1) & 1);
             tc_fence_after();
+            // BatchNorm statistics: a warp owns the same 32-column chunk in every M sub-tile (and, for the parity-merged
+            // scatter, every chunk folds onto the same 32 channels), so the per-thread values are summed in registers
+            // first and the 62-shuffle transposing reduction + the shared-memory update run once per chunk (once per tile
+            // when merged) instead of once per (chunk, sub-tile). Each warp adds into its own slot: no shared atomics
+            // (an ncu capture of the 32->128 discriminator layer showed 37 % of the epilogue in this path, with
+            // ATOMS.CAST.SPIN retry loops, and the tensor pipe waiting for TMEM at 32 % busy).
+            float sacc[32], qacc[32];
+            bool pending = false;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sacc[j] = qacc[j] = 0.f;
+            float* my_stat = s_stat + (warp - 2) * 2 * BN;
 #pragma unroll 1
-            for (int m = 0; m < MT; ++m) {
-                if (!tl.live[m]) continue;
-                const bool valid_tile = (ni < p.bn) && (tl.n0[m] + ni < p.lim_n) && (tl.y0[m] + yi < c.lim_y) &&
-                                        (tl.x0[m] + xi < c.lim_x);
-                const long long off_tile = c.out_off + (long long)(tl.n0[m] + ni) * p.out_sn +
-                                           (long long)(tl.y0[m] + yi) * p.out_sy + (long long)(tl.x0[m] + xi) * p.out_sx +
-                                           (long long)nt * BN;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int m = 0; m < MT; ++m) {
+                    if (!tl.live[m]) continue;
                     if ((((m * (BN / 32)) + (c0 >> 5)) & 1) != half) continue;
+                    const bool valid_tile = (ni < p.bn) && (tl.n0[m] + ni < p.lim_n) && (tl.y0[m] + yi < c.lim_y) &&
+                                            (tl.x0[m] + xi < c.lim_x);
+                    const long long off_tile = c.out_off + (long long)(tl.n0[m] + ni) * p.out_sn +
+                                               (long long)(tl.y0[m] + yi) * p.out_sy +
+                                               (long long)(tl.x0[m] + xi) * p.out_sx + (long long)nt * BN;
                     bool valid = valid_tile;
                     long long off = off_tile;
                     int stat_col = c0;
@@ -635,12 +684,29 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                                 g2[j] = f[j] * f[j];
                             }
                         }
-                        const float s1 = warp_colsum32(f, lane);
-                        const float s2 = warp_colsum32(g2, lane);
-                        atomicAdd(&s_stat[stat_col + lane], s1);
-                        atomicAdd(&s_stat[BN + stat_col + lane], s2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            sacc[j] += f[j];
+                            qacc[j] += g2[j];
+                        }
+                        pending = true;
                     }
                 }
+                if (do_stats && pending && !p.merge) {   // this chunk's columns are complete for the tile
+                    const float s1 = warp_colsum32(sacc, lane);
+                    const float s2 = warp_colsum32(qacc, lane);
+                    my_stat[c0 + lane] += s1;
+                    my_stat[BN + c0 + lane] += s2;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sacc[j] = qacc[j] = 0.f;
+                    pending = false;
+                }
+            }
+            if (do_stats && pending) {   // merged scatter: every chunk of the tile folded onto channels 0..31
+                const float s1 = warp_colsum32(sacc, lane);
+                const float s2 = warp_colsum32(qacc, lane);
+                my_stat[lane] += s1;
+                my_stat[BN + lane] += s2;
             }
             // accumulators of this buffer are in registers / memory: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
@@ -651,10 +717,16 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                 const int ncol = p.merge ? 32 : BN;
                 const int cbase = p.merge ? 0 : nt * BN;
                 for (int i = etid; i < ncol; i += 32 * IGP_EPI_WARPS) {
-                    atomicAdd(p.stat_sum + cbase + i, (double)s_stat[i]);
-                    atomicAdd(p.stat_sq + cbase + i, (double)s_stat[BN + i]);
-                    s_stat[i] = 0.f;
-                    s_stat[BN + i] = 0.f;
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int w = 0; w < L::STAT_SLOTS; ++w) {
+                        a += s_stat[w * 2 * BN + i];
+                        b += s_stat[w * 2 * BN + BN + i];
+                        s_stat[w * 2 * BN + i] = 0.f;
+                        s_stat[w * 2 * BN + BN + i] = 0.f;
+                    }
+                    atomicAdd(p.stat_sum + cbase + i, (double)a);
+                    atomicAdd(p.stat_sq + cbase + i, (double)b);
                 }
                 named_bar_sync(1, 32 * IGP_EPI_WARPS);
             }
@@ -681,6 +753,7 @@ struct WgParams {
     int m_tiles, n_tiles;
     int splits;
     int rows;  // bw*bh*bn, multiple of 16
+    int merge_taps;  // one N = TG*BN MMA per K step when the kernel supports it (A/B switch)
     float* out;
 };
 
@@ -743,22 +816,22 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-converged producer, elected TMA issue, incremental pixel-tile counters (see igemm_persistent_kernel)
             const int d_chunks_live = (p.m_total - mtile * 128) >= 128 ? 2 : 1;
+            const uint32_t tx_bytes = d_chunks_live * d_chunk_bytes + tg_live * S_CHUNKS * s_chunk_bytes;
+            int tx = pt_begin % p.tiles_x;
+            int ty = (pt_begin / p.tiles_x) % p.tiles_y;
+            int tn = pt_begin / (p.tiles_x * p.tiles_y);
             for (int i = 0; i < npt; ++i) {
                 const int st = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[st], d_chunks_live * d_chunk_bytes + tg_live * S_CHUNKS * s_chunk_bytes);
-                const int pt = pt_begin + i;
-                const int tx = pt % p.tiles_x;
-                const int ty = (pt / p.tiles_x) % p.tiles_y;
-                const int tn = pt / (p.tiles_x * p.tiles_y);
+                mbar_arrive_expect_tx_elect(&full_bar[st], tx_bytes);
                 const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
                 uint8_t* sd = smem + st * L::STAGE_BYTES;
                 for (int cchunk = 0; cchunk < d_chunks_live; ++cchunk)
-                    tma_load_4d(sd + cchunk * d_chunk_bytes, &p.mapD, &full_bar[st], mtile * 128 + cchunk * 64, x0,
-                                y0, n0);
+                    tma_load_4d_elect(sd + cchunk * d_chunk_bytes, &p.mapD, &full_bar[st], mtile * 128 + cchunk * 64, x0,
+                                      y0, n0);
 #pragma unroll
                 for (int tg = 0; tg < TG; ++tg) {
                     if (tg >= tg_live) break;
@@ -766,8 +839,15 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                     uint8_t* ss = sd + L::D_BYTES + tg * L::S_BYTES;
 #pragma unroll
                     for (int cchunk = 0; cchunk < S_CHUNKS; ++cchunk)
-                        tma_load_4d(ss + cchunk * s_chunk_bytes, &p.mapS[t.map], &full_bar[st],
-                                    ntile * BN + cchunk * NCH, x0 + t.dx, y0 + t.dy, n0);
+                        tma_load_4d_elect(ss + cchunk * s_chunk_bytes, &p.mapS[t.map], &full_bar[st],
+                                          ntile * BN + cchunk * NCH, x0 + t.dx, y0 + t.dy, n0);
+                }
+                if (++tx == p.tiles_x) {
+                    tx = 0;
+                    if (++ty == p.tiles_y) {
+                        ty = 0;
+                        ++tn;
+                    }
                 }
             }
         }
@@ -787,6 +867,21 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const uint32_t sd = smem_u32(smem + st * L::STAGE_BYTES);
                 // MN-major: LBO = distance between 64(32)-channel chunks, SBO = 8 pixel rows
                 const uint64_t adesc = umma_smem_desc(sd, d_chunk_bytes, 8 * 128, UMMA_SW128);
+                if constexpr (TG > 1 && BN == NCH && TG * BN <= 256) {
+                    // One channel chunk per tap: the TG shifted tiles sit at a fixed stride in the stage, which is exactly
+                    // an MN-major operand whose N-direction atom stride (LBO) is the tile stride. ONE N = TG*BN MMA per
+                    // K step instead of TG N = BN ones (FMRI_WG_MERGE=0 keeps the per-tap issue for A/B): the 32-channel
+                    // layers were issue-bound at 40 N = 32 MMAs per stage.
+                    if (p.merge_taps) {
+                        const uint32_t idesc_m = umma_idesc_bf16(128, tg_live * BN, true, true);
+                        const uint64_t bdesc = umma_smem_desc(sd + L::D_BYTES, L::S_BYTES, 8 * s_row, s_layout);
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16_elect(tmem_u, adesc + ((k * 16 * 128) >> 4), bdesc + ((k * 16 * s_row) >> 4), idesc_m,
+                                            (i | k) != 0);
+                        umma_commit_elect(&empty_bar[st]);
+                        continue;
+                    }
+                }
 #pragma unroll
                 for (int tg = 0; tg < TG; ++tg) {
                     if (tg >= tg_live) break;

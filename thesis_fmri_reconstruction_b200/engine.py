@@ -51,12 +51,14 @@ class _TrainerBase:
             return
         cur = torch.cuda.current_stream()
         self.comm_stream.wait_stream(cur)
+        NN.side_into(self.comm_stream)   # weight gradients are produced on nets' side stream
         with torch.cuda.stream(self.comm_stream):
             for t in tensors:
                 self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
                 t.record_stream(self.comm_stream)
 
     def _wait_comm(self):
+        NN.join_side()
         if self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
@@ -73,6 +75,7 @@ class _TrainerBase:
         return out
 
     def named_grads(self):
+        NN.join_side()
         out = OrderedDict()
         for b in self.buckets.values():
             for k, v in b.G.items():

@@ -153,14 +153,27 @@ class ConvBlock:
     def backward_raw(self, P, c, draw, G, acc, need_dw, need_dx, fuse=None):
         """Backward from a gradient on the raw (pre-BN) conv output -- the discriminator's feature tap (vae_gan.py:169-173)."""
         w = P[self.prefix + "conv.weight"]
-        if need_dw:
-            if self._ws is None:
-                self._ws = E(max(1, L.conv_wgrad_workspace(c.d)), dtype=torch.uint8)
-            L.conv_wgrad(c.d, c.x, draw, G[self.prefix + "conv.weight"], acc, self._ws)
         dx = None
         if need_dx:
             dx = torch.empty(c.x.shape, dtype=self.adt, device=draw.device)
             L.conv_dgrad(c.d, draw, w, c.pack_d, dx, fuse)
+        if need_dw:
+            if self._ws is None:
+                self._ws = E(max(1, L.conv_wgrad_workspace(c.d)), dtype=torch.uint8)
+            if WGRAD_SIDE_STREAM and self.adt == BF16:
+                # The weight gradient is a leaf of the backward graph: nothing downstream in this sweep reads it. It goes
+                # to a side stream, ordered AFTER this layer's data-gradient kernel (both are tensor-pipe bound and would
+                # only time-share the SMs), so that it runs beside the HBM-bound BatchNorm backward of the layer below.
+                # All weight-gradient launches share the one side stream, so accumulation into G stays ordered;
+                # consumers of G join it (join_side / side_into).
+                side, cur = side_stream(), torch.cuda.current_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    L.conv_wgrad(c.d, c.x, draw, G[self.prefix + "conv.weight"], acc, self._ws)
+                draw.record_stream(side)
+                c.x.record_stream(side)
+            else:
+                L.conv_wgrad(c.d, c.x, draw, G[self.prefix + "conv.weight"], acc, self._ws)
         return dx
 
 
@@ -170,6 +183,29 @@ class ConvBlock:
 import os as _os
 
 FUSE_BN_BWD = _os.environ.get("FMRI_FUSE_BN", "0") == "1"
+
+# Tensor-core weight gradients on a side stream (FMRI_WGRAD_STREAM=0 puts them back on the compute stream).
+WGRAD_SIDE_STREAM = _os.environ.get("FMRI_WGRAD_STREAM", "1") == "1"
+_SIDE = None
+
+
+def side_stream():
+    global _SIDE
+    if _SIDE is None:
+        _SIDE = torch.cuda.Stream()
+    return _SIDE
+
+
+def join_side():
+    """The current stream waits for every weight-gradient launch issued so far (before anything reads a gradient bucket)."""
+    if _SIDE is not None:
+        torch.cuda.current_stream().wait_stream(_SIDE)
+
+
+def side_into(stream):
+    """`stream` (the gradient all-reduce stream) waits for the weight-gradient side stream."""
+    if _SIDE is not None:
+        stream.wait_stream(_SIDE)
 
 
 def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_ready=False):
