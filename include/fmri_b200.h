@@ -64,7 +64,10 @@ int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const float* w, cons
 /* Optional fusion for fmri_conv_dgrad: when dx is the upstream gradient of a BatchNorm(+ReLU) layer whose pre-BN input is
  * `x` (same [N,H,W,Cin] layout and dtype as dx), the call also leaves that layer's backward sums in `sums`:
  * sums[c] = sum g, sums[Cin + c] = sum g * xhat, g = dx masked by the forward ReLU. Pass the same buffer as the `ws` of
- * fmri_bn_backward with sums_ready = 1 (the separate reduction pass, 2 of BN-backward's 5 tensor passes, disappears). */
+ * fmri_bn_backward with sums_ready = 1 (the separate reduction pass, 2 of BN-backward's 5 tensor passes, disappears).
+ * With mean == NULL the struct instead describes a bias+ReLU layer WITHOUT BatchNorm (Discriminator.conv[0],
+ * vae_gan.py:145-147): `x` is that layer's post-ReLU output and the call applies its ReLU backward, dx *= (x > 0), in the
+ * data-gradient epilogue (saves the separate read-dy / write-dx pass of fmri_relu_backward); the other fields are unused. */
 typedef struct {
     const void* x;
     const float *mean, *invstd, *gamma, *beta;

@@ -236,9 +236,14 @@ struct BnbFuse {  // fused BatchNorm-backward statistics of the layer whose dy t
     const void* x;
     const float *mean, *invstd, *gamma, *beta;
     int relu;
+    const void* mask_y = nullptr;  // instead: ReLU-backward mask of a bias+ReLU layer (no BatchNorm), see fmri_bn_fuse
 };
 static void apply_fuse(IgParams& p, const BnbFuse* f) {
     if (!f) return;
+    if (f->mask_y) {
+        p.mask_y = f->mask_y;
+        return;
+    }
     p.bnb_x = f->x; p.bnb_mean = f->mean; p.bnb_invstd = f->invstd; p.bnb_gamma = f->gamma; p.bnb_beta = f->beta;
     p.bnb_relu = f->relu;
 }
@@ -737,7 +742,11 @@ extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const fl
         if (!pack_d) return fail(FMRI_ERR_ARG, "bf16 conv dgrad needs the packed weights");
         BnbFuse bf;
         double *sg = nullptr, *sgx = nullptr;
-        if (fuse) {
+        const bool mask_only = fuse && !fuse->mean;   // ReLU mask of a bias+ReLU layer: dx *= (x > 0)
+        if (mask_only) {
+            bf.x = nullptr; bf.mean = bf.invstd = bf.gamma = bf.beta = nullptr; bf.relu = 1;
+            bf.mask_y = fuse->x;
+        } else if (fuse) {
             if (d->Cin > 256) return fail(FMRI_ERR_UNSUPPORTED, "fused BN-backward statistics need <= 256 channels");
             bf.x = fuse->x; bf.mean = fuse->mean; bf.invstd = fuse->invstd; bf.gamma = fuse->gamma; bf.beta = fuse->beta;
             bf.relu = fuse->relu;
@@ -754,6 +763,16 @@ extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const fl
         else
             return fail(FMRI_ERR_UNSUPPORTED, "stride-1 conv dgrad on the tensor path");
         if (rc) return rc;
+        if (mask_only) {
+            if (!g_last_ig_was_persistent) {  // small launch (one tile per CTA kernel, no fused mask): mask dx in place
+                const long long n = rows_in * d->Cin;
+                relu_bwd_kernel<__nv_bfloat16><<<grid1d((n + 7) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
+                    reinterpret_cast<const __nv_bfloat16*>(fuse->x), reinterpret_cast<const __nv_bfloat16*>(dx),
+                    reinterpret_cast<__nv_bfloat16*>(dx), n);
+                LAUNCH_OK();
+            }
+            return 0;
+        }
         if (fuse && !g_last_ig_was_persistent) {
             // small launch (one tile per CTA kernel): that epilogue produced plain sum(dx) / sum(dx^2); redo the sums properly
             return bn_bwd_sums(fuse->x, FMRI_BF16, dx, FMRI_BF16, rows_in, d->Cin, fuse->mean, fuse->invstd, fuse->gamma,
@@ -764,6 +783,13 @@ extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const fl
     rc = direct_conv<float>(d, true, reinterpret_cast<const float*>(dy), w, nullptr, 0, reinterpret_cast<float*>(dx),
                             S(stream));
     if (rc) return rc;
+    if (fuse && !fuse->mean) {
+        const long long n = rows_in * d->Cin;
+        relu_bwd_kernel<float><<<grid1d((n + 7) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
+            reinterpret_cast<const float*>(fuse->x), reinterpret_cast<const float*>(dx), reinterpret_cast<float*>(dx), n);
+        LAUNCH_OK();
+        return 0;
+    }
     if (fuse)
         return bn_bwd_sums(fuse->x, FMRI_F32, dx, FMRI_F32, rows_in, d->Cin, fuse->mean, fuse->invstd, fuse->gamma, fuse->beta,
                            fuse->relu, fuse->sums, S(stream));
@@ -882,7 +908,10 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
             q.tiles_y = cdiv(OH, tht);
             q.MT = cdiv((long long)tht * q.PW, 128);
             q.PH = tht + hx;
-            q.slab_rows = (q.PH * q.PW + 7) / 8 * 8;
+            // rows per channel-chunk slab. With several chunks a producer warp writes lanes (chunk j, pixel r) -> j * slab +
+            // r * 16 B; a slab size that is a multiple of 128 B puts all chunks of a pixel on the same banks (ncu: 49
+            // shared-memory wavefronts per cp.async instruction instead of 4), so the slab is padded to 32 B mod 128 B.
+            q.slab_rows = (q.PH * q.PW + 7) / 8 * 8 + (chunks > 1 ? 2 : 0);
             // the overshoot of the last sub-tile's windows must stay inside the CTA's allocation (it lands in the weight slab)
             const long long overshoot = ((long long)q.MT * 128 + max_off + 1 - q.slab_rows) * 16;
             if (overshoot > 0 && overshoot > hc_b_bytes(q, BN)) continue;
@@ -947,7 +976,14 @@ static bool hc_build(HcParams& p, HcPackSpec& spec, int N, int H, int W, int chu
 }
 
 template <int BN>
-static int hc_launch(const HcParams& p, cudaStream_t st) {
+static int hc_launch(const HcParams& p_in, cudaStream_t st) {
+    static int issuers = 0;
+    if (!issuers) {
+        const char* e = getenv("FMRI_HC_ISSUERS");
+        issuers = e ? std::max(1, std::min(HC_ISSUERS, atoi(e))) : HC_ISSUERS;
+    }
+    HcParams p = p_in;
+    p.issuers_max = issuers;
     const int smem = hc_smem_bytes(p, BN);
     static int attr_smem = 0;
     if (smem > attr_smem) {

@@ -42,7 +42,8 @@ struct HcParams {
     int pl_ys[4], pl_xs[4];      // input step per halo row / column (1, or 2 for stride-parity planes)
     int pl_yoff[4], pl_xoff[4];  // input y of halo row sy is (oy0 + sy) * ys + yoff, likewise x
     int PW, PH;                  // halo tile width / height (pixels)
-    int slab_rows;               // allocated rows per slab (>= MT*128 + max window offset + 1, multiple of 8)
+    int issuers_max;             // active MMA-issuing warps (<= HC_ISSUERS; A/B switch FMRI_HC_ISSUERS)
+    int slab_rows;               // allocated rows per slab (>= halo rows; 2 mod 8 when there are several channel chunks)
     int num_steps;
     HcStep steps[HC_MAX_STEPS];
     int THt, tiles_y;            // output rows per tile, tiles per image
@@ -78,9 +79,9 @@ __device__ __forceinline__ float hc_act(float v, int act) {
     return v;
 }
 
-constexpr int HC_ISSUERS = 3;                       // MMA-issuing warps
-constexpr int HC_PRODUCERS = 160;                   // warps 3-7: halo producers
-constexpr int HC_THREADS = 32 * HC_ISSUERS + HC_PRODUCERS + 128;  // + 4 epilogue warps (8-11, TMEM lane quarter = warp % 4)
+constexpr int HC_ISSUERS = 5;                       // MMA-issuing warps (one per 128-row sub-tile, MT <= 5)
+constexpr int HC_PRODUCERS = 160;                   // the next 5 warps: halo producers
+constexpr int HC_THREADS = 32 * HC_ISSUERS + HC_PRODUCERS + 128;  // + 4 epilogue warps (TMEM lane quarter = warp % 4)
 
 // shared-memory plan (host and device agree through these helpers)
 __host__ __device__ inline int hc_slab_bytes(const HcParams& p) { return p.slab_rows * 16; }
@@ -111,7 +112,8 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.N * p.tiles_y;
     const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
-    const int issuers = p.MT < HC_ISSUERS ? p.MT : HC_ISSUERS;
+    const int issuers_cap = p.issuers_max < HC_ISSUERS ? p.issuers_max : HC_ISSUERS;
+    const int issuers = p.MT < issuers_cap ? p.MT : issuers_cap;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
@@ -156,12 +158,12 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
                 const uint64_t a_base = umma_smem_desc(smem_u32(sA + sb * a_buf), 0, 128, 0);  // LBO filled in per step
                 const uint32_t d0 = tmem_u + sb * acc_cols;
                 uint32_t acc = 0;  // the first step overwrites the accumulators
-#pragma unroll 1
+#pragma unroll 4
                 for (int s = 0; s < p.num_steps; ++s) {
                     const HcStep stp = p.steps[s];
                     const uint64_t ad = (a_base | (static_cast<uint64_t>(stp.a_lbo & 0x3FFF) << 16)) + stp.a_off;
                     const uint64_t bd = b_base + stp.b_off;
-                    for (int m = warp; m < p.MT; m += HC_ISSUERS)  // this warp's sub-tiles: independent accumulators
+                    for (int m = warp; m < p.MT; m += issuers)  // this warp's sub-tiles: independent accumulators
                         umma_bf16_elect(d0 + m * BN, ad + (uint32_t)(m * 128), bd, idesc, acc);
                     acc = 1;
                 }

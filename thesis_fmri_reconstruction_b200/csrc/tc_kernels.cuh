@@ -57,6 +57,8 @@ struct IgParams {
     // use carry zero weights: 36/25 more MACs, but N = 128 instead of 32 and the activation tile is fetched 9x, not 25x).
     // Column group g = col / 32 -> (ph, pw) = (g >> 1, g & 1) is stored at fine pixel (2y + ph, 2x + pw).
     int merge;              // 0 / 1
+    const void* mask_y;     // persistent kernel, bf16 output: zero the output where this bf16 tensor (same layout) is <= 0
+                            // (ReLU backward of a bias+ReLU layer fused into the data-gradient epilogue)
     int legacy_producer;    // persistent kernel: 1 = single-lane TMA producer (A/B switch), 0 = warp-converged elected issue
     int merge_oh, merge_ow; // fine output extent
     long long merge_sy;     // fine row stride (elements)
@@ -619,6 +621,19 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+                    }
+                    if (p.mask_y && valid) {
+                        const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mask_y) + off + c0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(yp + 8 * j4));
+                            const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (!(__uint_as_float(rr[j] << 16) > 0.f)) f[8 * j4 + 2 * j] = 0.f;
+                                if (!(__uint_as_float(rr[j] & 0xffff0000u) > 0.f)) f[8 * j4 + 2 * j + 1] = 0.f;
+                            }
+                        }
                     }
                     if (p.out_fp32) {
                         if (valid) {

@@ -208,7 +208,10 @@ def conv_dgrad(d, dy, w, pack_d, dx, fuse=None):
     _require_cuda(dy, w, pack_d, dx)
     _note_flops(_conv_flops(d))
     f = None
-    if fuse is not None:
+    if fuse is not None and fuse[1] is None:   # (y,) + Nones: ReLU mask of a bias+ReLU layer, dx *= (y > 0)
+        _require_cuda(fuse[0])
+        f = BnFuse(fuse[0].data_ptr(), None, None, None, None, 1, None)
+    elif fuse is not None:
         x, mean, invstd, gamma, beta, relu, sums = fuse
         _require_cuda(x, mean, invstd, gamma, beta, sums)
         f = BnFuse(x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(relu),

@@ -208,7 +208,7 @@ def side_into(stream):
         stream.wait_stream(_SIDE)
 
 
-def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_ready=False):
+def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_ready=False, relu_mask=None):
     """Backward through a stack of ConvBlocks (last block first). Each block's data-gradient kernel also produces the
     BatchNorm-backward sums of the block below it (fmri_bn_fuse), so that block's BN backward skips its reduction pass.
     lower = (BatchNorm, ctx) of the BN below blocks[0], if any. Returns (dx of blocks[0], sums_ready for `lower`)."""
@@ -220,8 +220,11 @@ def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_read
             fuse = blocks[i - 1].bn.fuse_spec(P, ctxs[i - 1].bn)
         else:
             fuse = lower[0].fuse_spec(P, lower[1]) if lower is not None else None
+        if i == 0 and relu_mask is not None:
+            # the layer below blocks[0] is bias+ReLU without BatchNorm: its ReLU backward rides in this data-gradient epilogue
+            fuse = (relu_mask, None, None, None, None, 1, None)
         dy = blocks[i].backward(P, ctxs[i], dy, G, acc, need_dw, True, ready, fuse)
-        ready = fuse is not None
+        ready = fuse is not None and fuse[1] is not None
     return dy, ready
 
 
@@ -547,8 +550,7 @@ class DiscriminatorNet:
     def _conv0_backward(self, P, c, dy0, G, acc, need_dw, img_slices):
         """ReLU backward of conv[0], its weight/bias gradient, and image gradients for the requested source slices
         (a contiguous range [s0, s1) of sources -> one [ (s1-s0)*Bs, 3, H, W ] fp32 tensor)."""
-        dpre = torch.empty(c.y0.shape, dtype=self.adt, device=dy0.device)
-        L.relu_backward(c.y0, dy0, dpre)
+        dpre = dy0   # conv[0]'s ReLU backward was applied by the data-gradient kernel of block 1 (_backward_chain relu_mask)
         OH, OW = c.hw0
         if need_dw:
             L.edge_in_wgrad(c.d0, c.imgs, c.Bs, dpre, G["conv.0.0.weight"], acc, self._ews, G["conv.0.0.bias"])
@@ -574,14 +576,15 @@ class DiscriminatorNet:
         h, w = c.hw
         dy = E(N, h, w, self.Cl, dtype=self.adt)
         L.nchw_to_nhwc(dflat, dy, N, self.Cl, h, w)
-        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw)
+        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, relu_mask=c.y0)
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
     def backward_rec(self, P, c, draw3, G=None, acc=False, need_dw=False, img_slices=None):
         """Backward of the feature-tap path from a gradient on the raw conv output of block 3 [N,h,w,C] (adt)."""
         fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if FUSE_BN_BWD else None
         dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True, fuse)
-        dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None)
+        dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None,
+                                relu_mask=c.y0)
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
 
