@@ -184,8 +184,10 @@ import os as _os
 
 FUSE_BN_BWD = _os.environ.get("FMRI_FUSE_BN", "0") == "1"
 
-# Tensor-core weight gradients on a side stream (FMRI_WGRAD_STREAM=0 puts them back on the compute stream).
-WGRAD_SIDE_STREAM = _os.environ.get("FMRI_WGRAD_STREAM", "1") == "1"
+# Tensor-core weight gradients on a side stream: OFF by default (FMRI_WGRAD_STREAM=1 enables). Measured on one B200: -0.7 % step
+# time at batch 4096 (the GPU is power-capped, so overlapping tensor-pipe and HBM-bound kernels buys little), but 2x slower at
+# batch 64, where the step is launch-bound and the stream switches / record_stream bookkeeping dominate.
+WGRAD_SIDE_STREAM = _os.environ.get("FMRI_WGRAD_STREAM", "0") == "1"
 _SIDE = None
 
 
