@@ -378,8 +378,9 @@ def run_ours(args):
                     traffic_source="profiles/r1d_ncu_launches_time_dram_B4096.csv (ncu, cold cache)",
                     peak_source=pk["src"], kernel_ms_per_step=d["ms"] / psteps, kernel_launches_per_step=d["calls"] / psteps,
                     kernel_share_of_step=d["ms"] / tot_ms if tot_ms else None,
+                    # whole job: algorithmic FLOPs of the step x samples/s over ALL ranks, against world x the per-GPU peak
                     whole_step_achieved=ALG_MFLOP[args.workload] * 1e6 * value / 1e12,
-                    whole_step_frac=ALG_MFLOP[args.workload] * 1e6 * value / 1e12 / pk["tflops"],
+                    whole_step_frac=ALG_MFLOP[args.workload] * 1e6 * value / 1e12 / (pk["tflops"] * world),
                     top_entry_points_ms_per_step=top)
 
     cpu = None
