@@ -29,11 +29,16 @@ ALG_MFLOP = {"stage1_vaegan": 16966.2, "stage1_waegan": 3352.8, "stage2_cognitiv
              # configs[3] composite: Stage III + teacher-encoder forward + latent-discriminator D-phase
              "stage3_dual": 15624.3,
              # WAE-MMD extension: E + D forward, 2D + (2E - c0) backward; the pairwise kernel adds 9 * B * Z flop / sample
-             "stage1_wae_mmd": 3339.2}
+             "stage1_wae_mmd": 3339.2,
+             # WAE Stage II: fwd E + 2D (one unused teacher reconstruction) + C + 3W, bwd 5W + D (dgrad) + C; Stage III: fwd
+             # E + C + D + 3W, bwd 4W + (2D - fc)   (same conventions as SURVEY.md 8d; W, C terms are < 1 %)
+             "stage2_wae_cognitive": 2871.2, "stage3_wae_cognitive": 2857.4}
 CONFIG_OF = {"stage1_vaegan": "configs[4] (configs[0] at --batch 64)", "stage1_waegan": "configs[1] (reference WAE/GAN step; "
              "the reference has no MMD)", "stage2_cognitive": "configs[2]", "stage3_cognitive": "train_vgan_stage3.py proper",
              "stage3_dual": "configs[3] (composite, SURVEY.md 8d C4)",
-             "stage1_wae_mmd": "configs[1] with the MMD latent loss (extension: no reference code, parity unpinned)"}
+             "stage1_wae_mmd": "configs[1] with the MMD latent loss (extension: no reference code, parity unpinned)",
+             "stage2_wae_cognitive": "train_wae_stage2.py step (SURVEY.md 8a row a15)",
+             "stage3_wae_cognitive": "train_wae_stage3.py step (SURVEY.md 8a row a15)"}
 METRIC = "stage1_vaegan_train_samples_per_sec_64x64"  # BASELINE.json metric; other workloads rename it below
 
 
@@ -43,7 +48,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive", "stage3_dual", "stage1_wae_mmd"])
+    ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive", "stage3_dual", "stage1_wae_mmd",
+                                                                    "stage2_wae_cognitive", "stage3_wae_cognitive"])
     ap.add_argument("--batch", type=int, default=4096, help="GLOBAL batch (BASELINE.json configs[4]: 4096, strong scaling)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -145,6 +151,16 @@ def cpu_reference_steps(workload, B, steps, warmup, threads=None):
             nonlocal P
             out = O.stage1_wae_mmd_step(P, S, x, z_fake, opt=st["opt"], step=st["t"])
             P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
+    elif workload in ("stage2_wae_cognitive", "stage3_wae_cognitive"):
+        stage = 2 if workload == "stage2_wae_cognitive" else 3
+        P, S = O.make_cognitive_wae(O.CFG64, seed=12345, jitter=False)
+        fmri, x = O.synthetic_fmri(B), O.synthetic_images(B)
+        st = dict(opt=None, t=1)
+
+        def one():
+            nonlocal P
+            out = O.cognitive_wae_step(P, S, fmri, x, stage, opt=st["opt"], step=st["t"])
+            P, st["opt"], st["t"] = out["params"], out["adam"], st["t"] + 1
     elif workload == "stage3_dual":
         P, S = O.make_dual_stage3(O.CFG64, seed=12345, jitter=False)
         fmri, x = O.synthetic_fmri(B), O.synthetic_images(B)
@@ -230,7 +246,11 @@ def run_ours(args):
         n1_host = (torch.randn(B, z, generator=gen) * 0.5).pin_memory()
         n2_host = None
     else:
-        if args.workload == "stage3_dual":
+        if args.workload in ("stage2_wae_cognitive", "stage3_wae_cognitive"):
+            P, S = init.init_cognitive_wae(cfg, z, seed=12345)
+            tr = engine.WaeCognitiveStage(P, S, cfg, 2 if args.workload == "stage2_wae_cognitive" else 3, z,
+                                          torch.bfloat16, dist_group=group)
+        elif args.workload == "stage3_dual":
             P, S = init.init_dual_stage3(cfg, z, seed=12345)
             tr = engine.DualCognitiveStage3(P, S, cfg, z, torch.bfloat16, dist_group=group)
         else:
@@ -244,12 +264,16 @@ def run_ours(args):
     x = x_host.cuda(non_blocking=True)
     n1 = n1_host.cuda(non_blocking=True)
     n2 = n2_host.cuda(non_blocking=True) if n2_host is not None else None
-    cog = args.workload in ("stage2_cognitive", "stage3_cognitive", "stage3_dual")
+    cog = args.workload in ("stage2_cognitive", "stage3_cognitive", "stage3_dual", "stage2_wae_cognitive",
+                            "stage3_wae_cognitive")
     dual = args.workload == "stage3_dual"
+    waecog = args.workload in ("stage2_wae_cognitive", "stage3_wae_cognitive")
     fmri = fmri_host.cuda(non_blocking=True) if cog else None
 
     def run_step(xb, a, b2, fb=None):
-        if dual:
+        if waecog:
+            tr.step(fb if fb is not None else fmri, xb)
+        elif dual:
             tr.step(fb if fb is not None else fmri, xb, a, b2)
         elif cog:
             tr.step(fb if fb is not None else fmri, xb, a, eps_t, b2)

@@ -346,3 +346,61 @@ def test_stage1_wae_mmd_variant(adt, B):
     assert max(fwd.values()) < (1e-4 if adt == torch.float32 else 2e-2), fwd
     assert max(gerr.values()) < (5e-3 if adt == torch.float32 else 0.5), gerr
     assert nbt == 1
+
+
+def run_wae_cog_case(stage, B, adt, seed=515):
+    """engine.WaeCognitiveStage against oracle.cognitive_wae_step (pinned to tests/golden/stage{2,3}_cognitive_wae_*)."""
+    P, S = O.make_cognitive_wae(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.cognitive_wae_step(P, S_ref, fmri, image, stage)
+    tr = engine.WaeCognitiveStage(P, S, hp.CFG64, stage, 128, adt)
+    out = tr.step(fmri.cuda(), image.cuda())
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = {k: rel(out[k], ref[k].reshape(out[k].shape)) for k in ("z_fake", "z_real", "x_recon", "d_real", "d_fake", "d_real_g")}
+    for k in ("loss_discriminator_fake", "loss_discriminator_real", "loss_reconstruction", "loss_penalty"):
+        fwd[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    grads = tr.named_grads()
+    trained = ref["trained"] + "."
+    gerr = {}
+    for b in ("discriminator.", trained):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        assert ks
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    # Adam state after one step (m = (1 - beta1) g, v = (1 - beta2) g^2) of the trained bucket
+    bk = tr.buckets[trained]
+    ks = [k for k in ref["grads"] if k.startswith(trained)]
+    adam = {}
+    for i, name in enumerate(("m", "v")):
+        got = torch.cat([bk.state_view(i, k[len(trained):]).reshape(-1) for k in ks])
+        want = torch.cat([ref["adam"][name][k].reshape(-1) for k in ks])
+        adam[name] = rel(got, want)
+    newP = tr.named_parameters()
+    frozen = [p for p in ("encoder.", "decoder.", "teacher_net.encoder.") if p != trained]
+    frozen_same = all(torch.equal(newP[k].cpu(), P[k].float()) for k in newP if any(k.startswith(f) for f in frozen))
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
+    rep = dict(stage=stage, B=B, dtype=str(adt), forward=fwd, grad_bucket=gerr, adam=adam, frozen_same=frozen_same,
+               nbt_ok=nbt_ok, bn_worst=max(berr.items(), key=lambda t: t[1]))
+    with open(f"gpurun_out/parity_wae_stage{stage}_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_wae_cognitive_stage_fp32_exact_path(stage):
+    rep = run_wae_cog_case(stage, 8, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert max(rep["adam"].values()) < 1e-2, rep["adam"]
+    assert rep["frozen_same"] and rep["nbt_ok"] and rep["bn_worst"][1] < 1e-4
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_wae_cognitive_stage_bf16_tensor_path(stage):
+    rep = run_wae_cog_case(stage, 16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["frozen_same"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2

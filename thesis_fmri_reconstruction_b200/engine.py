@@ -571,3 +571,128 @@ class DualCognitiveStage3(VaeGanCognitiveStage):
         lf, lr = self.lsc.tolist()
         d.update(loss_discriminator_fake=lf, loss_discriminator_real=lr)
         return d
+
+
+class WaeCognitiveStage(_TrainerBase):
+    """Stage-II / Stage-III cognitive WAE/GAN trainer (/root/reference/train/train_wae_stage2.py:274-328,
+    train_wae_stage3.py:295-347) over WaeGanCognitive (models/vae_gan.py:532-578) and the Stage-I teacher's visual encoder.
+
+    Both stages: D-phase on z_fake = cognitive_encoder(fmri) vs z_real = teacher.encoder(image) (train-mode BN, frozen
+    weights), L_fake = -10 sum log(d(z_fake) + 1e-3), L_real = -10 sum log(1 - d(z_real) + 1e-3), Adam(5e-4) on the latent
+    discriminator. G-phase: the scripts run the cognitive encoder a second time on unchanged weights (same output: computed
+    once, BN running statistics updated twice), x_recon = decoder(z), d from the UPDATED discriminator,
+    L_rec = nn.MSELoss()(x_recon, image) (a MEAN over all elements), L_pen = -10 mean log(d + 1e-3).
+      stage 2 (:274-328): an extra, unused teacher reconstruction decoder(teacher.encoder(image)) runs first for its BN side
+               effects (:284-285); trains the cognitive encoder on L_rec + L_pen with Adam(1e-3); decoder frozen.
+      stage 3 (:295-347): trains the DECODER on L_rec only (:338-347) with Adam(1e-3); cognitive encoder frozen.
+    Data parallel: the two means are taken over the GLOBAL batch (each rank scales by 1 / (world * B_local)), so the SUM
+    all-reduce of the gradient buckets reproduces the single-process step on the concatenated batch up to per-rank BatchNorm.
+    Parameter keys: encoder.* (CognitiveEncoder), decoder.*, discriminator.main.*, teacher_net.encoder.*."""
+
+    def __init__(self, params, buffers, cfg, stage, z=128, adt=BF16, hp=None, dist_group=None, voxels=None):
+        from .hp import HP_WAE23, NUM_VOXELS
+
+        if stage not in (2, 3):
+            raise L.FmriError("stage must be 2 or 3")
+        self.cfg, self.z, self.adt, self.stage = cfg, z, adt, stage
+        self.hp = dict(HP_WAE23 if hp is None else hp)
+        self.cog = NN.CognitiveEncoderNet(voxels or NUM_VOXELS, z, adt)
+        self.dec = NN.DecoderNet(cfg, z, adt)
+        self.dis = NN.WaeDiscriminatorNet(z, adt)
+        self.tenc = NN.EncoderNet(cfg, z, adt)
+        self.nets = OrderedDict((("encoder.", self.cog), ("decoder.", self.dec), ("discriminator.", self.dis),
+                                 ("teacher_net.encoder.", self.tenc)))
+        dev = torch.device("cuda")
+        self.buckets = OrderedDict()
+        for pre, net in self.nets.items():
+            named = _split(params, pre)
+            diff = set(net.param_names()) ^ set(named)
+            if diff:
+                raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(diff)}")
+            self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to(dev, F32)) for k in named), 2)
+        self.S = OrderedDict((k, v.to(dev).clone()) for k, v in buffers.items())
+        self.Ssub = {pre: _split(self.S, pre) for pre in self.buckets}
+        self.nbt = {}
+        self.sc = Z(16)  # [0..3] = L_fake, L_real (sums), L_rec, L_pen (global means)
+        self.lr = {"encoder.": float(self.hp["lr"]), "decoder.": float(self.hp["lr"]),
+                   "discriminator.": float(self.hp["lr_dis"])}
+        self.t = 0
+        self._ones_buf = None
+        self._setup_dist(dist_group)
+        for pre, net in self.nets.items():
+            net.refresh(self.buckets[pre].P, inplace=True)
+
+    _ones = WaeGanStage1._ones
+    _adam = WaeGanStage1._adam
+
+    def step(self, fmri, image):
+        """fmri [B,V], image [B,3,H,W]: fp32, device resident."""
+        B, z, stage = fmri.shape[0], self.z, self.stage
+        Bg = float(B * self.world)
+        be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
+        bt = self.buckets["teacher_net.encoder."]
+        self.t += 1
+        sc, ones = self.sc, self._ones(B)
+        nb = {pre: {} for pre in self.buckets}
+        # teacher encoder: stage 2 runs it twice on the same input (:284 and the D-phase), stage 3 once
+        yt, _ = self.tenc.forward(bt.P, self.Ssub["teacher_net.encoder."], image, True, 2 if stage == 2 else 1,
+                                  nb["teacher_net.encoder."])
+        z_real = yt[:, :z]
+        if stage == 2:   # unused teacher reconstruction: BatchNorm running statistics of the decoder only
+            self.dec.forward(bd.P, self.Ssub["decoder."], z_real, True, 1, nb["decoder."])
+        # cognitive encoder: D-phase and G-phase forwards see the same weights -> one forward, two BN updates
+        ycat, ce = self.cog.forward(be.P, self.Ssub["encoder."], fmri, True, 2, nb["encoder."])
+        z_fake = ycat[:, :z]
+        # ---------------- discriminator phase
+        p_real, cr = self.dis.forward(bc.P, z_real)
+        p_fake, cf = self.dis.forward(bc.P, z_fake)
+        l, gp = E(2 * B), E(2 * B)
+        L.bce_fwd(p_fake, l[:B], B, True, 10.0)
+        L.bce_fwd(p_real, l[B:], B, False, 10.0)
+        L.vecsum(l[:B], B, 1.0, sc[0:1])
+        L.vecsum(l[B:], B, 1.0, sc[1:2])
+        L.bce_bwd(p_fake, ones, gp[:B], B, True, 10.0)
+        L.bce_bwd(p_real, ones, gp[B:], B, False, 10.0)
+        self.dis.backward(bc.P, cf, gp[:B], bc.G, False, True, False)
+        self.dis.backward(bc.P, cr, gp[B:], bc.G, True, True, False)
+        self._allreduce_async([bc.flat_g])
+        self._wait_comm()
+        self._adam("discriminator.")
+        # ---------------- generator phase
+        x_recon, cd = self.dec.forward(bd.P, self.Ssub["decoder."], z_fake, True, 1, nb["decoder."])
+        p2, c2 = self.dis.forward(bc.P, z_fake)
+        Fimg = image[0].numel()
+        rec = E(B)
+        L.rowsqdiff_fwd(x_recon, image, rec, B, Fimg, 1.0 / (Bg * Fimg))
+        L.vecsum(rec, B, 1.0, sc[2:3])
+        L.bce_fwd(p2, l[:B], B, True, 10.0 / Bg)
+        L.vecsum(l[:B], B, 1.0, sc[3:4])
+        dxr = torch.empty_like(x_recon)
+        L.rowsqdiff_bwd(x_recon, image, ones, dxr, None, B, Fimg, 1.0 / (Bg * Fimg))
+        if stage == 2:
+            L.bce_bwd(p2, ones, gp[:B], B, True, 10.0 / Bg)
+            dz_pen = self.dis.backward(bc.P, c2, gp[:B], None, False, False, True)
+            dz_rec = self.dec.backward(bd.P, cd, 1.0, dxr, 0.0, None, None, False, False, True)
+            dmu = E(B, z)
+            L.axpby_tanh_bwd(1.0, dz_rec, 1.0, dz_pen, None, dmu)
+            dycat = Z(B, 2 * z, dtype=self.adt)
+            L.cast2d(dmu, z, dycat[:, :z], 2 * z, B, z)
+            be.flat_g.zero_()  # l_var receives no gradient (logvar unused): zero slots, Adam leaves it unchanged
+            self.cog.backward(be.P, ce, dycat, be.G, False, True, False)
+            self._allreduce_async([be.flat_g, sc[:8]])
+            self._wait_comm()
+            self._adam("encoder.")
+        else:
+            self.dec.backward(bd.P, cd, 1.0, dxr, 0.0, None, bd.G, False, True, False)
+            self._allreduce_async([bd.flat_g, sc[:8]])
+            self._wait_comm()
+            self._adam("decoder.")
+        for pre, d in nb.items():
+            for k, v in d.items():
+                self.nbt[pre + k] = self.nbt.get(pre + k, 0) + v
+        return dict(z_fake=z_fake, z_real=z_real, x_recon=x_recon, d_real=p_real, d_fake=p_fake, d_real_g=p2)
+
+    def losses(self):
+        s = self.sc.tolist()
+        return dict(loss_discriminator_fake=s[0], loss_discriminator_real=s[1], loss_reconstruction=s[2],
+                    loss_penalty=s[3])

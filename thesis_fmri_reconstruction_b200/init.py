@@ -141,3 +141,16 @@ def init_dual_stage3(cfg, z, seed=12345, input_size=NUM_VOXELS):
     P.update(p)
     S.update(s)
     return P, S
+
+
+def init_cognitive_wae(cfg, z, seed=12345, input_size=NUM_VOXELS):
+    """WaeGanCognitive (models/vae_gan.py:532-546): CognitiveEncoder + Decoder + latent WaeDiscriminator (its own
+    N(0, 0.0099999) init) + the Stage-I teacher's visual Encoder (train_wae_stage2.py:195-203)."""
+    P, S = init_cognitive(cfg, z, seed, True, input_size)
+    P = OrderedDict((k, v) for k, v in P.items() if not k.startswith("discriminator."))
+    S = OrderedDict((k, v) for k, v in S.items() if not k.startswith("discriminator."))
+    gen = torch.Generator().manual_seed(seed + 2)
+    p, s = init_net("discriminator.", wae_discriminator_table(z), gen, 0.0099999)
+    P.update(p)
+    S.update(s)
+    return P, S
