@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (engine.GraphedStep; RMSprop "
+                    "engines on one GPU): for launch-bound batch sizes such as configs[0]'s 64")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for runs under ncu)")
     return ap.parse_args()
 
@@ -282,8 +284,17 @@ def run_ours(args):
         else:
             tr.step(xb, a)
 
+    graphed = None
+    if args.graph:
+        if world > 1 or args.workload not in ("stage1_vaegan", "stage3_cognitive"):
+            raise SystemExit("--graph: one GPU, workloads stage1_vaegan / stage3_cognitive")
+        graphed = engine.GraphedStep(tr, *((fmri, x, n1, eps_t, n2) if cog else (x, n1, n2)))
+
     def step_dev():
-        run_step(x, n1, n2)
+        if graphed is not None:
+            graphed(*((fmri, x, n1, eps_t, n2) if cog else (x, n1, n2)))
+        else:
+            run_step(x, n1, n2)
 
     def sync_all():
         if world > 1:
@@ -311,7 +322,7 @@ def run_ours(args):
         clocks.start()
     lib.launch_count(reset=True)
     ms_total = timed(step_dev, args.steps)
-    launches = lib.launch_count()
+    launches = lib.launch_count() if graphed is None else graphed.launches * args.steps  # replays bypass the host counter
     ck = clocks.stop() if rank == 0 else None
     losses = tr.losses()
     ms_step = ms_total / args.steps
@@ -350,7 +361,10 @@ def run_ours(args):
         torch.cuda.current_stream().wait_event(evs[slot])
         upload(slot ^ 1)  # prefetch the next batch while this step computes (the DataLoader's role in the reference)
         b = bufs[slot]
-        run_step(b[0], b[1], b[2], b[3])
+        if graphed is not None:   # the replay copies the slot into the graph's static input buffers (device to device)
+            graphed(*((b[3], b[0], b[1], eps_t, b[2]) if cog else (b[0], b[1], b[2])))
+        else:
+            run_step(b[0], b[1], b[2], b[3])
         done[slot].record()
         sc_host.copy_(tr.sc, non_blocking=True)  # D2H of the step's loss sums (what train_vgan_stage1.py:391-401 reads)
         state["i"] = i + 1
@@ -377,7 +391,7 @@ def run_ours(args):
         lib.profile_begin()
         psteps = max(1, min(3, args.steps))
         for _ in range(psteps):
-            step_dev()
+            run_step(x, n1, n2)   # eager even under --graph: the per-entry-point events need real launches
         agg = lib.profile_end()
         _nets.WGRAD_SIDE_STREAM = side
         tot_ms = sum(a["ms"] for a in agg.values())

@@ -696,3 +696,51 @@ class WaeCognitiveStage(_TrainerBase):
         s = self.sc.tolist()
         return dict(loss_discriminator_fake=s[0], loss_discriminator_real=s[1], loss_reconstruction=s[2],
                     loss_penalty=s[3])
+
+
+class GraphedStep:
+    """One training step captured in a CUDA graph and replayed: for launch-bound batch sizes (Stage I at batch 64 is 276
+    kernel launches in 5 ms, i.e. the host's launch rate, not the GPU, sets the step time). Works for the trainers whose
+    step has no host-side scalar that changes from step to step (the RMSprop engines: VaeGanStage1 with the device-side gate,
+    VaeGanCognitiveStage(3)); the Adam engines pass the step count for the bias correction as a kernel argument and are not
+    capturable as they stand.
+
+        g = GraphedStep(trainer, x, eps, z_p)      # warms up (3 eager steps), then captures
+        out = g(x, eps, z_p)                       # copies the inputs into the graph's static buffers and replays
+
+    The tensors in `out` live in the graph's memory pool and are overwritten by the next replay."""
+
+    def __init__(self, trainer, *inputs, warmup=3):
+        if not isinstance(trainer, (VaeGanStage1, VaeGanCognitiveStage)) or getattr(trainer, "stage", 3) == 2 or \
+                isinstance(trainer, DualCognitiveStage3):
+            raise L.FmriError("GraphedStep supports VaeGanStage1 and VaeGanCognitiveStage(stage=3)")
+        if isinstance(trainer, VaeGanStage1) and not trainer.gate_on:
+            raise L.FmriError("GraphedStep needs the device-side gate (gate=True)")
+        self.tr = trainer
+        self.static = [t.clone() if t is not None else None for t in inputs]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):   # eager warm-up: lazy workspaces, function attributes, tensor-map cache
+            for _ in range(warmup):
+                trainer.step(*self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        nbt0 = dict(trainer.nbt)
+        n0 = L.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = trainer.step(*self.static)
+        self.launches = L.launch_count() - n0           # kernels per replay (the host counter only saw the capture)
+        self.nbt_inc = {k: v - nbt0.get(k, 0) for k, v in trainer.nbt.items()}
+        trainer.nbt = nbt0                               # the capture itself executed nothing
+
+    def __call__(self, *inputs):
+        for s, t in zip(self.static, inputs):
+            if s is not None and t is not s:
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        nbt = self.tr.nbt
+        for k, v in self.nbt_inc.items():
+            nbt[k] = nbt.get(k, 0) + v
+        return self.out

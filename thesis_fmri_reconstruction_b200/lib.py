@@ -13,7 +13,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfmri_b200.so")
+LIB_PATH = os.environ.get("FMRI_B200_LIB", os.path.join(_HERE, "libfmri_b200.so"))  # override: same-box kernel A/B runs
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fmri_b200.h")
 
 F32, BF16 = 0, 1
