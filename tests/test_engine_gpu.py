@@ -436,7 +436,10 @@ def test_graphed_step_matches_eager():
     assert worst_graph <= max(3 * worst_eager, 1e-5), (worst_graph, worst_eager)
     assert abs(la["loss_encoder"] - lb["loss_encoder"]) <= 1e-3 * abs(la["loss_encoder"])
     assert (la["train_dis"], la["train_dec"]) == (lb["train_dis"], lb["train_dec"])
-    sa, sb = a.named_buffers(), b.named_buffers()
+    sa, sb, sc_ = a.named_buffers(), b.named_buffers(), c.named_buffers()
     assert all(int(sa[k]) == int(sb[k]) for k in sa if not sa[k].dtype.is_floating_point)
-    assert max(rel(sb[k], sa[k].cpu()) for k in sa if sa[k].dtype.is_floating_point) < 1e-3
+    fl = [k for k in sa if sa[k].dtype.is_floating_point]
+    buf_graph = max(rel(sb[k], sa[k].cpu()) for k in fl)
+    buf_eager = max(rel(sc_[k], sa[k].cpu()) for k in fl)
+    assert buf_graph <= max(3 * buf_eager, 1e-5), (buf_graph, buf_eager)
     assert g.launches > 100 and torch.isfinite(out["x_tilde"].float()).all()
