@@ -1062,8 +1062,15 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
     p.N = N; p.PH = PH; p.PW = PW; p.C = C;
     p.PWp = (PW + 4 + 15) / 16 * 16;
     if (p.PWp > 128) return 1;
-    p.bh = std::max(1, std::min(PH, 128 / p.PWp));
-    while (p.bh > 1 && PH % p.bh) --p.bh;
+    // tile rows: every tile re-stages bh + 4 image rows for bh output rows, so taller tiles cut the halo traffic that bounds
+    // this kernel reads (5x at bh = 1, 3x at 2, 2.3x at 3) -- which turned out NOT to be its bound; rows = bh * PWp <= 256 (ones slab). A ragged last tile is fine: TMA
+    // zero-fills the T rows below the image. FMRI_HW_BH caps bh (A/B switch).
+    static int bh_cap = 0;
+    if (!bh_cap) {
+        const char* e = getenv("FMRI_HW_BH");
+        bh_cap = e ? std::max(1, atoi(e)) : 2;  // measured: bh = 2 is 0-3 % faster than 1; bh = 3 needs one CTA per SM and is 10 % slower
+    }
+    p.bh = std::max(1, std::min(std::min(PH, bh_cap), 256 / p.PWp));
     p.tiles_y = cdiv(PH, p.bh);
     p.slab_rows = ((p.bh + 4) * p.PWp + 16 + 7) / 8 * 8;
     p.d_chunk = (p.bh * p.PWp * 128 + 1023) / 1024 * 1024;

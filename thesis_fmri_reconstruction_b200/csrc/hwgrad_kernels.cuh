@@ -24,7 +24,7 @@ struct HwParams {
     CUtensorMap mapT;            // (C, PW, PH, N) box (64, PWp, bh, 1), SWIZZLE_128B
     const __nv_bfloat16* img8;   // [N][IH][IW][8]
     int N, PH, PW, C;
-    int PWp, bh;                 // padded tile width, tile rows; rows = bh*PWp (multiple of 16, <= 128)
+    int PWp, bh;                 // padded tile width, tile rows; rows = bh*PWp (multiple of 16, <= 256: the ones slab)
     int tiles_y;                 // tiles per image
     int slab_rows;               // (bh+4)*PWp + 16, multiple of 8
     float* dwk;                  // [75][C] fp32, +=
@@ -39,15 +39,15 @@ constexpr int HW_MAX_STAGES = 8;
 constexpr int HW_THREADS = 384;
 constexpr int HW_PRODUCERS = 160;   // warps 2-6
 __host__ __device__ inline int hw_stage_bytes(const HwParams& p) { return 2 * p.d_chunk + ((p.slab_rows * 16 + 1023) / 1024) * 1024; }
-__host__ __device__ inline int hw_smem_bytes(const HwParams& p) { return p.stages * hw_stage_bytes(p) + 2048 + 256 + 1024; }
+__host__ __device__ inline int hw_smem_bytes(const HwParams& p) { return p.stages * hw_stage_bytes(p) + 4096 + 256 + 1024; }
 
 __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constant__ HwParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = hw_stage_bytes(p);
     const int HW_STAGES = p.stages;
-    uint8_t* s_ones = smem + HW_STAGES * stage_bytes;                 // [128 rows][16 B] of bf16 1.0
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + 2048);
+    uint8_t* s_ones = smem + HW_STAGES * stage_bytes;                 // [256 rows][16 B] of bf16 1.0 (rows = bh*PWp <= 256)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + 4096);
     uint64_t* full_bar = bars;                    // [STAGES] count = 1 (TMA expect_tx) + producers
     uint64_t* empty_bar = bars + HW_MAX_STAGES;   // [STAGES] count = 2 (one tcgen05.commit per issuing warp)
     uint64_t* tmem_full = bars + 2 * HW_MAX_STAGES;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     // constant smem: ones slab, zeroed second channel chunk of every A stage (rows 64..127 of M are never loaded) and zeroed
     // slab tails, so no uninitialised (possibly NaN) word ever meets a zero of the other operand
-    for (int i = threadIdx.x; i < 2048 / 4; i += HW_THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
+    for (int i = threadIdx.x; i < 4096 / 4; i += HW_THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
     for (int s = 0; s < HW_STAGES; ++s) {
         uint32_t* st = reinterpret_cast<uint32_t*>(smem + s * stage_bytes);
         for (int i = threadIdx.x; i < stage_bytes / 4; i += HW_THREADS) st[i] = 0u;
