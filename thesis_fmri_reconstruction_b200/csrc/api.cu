@@ -129,12 +129,12 @@ static int launch_ig(const IgParams& p, int classes, cudaStream_t st) {
     LAUNCH_OK();
     return 0;
 }
-template <int BN, int KCH, int STAGES, int MT>
-static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
+template <int BN, int KCH, int STAGES, int MT, bool EXTRA>
+static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t st) {
     using L = IgSmem<BN, KCH, STAGES, MT>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(igemm_persistent_kernel<BN, KCH, STAGES, MT>,
+        CUDA_OK(cudaFuncSetAttribute(igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_done = true;
     }
@@ -142,9 +142,15 @@ static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st)
     const long long tiles = m_groups * p.n_tiles * classes;
     const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), (227 * 1024) / L::TOTAL));
     const int grid = (int)std::min<long long>(tiles, 148LL * per_sm);
-    igemm_persistent_kernel<BN, KCH, STAGES, MT><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
+    igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
     LAUNCH_OK();
     return 0;
+}
+template <int BN, int KCH, int STAGES, int MT>
+static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
+    // the fused BN-backward-sums / ReLU-mask epilogues live in their own instantiation (register pressure of the common case)
+    if (p.bnb_x || p.mask_y) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true>(p, classes, st);
+    return launch_ig_persistent_x<BN, KCH, STAGES, MT, false>(p, classes, st);
 }
 static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
 static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)

@@ -390,7 +390,9 @@ __device__ __forceinline__ IgTile ig_decode_tile(const IgParams& p, int t, int m
 constexpr int IGP_EPI_WARPS = 8;
 constexpr int IGP_THREADS = 64 + 32 * IGP_EPI_WARPS;
 
-template <int BN, int KCH, int STAGES, int MT>
+// EXTRA = the rarely used epilogue paths (fused BatchNorm-backward sums, fused ReLU mask) are compiled in; the plain
+// instantiation keeps them out of the register allocation of the common case (the epilogue sits at the 168-register cap).
+template <int BN, int KCH, int STAGES, int MT, bool EXTRA = false>
 __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
     using L = IgSmem<BN, KCH, STAGES, MT>;
     extern __shared__ uint8_t smem_raw[];
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     for (int i = threadIdx.x; i < L::STAT_SLOTS * 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
     float* s_bnp = reinterpret_cast<float*>(smem + L::BNP_OFF);
-    if (p.bnb_x) {
+    if (EXTRA && p.bnb_x) {
         const int nch = p.merge ? 32 : p.n_total;  // channels of the BN layer (<= 256)
         for (int i = threadIdx.x; i < nch; i += blockDim.x) {
             const float is = p.bnb_invstd[i];
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
                     }
-                    if (p.mask_y && valid) {
+                    if (EXTRA && p.mask_y && valid) {
                         const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mask_y) + off + c0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     }
                     if (do_stats) {
                         float g2[32];
-                        if (p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
+                        if (EXTRA && p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
                             const int cb = (p.merge ? 0 : nt * BN) + stat_col;
                             float xv[32];
                             if (valid) {
