@@ -434,7 +434,10 @@ def run_ours(args):
                     config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})",
                                 global_batch=args.batch, per_gpu_batch=B, parallelism=f"dp{world}",
                                 l2="inputs larger than L2: per-step activation working set ~%.1f GB per GPU >> 126 MB" % act_gb,
-                                optimizer="3 x RMSprop (fused multi-tensor), equilibrium gate on device"),
+                                cuda_graph=bool(args.graph),
+                                optimizer=("Adam (fused multi-tensor), betas (0.5, 0.999)" if "wae" in args.workload else
+                                           "RMSprop (fused multi-tensor), equilibrium gate on device")
+                                          + (" + Adam on the latent discriminator" if args.workload == "stage3_dual" else "")),
                     e2e=dict(value=e2e_value, unit="samples/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h), gpu_launches=launches, clocks=ck, roofline=roof, cpu_baseline=cpu,
                     losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in losses.items()})
