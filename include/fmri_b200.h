@@ -73,6 +73,8 @@ typedef struct {
     const float *mean, *invstd, *gamma, *beta;
     int relu;
     double* sums; /* >= 3 * Cin doubles (fmri_bn_backward workspace) */
+    const unsigned* mask_bits; /* mean == NULL mode, optional: fmri_relu_bitmask() of `x` (32-channel tensors): the epilogue
+                                * then reads 4 bytes per pixel instead of 64 */
 } fmri_bn_fuse;
 /* dx = conv data-gradient of dy (replaces aten::convolution_backward input-grad); fuse nullable */
 int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const float* w, const void* pack_d, void* dx,
@@ -147,6 +149,9 @@ int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long ro
 int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, int train,
                      float* dgamma, float* dbeta, int accumulate, double* ws, int sums_ready, void* stream);
+/* bits[pixel] bit j = (y[pixel][j] > 0): ReLU mask of a channels-last bf16 tensor with exactly 32 channels, 4 B per pixel
+ * (consumed by fmri_conv_dgrad through fmri_bn_fuse.mask_bits) */
+int fmri_relu_bitmask(const void* y, int dtype, long long pixels, int C, unsigned* bits, void* stream);
 int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream);
 int fmri_colsum(const void* x, int dtype, long long rows, int C, float* out /* += */, void* stream);
 

@@ -149,7 +149,7 @@ static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t s
 template <int BN, int KCH, int STAGES, int MT>
 static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
     // the fused BN-backward-sums / ReLU-mask epilogues live in their own instantiation (register pressure of the common case)
-    if (p.bnb_x || p.mask_y) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true>(p, classes, st);
+    if (p.bnb_x || p.mask_y || p.mask_bits) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true>(p, classes, st);
     return launch_ig_persistent_x<BN, KCH, STAGES, MT, false>(p, classes, st);
 }
 static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
@@ -243,11 +243,13 @@ struct BnbFuse {  // fused BatchNorm-backward statistics of the layer whose dy t
     const float *mean, *invstd, *gamma, *beta;
     int relu;
     const void* mask_y = nullptr;  // instead: ReLU-backward mask of a bias+ReLU layer (no BatchNorm), see fmri_bn_fuse
+    const unsigned* mask_bits = nullptr;  // the same mask as a bit word per 32-channel pixel (fmri_relu_bitmask)
 };
 static void apply_fuse(IgParams& p, const BnbFuse* f) {
     if (!f) return;
     if (f->mask_y) {
         p.mask_y = f->mask_y;
+        p.mask_bits = f->mask_bits;
         return;
     }
     p.bnb_x = f->x; p.bnb_mean = f->mean; p.bnb_invstd = f->invstd; p.bnb_gamma = f->gamma; p.bnb_beta = f->beta;
@@ -752,6 +754,7 @@ extern "C" int fmri_conv_dgrad(const fmri_conv_desc* d, const void* dy, const fl
         if (mask_only) {
             bf.x = nullptr; bf.mean = bf.invstd = bf.gamma = bf.beta = nullptr; bf.relu = 1;
             bf.mask_y = fuse->x;
+            bf.mask_bits = d->Cin == 32 ? fuse->mask_bits : nullptr;   // bit words describe 32-channel pixels only
         } else if (fuse) {
             if (d->Cin > 256) return fail(FMRI_ERR_UNSUPPORTED, "fused BN-backward statistics need <= 256 channels");
             bf.x = fuse->x; bf.mean = fuse->mean; bf.invstd = fuse->invstd; bf.gamma = fuse->gamma; bf.beta = fuse->beta;
@@ -1592,6 +1595,12 @@ extern "C" int fmri_relu_backward(const void* y, const void* dy, void* dx, int d
     else
         relu_bwd_kernel<float><<<grid1d((n + 7) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
             reinterpret_cast<const float*>(y), reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(dx), n);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_relu_bitmask(const void* y, int dtype, long long pixels, int C, unsigned* bits, void* stream) {
+    if (dtype != FMRI_BF16 || C != 32) return fail(FMRI_ERR_UNSUPPORTED, "relu_bitmask: bf16 tensors with 32 channels only");
+    relu_bitmask32_kernel<<<cdiv(pixels, 256), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(y), bits, pixels);
     LAUNCH_OK();
     return 0;
 }

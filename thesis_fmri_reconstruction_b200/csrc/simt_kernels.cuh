@@ -1010,6 +1010,28 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sum_g, const dou
     }
 }
 
+// bits[pixel] bit j = (y[pixel][j] > 0) for a channels-last bf16 tensor with exactly 32 channels: the ReLU mask of
+// Discriminator.conv[0] in 4 B per pixel instead of 64 B, read back by the data-gradient epilogue that applies the ReLU backward
+__global__ void relu_bitmask32_kernel(const __nv_bfloat16* __restrict__ y, uint32_t* __restrict__ bits, long long pixels) {
+    // one warp per 32 pixels: lane l loads 16-byte pieces so that the warp reads 2 KB contiguous; ballot-free formulation:
+    // thread t of the block handles pixel p = block*256 + t with four 16-byte loads
+    const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= pixels) return;
+    const uint4* src = reinterpret_cast<const uint4*>(y + px * 32);
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 r = __ldg(src + q);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (__uint_as_float(w[j] << 16) > 0.f) m |= 1u << (q * 8 + 2 * j);
+            if (__uint_as_float(w[j] & 0xffff0000u) > 0.f) m |= 1u << (q * 8 + 2 * j + 1);
+        }
+    }
+    bits[px] = m;
+}
+
 // relu backward on its own (bias+ReLU layers: discriminator conv0, WAE discriminator MLP): dx = dy * (y > 0);
 // 8 elements per thread when n % 8 == 0 (always, for channels-last tensors with C % 8 == 0)
 template <typename T>

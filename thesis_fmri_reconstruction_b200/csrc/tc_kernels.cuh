@@ -59,6 +59,7 @@ struct IgParams {
     int merge;              // 0 / 1
     const void* mask_y;     // persistent kernel, bf16 output: zero the output where this bf16 tensor (same layout) is <= 0
                             // (ReLU backward of a bias+ReLU layer fused into the data-gradient epilogue)
+    const uint32_t* mask_bits;  // same mask as 1 bit per element of a 32-channel pixel (bits[(offset) >> 5]); preferred over mask_y
     int legacy_producer;    // persistent kernel: 1 = single-lane TMA producer (A/B switch), 0 = warp-converged elected issue
     int merge_oh, merge_ow; // fine output extent
     long long merge_sy;     // fine row stride (elements)
@@ -604,6 +605,9 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                         off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
                         stat_col = 0;
                     }
+                    // fused ReLU mask as a bit word (one 4-byte load, issued before the TMEM load so its latency hides)
+                    uint32_t mbits = 0xffffffffu;
+                    if (EXTRA && p.mask_bits && valid) mbits = __ldg(p.mask_bits + ((off + c0) >> 5));
                     uint32_t v[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + m * BN + c0, v);
                     tmem_ld_wait();
@@ -624,7 +628,11 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
                     }
-                    if (EXTRA && p.mask_y && valid) {
+                    if (EXTRA && p.mask_bits) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (!((mbits >> j) & 1u)) f[j] = 0.f;
+                    } else if (EXTRA && p.mask_y && valid) {
                         const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mask_y) + off + c0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {

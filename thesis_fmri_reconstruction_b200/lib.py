@@ -34,7 +34,7 @@ class EdgeDesc(C.Structure):
 
 class BnFuse(C.Structure):
     _fields_ = [("x", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p),
-                ("beta", C.c_void_p), ("relu", C.c_int), ("sums", C.c_void_p)]
+                ("beta", C.c_void_p), ("relu", C.c_int), ("sums", C.c_void_p), ("mask_bits", C.c_void_p)]
 
 
 class LinearDesc(C.Structure):
@@ -208,14 +208,15 @@ def conv_dgrad(d, dy, w, pack_d, dx, fuse=None):
     _require_cuda(dy, w, pack_d, dx)
     _note_flops(_conv_flops(d))
     f = None
-    if fuse is not None and fuse[1] is None:   # (y,) + Nones: ReLU mask of a bias+ReLU layer, dx *= (y > 0)
-        _require_cuda(fuse[0])
-        f = BnFuse(fuse[0].data_ptr(), None, None, None, None, 1, None)
+    if fuse is not None and fuse[1] is None:   # (y, None x5 [, bits]): ReLU mask of a bias+ReLU layer, dx *= (y > 0)
+        bits = fuse[7] if len(fuse) > 7 else None
+        _require_cuda(fuse[0], bits)
+        f = BnFuse(fuse[0].data_ptr(), None, None, None, None, 1, None, bits.data_ptr() if bits is not None else None)
     elif fuse is not None:
         x, mean, invstd, gamma, beta, relu, sums = fuse
         _require_cuda(x, mean, invstd, gamma, beta, sums)
         f = BnFuse(x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(relu),
-                   sums.data_ptr())
+                   sums.data_ptr(), None)
     _check(load().fmri_conv_dgrad(C.byref(d), ptr(dy), ptr(w), ptr(pack_d), ptr(dx), C.byref(f) if f else None, stream()))
 
 
@@ -391,6 +392,11 @@ def mmd_imq_bwd(zq, zp, B, Z, sigma2, lam, dzq, accumulate=False):
     _require_cuda(zq, zp, dzq, contiguous=False)
     _check(load().fmri_mmd_imq_bwd(ptr(zq), zq.stride(0), ptr(zp), zp.stride(0), B, Z, _f(sigma2), _f(lam), ptr(dzq),
                                    dzq.stride(0), int(accumulate), stream()))
+
+
+def relu_bitmask(y, pixels, Cc, bits):
+    _require_cuda(y, bits)
+    _check(load().fmri_relu_bitmask(ptr(y), dt(y), _ll(pixels), Cc, ptr(bits), stream()))
 
 
 def head_sigmoid_fwd(x, w, bias, p, rows, F):

@@ -224,7 +224,8 @@ def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_read
             fuse = lower[0].fuse_spec(P, lower[1]) if lower is not None else None
         if i == 0 and relu_mask is not None:
             # the layer below blocks[0] is bias+ReLU without BatchNorm: its ReLU backward rides in this data-gradient epilogue
-            fuse = (relu_mask, None, None, None, None, 1, None)
+            y_below, bits = relu_mask if isinstance(relu_mask, tuple) else (relu_mask, None)
+            fuse = (y_below, None, None, None, None, 1, None, bits)
         dy = blocks[i].backward(P, ctxs[i], dy, G, acc, need_dw, True, ready, fuse)
         ready = fuse is not None and fuse[1] is not None
     return dy, ready
@@ -532,12 +533,16 @@ class DiscriminatorNet:
         OH, OW = (H - 1) // self.stride0 + 1, (W - 1) // self.stride0 + 1
         y0 = E(N, OH, OW, self.C0, dtype=self.adt)
         L.edge_in_fprop(d0, imgs, Bs, P["conv.0.0.weight"], P["conv.0.0.bias"], L.ACT_RELU, y0, self._ews)
+        mask0 = None
+        if train and self.adt == BF16 and self.C0 == 32:   # ReLU mask as 4 B per pixel for the fused backward (see _backward_chain)
+            mask0 = torch.empty(N * OH * OW, dtype=torch.int32, device=y0.device)
+            L.relu_bitmask(y0, N * OH * OW, self.C0, mask0)
         cs, y, h, w = [], y0, OH, OW
         for b in self.blocks:
             y, c = b.forward(P, S, y, N, h, w, train, n_updates, nbt)
             cs.append(c)
             h, w = c.OH, c.OW
-        ctx = Ctx(imgs=list(imgs), Bs=Bs, N=N, d0=d0, y0=y0, blocks=cs, hw=(h, w), H=H, W=W, hw0=(OH, OW))
+        ctx = Ctx(imgs=list(imgs), Bs=Bs, N=N, d0=d0, y0=y0, mask0=mask0, blocks=cs, hw=(h, w), H=H, W=W, hw0=(OH, OW))
         raw3 = cs[-1].bn.raw
         p = None
         if head:
@@ -578,7 +583,7 @@ class DiscriminatorNet:
         h, w = c.hw
         dy = E(N, h, w, self.Cl, dtype=self.adt)
         L.nchw_to_nhwc(dflat, dy, N, self.Cl, h, w)
-        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, relu_mask=c.y0)
+        dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, relu_mask=(c.y0, c.mask0))
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
     def backward_rec(self, P, c, draw3, G=None, acc=False, need_dw=False, img_slices=None):
@@ -586,7 +591,7 @@ class DiscriminatorNet:
         fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if FUSE_BN_BWD else None
         dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True, fuse)
         dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None,
-                                relu_mask=c.y0)
+                                relu_mask=(c.y0, c.mask0))
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
 
