@@ -29,7 +29,10 @@ from oracle import vaegan as O  # noqa: E402
 from oracle.golden_util import summarize, summarize_dict  # noqa: E402
 
 
-def import_reference():
+def import_reference(cfg=None):
+    """cfg: an oracle architecture dict (O.CFG64 default, O.CFG100 = the reference's ACTIVE block,
+    configs/models_config.py:13-21); its values are written into the imported reference config module."""
+    cfg = cfg or O.CFG64
     saved = list(sys.path)
     sys.path[:] = [REF] + [q for q in sys.path if os.path.abspath(q or ".") != ROOT]  # reference's models/ is a namespace pkg
     for m in [k for k in sys.modules if k == "configs" or k.startswith("configs.") or k == "models"
@@ -38,9 +41,12 @@ def import_reference():
     import configs.models_config as mc
 
     assert mc.__file__.startswith(REF), mc.__file__
-    mc.image_size = 64; mc.fc_input = 8; mc.fc_output = 1024; mc.fc_input_gan = 8; mc.fc_output_gan = 512
-    mc.stride_gan = 1; mc.latent_dim = 128; mc.output_pad_dec = [True, True, True]
-    mc.decoder_channels = [256, 128, 32, 3]
+    for k in ("image_size", "fc_input", "fc_output", "fc_input_gan", "fc_output_gan", "stride_gan", "latent_dim"):
+        setattr(mc, k, cfg[k])
+    mc.output_pad_dec = list(cfg["output_pad_dec"])
+    mc.encoder_channels = list(cfg["encoder_channels"])
+    mc.decoder_channels = list(cfg["decoder_channels"])
+    mc.discrim_channels = list(cfg["discrim_channels"])
     import models.vae_gan as ref
 
     assert ref.__file__.startswith(REF), ref.__file__
@@ -72,12 +78,14 @@ def buffers_of(model):
     return {k: v for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
 
 
-def golden_stage1_vaegan(ref, B, seed):
+def golden_stage1_vaegan(ref, B, seed, cfg=None):
+    cfg = cfg or O.CFG64
+    z = cfg["latent_dim"]
     torch.manual_seed(0)
-    P, S = O.make_vaegan(O.CFG64, seed=seed, dtype=torch.float64)
-    x = O.synthetic_images(B, seed=seed).double()
-    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
-    model = ref.VaeGan(device="cpu", z_size=128).double()
+    P, S = O.make_vaegan(cfg, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, size=cfg["image_size"], seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, z, seed=seed)]
+    model = ref.VaeGan(device="cpu", z_size=z).double()
     load(model, P, S)
     model.train()
     model.reparameterize = lambda mu, logvar: eps * torch.exp(0.5 * logvar) + mu  # models/vae_gan.py:266-269, eps injected
@@ -128,6 +136,12 @@ def golden_stage1_vaegan(ref, B, seed):
     fx.update(summarize_dict(grads, "grad:"))
     fx.update(summarize_dict(delta, "delta:"))
     fx.update(summarize_dict({k: v for k, v in buffers_of(model).items()}, "buf:"))
+    # inference path (inference/inference_gan.py drives VaeGan.forward in eval mode, models/vae_gan.py:288-292): updated
+    # weights, the running statistics the step just produced, eval-mode BatchNorm, the same injected eps
+    model.eval()
+    with torch.no_grad():
+        x_eval = model(x)
+    fx["eval_x_tilde"] = summarize(x_eval)
     return fx
 
 
@@ -362,6 +376,10 @@ def main():
         np.savez_compressed(os.path.join(out, f"stage1_vaegan_B{B}_s{seed}.npz"), **golden_stage1_vaegan(ref, B, seed))
         np.savez_compressed(os.path.join(out, f"stage1_waegan_B{B}_s{seed}.npz"), **golden_stage1_waegan(ref, B, seed))
         print("wrote goldens for", B, seed)
+    ref100 = import_reference(O.CFG100)   # the reference's active 100x100 / latent-512 block: odd 13/25/50-pixel grids
+    np.savez_compressed(os.path.join(out, "stage1_vaegan100_B2_s99.npz"), **golden_stage1_vaegan(ref100, 2, 99, O.CFG100))
+    print("wrote the 100x100 golden")
+    ref = import_reference()
     for stage in (2, 3):
         np.savez_compressed(os.path.join(out, f"stage{stage}_cognitive_B4_s4711.npz"), **golden_cognitive(ref, 4, 4711, stage))
         print("wrote cognitive golden for stage", stage)

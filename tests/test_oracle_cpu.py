@@ -29,14 +29,18 @@ def _cases(kind):
     return fs
 
 
-@pytest.mark.parametrize("path", _cases("stage1_vaegan"))
+@pytest.mark.parametrize("path", _cases("stage1_vaegan") + _cases("stage1_vaegan100"))
 def test_stage1_vaegan_fp64_matches_reference(path):
+    """64x64 fixtures and the reference's ACTIVE 100x100 / latent-512 configuration (configs/models_config.py:13-21:
+    stride-2 first discriminator conv, output_padding [False, True, True], odd 13/25/50-pixel feature maps)."""
     g = np.load(path)
     B, seed = int(g["B"]), int(g["seed"])
-    P, S = O.make_vaegan(O.CFG64, seed=seed, dtype=torch.float64)
-    x = O.synthetic_images(B, seed=seed).double()
-    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
-    out = O.stage1_vaegan_step(P, S, x, eps, z_p)
+    cfg = O.CFG100 if "vaegan100" in os.path.basename(path) else O.CFG64
+    z = cfg["latent_dim"]
+    P, S = O.make_vaegan(cfg, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, size=cfg["image_size"], seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, z, seed=seed)]
+    out = O.stage1_vaegan_step(P, S, x, eps, z_p, cfg=cfg)
     assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
     for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder", "loss_decoder",
               "loss_discriminator"):
@@ -55,6 +59,12 @@ def test_stage1_vaegan_fp64_matches_reference(path):
         elif k.startswith("buf:"):
             assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
     assert n == len(P)
+    # inference path (VaeGan.forward in eval mode, models/vae_gan.py:288-295): updated weights, the running statistics the
+    # step produced, eval-mode BatchNorm
+    P2 = out["params"]
+    mu_e, lv_e = O.encoder(P2, S, x, cfg, train=False)
+    x_e = O.decoder(P2, S, O.reparameterize(mu_e, lv_e, eps), cfg, train=False)
+    assert summary_error(summarize(x_e), g["eval_x_tilde"]) < 1e-9
 
 
 @pytest.mark.parametrize("path", _cases("stage1_vaegan")[:1])
