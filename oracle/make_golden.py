@@ -78,7 +78,7 @@ def buffers_of(model):
     return {k: v for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
 
 
-def golden_stage1_vaegan(ref, B, seed, cfg=None):
+def golden_stage1_vaegan(ref, B, seed, cfg=None, mode="vae-gan", beta=1.0):
     cfg = cfg or O.CFG64
     z = cfg["latent_dim"]
     torch.manual_seed(0)
@@ -97,7 +97,11 @@ def golden_stage1_vaegan(ref, B, seed, cfg=None):
     dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]          # :333-335
     dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]          # :337-339
     nle, kld, mse, bo, bp, bs = ref.VaeGan.loss(x, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)  # :342
-    loss_encoder = torch.sum(kld) + torch.sum(mse)                                # :369
+    if mode == "beta-vae":
+        kld_weight = 1 / B                                                        # :361
+        loss_encoder = torch.sum(kld) * beta * kld_weight + torch.sum(mse)        # :362
+    else:
+        loss_encoder = torch.sum(kld) + torch.sum(mse)                            # :369
     loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)            # :370
     loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator  # :372
     train_dis, train_dec = True, True
@@ -376,6 +380,9 @@ def main():
         np.savez_compressed(os.path.join(out, f"stage1_vaegan_B{B}_s{seed}.npz"), **golden_stage1_vaegan(ref, B, seed))
         np.savez_compressed(os.path.join(out, f"stage1_waegan_B{B}_s{seed}.npz"), **golden_stage1_waegan(ref, B, seed))
         print("wrote goldens for", B, seed)
+    np.savez_compressed(os.path.join(out, "stage1_betavae_B4_s2024.npz"),
+                        **golden_stage1_vaegan(ref, 4, 2024, mode="beta-vae", beta=4.0), beta=np.array(4.0))
+    print("wrote the beta-vae golden")
     ref100 = import_reference(O.CFG100)   # the reference's active 100x100 / latent-512 block: odd 13/25/50-pixel grids
     np.savez_compressed(os.path.join(out, "stage1_vaegan100_B2_s99.npz"), **golden_stage1_vaegan(ref100, 2, 99, O.CFG100))
     print("wrote the 100x100 golden")

@@ -298,7 +298,8 @@ def _leaf(P):
 
 
 # ---------------------------------------------------------------------------------------------------- Stage I VAE/GAN
-def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update=True, force_gate=None):
+def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update=True, force_gate=None, mode="vae-gan",
+                       beta=1.0):
     """One iteration of train/train_vgan_stage1.py:316-432 (mode 'vae-gan').
 
     Forward = VaeGan.forward train branch (models/vae_gan.py:276-286): encoder, reparameterize, decoder(z), decoder(z_p),
@@ -319,7 +320,10 @@ def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update
     dl_o, dl_p = disc_layer[:B], disc_layer[B:-B]
     dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
     nle, kl, mse, bce_o, bce_p, bce_s = vaegan_loss(x, x_tilde, dl_o, dl_p, dc_o, dc_p, dc_s, mu, logvar)
-    loss_enc = kl.sum() + mse.sum()                                            # :369
+    if mode not in ("vae-gan", "beta-vae"):
+        raise ValueError("oracle restates the 'vae-gan' (:368-372) and 'beta-vae' (:359-365) loss mixes")
+    kl_w = beta / B if mode == "beta-vae" else 1.0                             # :360-362 (kld_weight = 1 / batch_size)
+    loss_enc = kl.sum() * kl_w + mse.sum()                                     # :369 / :362
     loss_dis = bce_o.sum() + bce_p.sum() + bce_s.sum()                         # :370
     loss_dec = (hp["lambda_mse"] * mse).sum() - (1.0 - hp["lambda_mse"]) * loss_dis  # :372
     train_dis, train_dec = gate(bce_o.mean().item(), bce_p.mean().item(), hp["margin"], hp["equilibrium"])

@@ -443,3 +443,24 @@ def test_graphed_step_matches_eager():
     buf_eager = max(rel(sc_[k], sa[k].cpu()) for k in fl)
     assert buf_graph <= max(3 * buf_eager, 1e-5), (buf_graph, buf_eager)
     assert g.launches > 100 and torch.isfinite(out["x_tilde"].float()).all()
+
+
+def test_stage1_beta_vae_mode_fp32():
+    """The 'beta-vae' loss mix of train/train_vgan_stage1.py:359-365 (KL weighted by beta / batch_size): engine vs the oracle
+    (pinned to the reference by tests/golden/stage1_betavae_*). Only the encoder bucket and loss_encoder differ from 'vae-gan'."""
+    B, seed, beta = 8, 77, 4.0
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    P64 = {k: v.double() for k, v in P.items()}
+    ref = O.stage1_vaegan_step(P64, {k: v.clone().double() if v.dtype.is_floating_point else v.clone() for k, v in S.items()},
+                               x.double(), eps.double(), z_p.double(), update=False, mode="beta-vae", beta=beta)
+    tr = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32, mode="beta-vae", beta=beta)
+    tr.forward_backward(x.cuda(), eps.cuda(), z_p.cuda())
+    torch.cuda.synchronize()
+    lo, grads = tr.losses(), tr.named_grads()
+    ks = [k for k in ref["grads"] if k.startswith("encoder.")]
+    gerr = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    lerr = abs(lo["loss_encoder"] - ref["loss_encoder"].item()) / abs(ref["loss_encoder"].item())
+    print("beta-vae encoder bucket", gerr, "loss_encoder", lerr)
+    assert gerr < 5e-3 and lerr < 1e-4

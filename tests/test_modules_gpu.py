@@ -367,3 +367,71 @@ def test_cognitive_wae_script_sequence(stage, dtype, B):
             assert rel(sd[k], v) < ftol, k
         else:
             assert int(sd[k]) == int(v), k
+
+
+def test_pixel_nle_modes_and_dcgan_module_fp32():
+    """The 'vae' and 'dcgan' loss mixes of train/train_vgan_stage1.py:374-388 (pixel NLE instead of the feature MSE) and the
+    DCGan container (models/vae_gan.py:581-622, the same generated batch passed as `predicted` AND `sampled`) through the
+    module path, against the oracle's functional nets differentiated by torch autograd on the CPU (fp32 exact path)."""
+    from models.vae_gan import DCGan, VaeGan
+
+    B, seed = 8, 53
+    lam = O.HP_VGAN["lambda_mse"]
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    # ---------------- oracle side
+    W = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    Sr = {k: v.clone() for k, v in S.items()}
+    mu, lv = O.encoder(W, Sr, x, O.CFG64)
+    xt = O.decoder(W, Sr, O.reparameterize(mu, lv, eps), O.CFG64)
+    xp = O.decoder(W, Sr, z_p, O.CFG64)
+    dl = O.discriminator(W, Sr, x, xt, xp, O.CFG64, "REC")
+    dc = O.discriminator(W, Sr, x, xt, xp, O.CFG64, "GAN")
+    nle, kl, mse, bo, bp, bs = O.vaegan_loss(x, xt, dl[:B], dl[B:-B], dc[:B], dc[B:-B], dc[-B:], mu, lv)
+    ref_enc = kl.sum() + nle.sum()                                      # 'vae' :384 / 'dcgan' :378
+    ref_dis = bo.sum() + bs.sum()                                       # :379 / :385
+    ref_dec = (lam * nle).sum() - (1.0 - lam) * ref_dis                 # 'dcgan' :380
+    names = {b: [k for k in W if k.startswith(b + ".")] for b in ("encoder", "decoder", "discriminator")}
+    g_ref = {}
+    for b, loss in (("encoder", ref_enc), ("decoder", ref_dec), ("discriminator", ref_dis)):
+        g_ref.update(zip(names[b], torch.autograd.grad(loss, [W[n] for n in names[b]], retain_graph=True)))
+    # ---------------- module side
+    with compute(torch.float32):
+        model = build_vaegan(P, S)
+        model.train()
+        eps_d = eps.cuda()
+        model.reparameterize = lambda m, l: ag.reparameterize(m, l, eps_d)
+        with patched_randn(z_p):
+            x_tilde, disc_class, disc_layer, mus, lvs = model(x)
+        n2, k2, m2, o2, p2, s2 = VaeGan.loss(x.cuda(), x_tilde, disc_layer[:B], disc_layer[B:-B], disc_layer[-B:],
+                                             disc_class[:B], disc_class[B:-B], disc_class[-B:], mus, lvs)
+        loss_enc = torch.sum(k2) + torch.sum(n2)
+        loss_dis = torch.sum(o2) + torch.sum(s2)
+        loss_dec = torch.sum(lam * n2) - (1.0 - lam) * loss_dis
+        g = {}
+        for b, loss in (("encoder", loss_enc), ("decoder", loss_dec), ("discriminator", loss_dis)):
+            ps = dict(getattr(model, b).named_parameters())
+            gs = torch.autograd.grad(loss, list(ps.values()), retain_graph=True)
+            g.update({b + "." + k: v for k, v in zip(ps, gs)})
+        fwd = dict(nle=rel(n2, nle), loss_enc=rel(loss_enc, ref_enc), loss_dec=rel(loss_dec, ref_dec), loss_dis=rel(loss_dis, ref_dis))
+        gerr = {b: bucket_err(g, g_ref, b + ".") for b in names}
+        print("pixel-NLE modes: forward", fwd, "grad buckets", gerr)
+        assert max(fwd.values()) < 1e-4, fwd
+        assert max(gerr.values()) < 5e-3, gerr
+        # ---------------- DCGan container: decoder(z_p) judged against the real batch, generated batch in two slots
+        dcg = DCGan(device="cuda", decoder=model.decoder, discriminator=model.discriminator, z_size=128)
+        dcg.train()
+        with patched_randn(z_p):
+            out = dcg(x)
+        torch.cuda.synchronize()
+    # train-mode outputs depend on the weights and the batch statistics only (not on the running statistics)
+    Sr2 = {k: v.clone() for k, v in S.items()}
+    xg = O.decoder(P, Sr2, z_p, O.CFG64)
+    dl2 = O.discriminator(P, Sr2, x, xg, xg, O.CFG64, "REC")
+    dc2 = O.discriminator(P, Sr2, x, xg, xg, O.CFG64, "GAN")
+    gt_x, x_gen, d_class, d_layer = out                                  # models/vae_gan.py:613
+    assert torch.equal(gt_x.cpu(), x)
+    errs = dict(x_tilde=rel(x_gen, xg), disc_class=rel(d_class, dc2), disc_layer=rel(d_layer, dl2))
+    print("DCGan forward", errs)
+    assert max(errs.values()) < 1e-4, errs

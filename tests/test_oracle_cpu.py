@@ -29,7 +29,7 @@ def _cases(kind):
     return fs
 
 
-@pytest.mark.parametrize("path", _cases("stage1_vaegan") + _cases("stage1_vaegan100"))
+@pytest.mark.parametrize("path", _cases("stage1_vaegan") + _cases("stage1_vaegan100") + _cases("stage1_betavae"))
 def test_stage1_vaegan_fp64_matches_reference(path):
     """64x64 fixtures and the reference's ACTIVE 100x100 / latent-512 configuration (configs/models_config.py:13-21:
     stride-2 first discriminator conv, output_padding [False, True, True], odd 13/25/50-pixel feature maps)."""
@@ -40,7 +40,8 @@ def test_stage1_vaegan_fp64_matches_reference(path):
     P, S = O.make_vaegan(cfg, seed=seed, dtype=torch.float64)
     x = O.synthetic_images(B, size=cfg["image_size"], seed=seed).double()
     eps, z_p = [t.double() for t in O.synthetic_noise(B, z, seed=seed)]
-    out = O.stage1_vaegan_step(P, S, x, eps, z_p, cfg=cfg)
+    kw = dict(mode="beta-vae", beta=float(g["beta"])) if "betavae" in os.path.basename(path) else {}   # :359-365
+    out = O.stage1_vaegan_step(P, S, x, eps, z_p, cfg=cfg, **kw)
     assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
     for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder", "loss_decoder",
               "loss_discriminator"):

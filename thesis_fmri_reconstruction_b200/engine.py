@@ -90,9 +90,13 @@ class _TrainerBase:
 class VaeGanStage1(_TrainerBase):
     """Stage-I VAE/GAN trainer (image -> image): visual Encoder, Decoder, Discriminator, three RMSprop optimizers."""
 
-    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None, gate=True):
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None, gate=True, mode="vae-gan", beta=1.0):
         from .hp import HP_VGAN
 
+        if mode not in ("vae-gan", "beta-vae"):
+            # train_vgan_stage1.py:359-388 also has 'dcgan' and 'vae' (pixel-NLE mixes): served by the module path
+            raise L.FmriError("the fused Stage-I step implements the 'vae-gan' and 'beta-vae' loss mixes")
+        self.mode, self.beta, self._klw = mode, float(beta), 1.0
         self.cfg, self.z, self.adt = cfg, z, adt
         self.hp = dict(HP_VGAN if hp is None else hp)
         self.gate_on = gate
@@ -175,7 +179,9 @@ class VaeGanStage1(_TrainerBase):
         # (4) encoder: g_enc = d [sum kl + sum mse] / d encoder; the mse term flows x_tilde -> decoder (data gradient) -> z
         dz = self.dec.backward(bd.P, cd1, 1.0, dimg_mse, 0.0, None, None, False, False, True)
         dycat = E(B, 2 * z, dtype=self.adt)
-        L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=1.0)
+        # 'beta-vae' (:359-362): loss_encoder = beta / batch_size * sum kl + sum mse, the batch being the global one here
+        self._klw = self.beta / float(B * self.world) if self.mode == "beta-vae" else 1.0
+        L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=self._klw)
         self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
         self._allreduce_async([be.flat_g])
         return dict(x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, z=zz, kl=kl, mse=mse,
@@ -212,7 +218,8 @@ class VaeGanStage1(_TrainerBase):
         s = self.sc.tolist()
         lam = float(self.hp["lambda_mse"])
         loss_dis = s[0] + s[1] + s[2]
-        return dict(loss_encoder=s[3] + s[4], loss_discriminator=loss_dis, loss_decoder=lam * s[4] - (1 - lam) * loss_dis,
+        return dict(loss_encoder=getattr(self, "_klw", 1.0) * s[3] + s[4], loss_discriminator=loss_dis,
+                    loss_decoder=lam * s[4] - (1 - lam) * loss_dis,
                     nle=s[5], bce_o=s[0], bce_p=s[1], bce_s=s[2], kl=s[3], mse=s[4], train_dis=s[8] != 0,
                     train_dec=s[9] != 0)
 
