@@ -371,6 +371,100 @@ def golden_cognitive_wae(ref, B, seed, stage):
     return fx
 
 
+def golden_dual_stage1(ref, B, seed, lam=1.0):
+    """train/wae_vgan_stage1.py:282-441 (mode 'vae-gan') with the reference's VaeGan + a second WaeGan's latent discriminator,
+    under THIS torch (>= 2: zero_grad() leaves None gradients, so the decoder step of :417 is a no-op -- asserted below). As in
+    golden_stage1_vaegan the three VAE/GAN optimizer steps are applied after the three backward sweeps (torch-1.4 order)."""
+    torch.manual_seed(0)
+    P, S = O.make_dual_stage1(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    z_fake = (O.synthetic_noise(B, 128, seed=seed + 7)[0] * 0.5).double()      # :385 torch.randn_like(z_real) * 0.5
+    model = ref.VaeGan(device="cpu", z_size=128).double()
+    load(model, {k: v for k, v in P.items() if not k.startswith("latent_")}, S)
+    model_wae = ref.WaeGan(device="cpu", z_size=128).double()                  # :200; only its discriminator is used
+    model_wae.discriminator.load_state_dict({k[len("latent_discriminator."):]: v for k, v in P.items()
+                                             if k.startswith("latent_discriminator.")}, strict=True)
+    model.train()
+    model.reparameterize = lambda mu, logvar: eps * torch.exp(0.5 * logvar) + mu
+    hp = O.HP_VGAN
+    mk = lambda ps: torch.optim.RMSprop(ps, lr=hp["lr"], alpha=0.9, eps=1e-8, weight_decay=0, momentum=0, centered=False)
+    opts = {b: mk(getattr(model, b).parameters()) for b in ("encoder", "decoder", "discriminator")}   # :238-246
+    opt_wae = mk(model_wae.discriminator.parameters())                                                  # :248
+
+    def freeze(m, on):
+        for p in m.parameters():
+            p.requires_grad = not on
+
+    with patched_randn(z_p):
+        x_tilde, disc_class, disc_layer, mus, lv = model(x)                       # :290
+    dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]
+    dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
+    nle, kld, mse, bo, bp, bs = ref.VaeGan.loss(x, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)  # :302
+    loss_encoder = torch.sum(kld) + torch.sum(mse)                                # :329
+    loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+    loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator
+    train_dis, train_dec = True, True                                             # :356-364
+    if torch.mean(bo).item() < hp["equilibrium"] - hp["margin"] or torch.mean(bp).item() < hp["equilibrium"] - hp["margin"]:
+        train_dis = False
+    if torch.mean(bo).item() > hp["equilibrium"] + hp["margin"] or torch.mean(bp).item() > hp["equilibrium"] + hp["margin"]:
+        train_dec = False
+    if train_dec is False and train_dis is False:
+        train_dis = True
+        train_dec = True
+    model.zero_grad()                                                             # :368
+    model.encoder.zero_grad(); model.decoder.zero_grad(); model.discriminator.zero_grad()   # :372-374
+    # ---------- latent discriminator (:380-397)
+    freeze(model.decoder, True); freeze(model.encoder, True); freeze(model_wae.discriminator, False)
+    z_real, _ = model.encoder(x)
+    d_real = model_wae.discriminator(z_real)
+    d_fake = model_wae.discriminator(z_fake)
+    loss_fake = -lam * torch.sum(torch.log(d_fake + 1e-3))
+    loss_real = -lam * torch.sum(torch.log(1 - d_real + 1e-3))
+    loss_fake.backward(retain_graph=True)
+    loss_real.backward(retain_graph=True)
+    grads = {"latent_discriminator." + k: p.grad.clone() for k, p in model_wae.discriminator.named_parameters()}
+    opt_wae.step()
+    # ---------- penalty (:401-417)
+    freeze(model.encoder, False); freeze(model.decoder, False); freeze(model_wae.discriminator, True)
+    z_real2, _ = model.encoder(x)
+    x_recon = model.decoder(z_real2)                                              # unused (BatchNorm side effects)
+    d_real2 = model_wae.discriminator(z_real2)
+    loss_penalty = -lam * torch.sum(torch.log(d_real2 + 1e-3))
+    loss_penalty.backward()
+    assert all(p.grad is None for p in model.decoder.parameters()), "torch >= 2 semantics expected (SURVEY 8a a16)"
+    opts["decoder"].step()                                                        # :417 -- a no-op here
+    # ---------- the three VAE/GAN sweeps (:419-441), steps deferred
+    loss_encoder.backward(retain_graph=True)                                      # accumulates onto the penalty gradient
+    grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters() if p.grad is not None})
+    model.zero_grad()
+    loss_decoder.backward(retain_graph=True)
+    grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+    model.discriminator.zero_grad()
+    loss_discriminator.backward()
+    grads.update({"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()})
+    for b, on in (("encoder", True), ("decoder", train_dec), ("discriminator", train_dis)):
+        if not on:
+            continue
+        for k, p in getattr(model, b).named_parameters():
+            p.grad = grads[b + "." + k].clone() if (b + "." + k) in grads else None
+        opts[b].step()
+    newP = {k: v.detach() for k, v in model.named_parameters()}
+    newP.update({"latent_discriminator." + k: v.detach() for k, v in model_wae.discriminator.named_parameters()})
+    delta = {k: newP[k] - P[k] for k in P}
+    fx = dict(B=np.array(B), seed=np.array(seed), lam=np.array(lam), train_dis=np.array(train_dis), train_dec=np.array(train_dec),
+              mu=mus.detach().numpy(), kl=kld.detach().numpy(), mse=mse.detach().numpy(),
+              loss_encoder=loss_encoder.detach().numpy(), loss_decoder=loss_decoder.detach().numpy(),
+              loss_discriminator=loss_discriminator.detach().numpy(), d_real=d_real.detach().numpy(),
+              d_fake=d_fake.detach().numpy(), d_real_g=d_real2.detach().numpy(),
+              loss_discriminator_fake=loss_fake.detach().numpy(), loss_discriminator_real=loss_real.detach().numpy(),
+              loss_penalty=loss_penalty.detach().numpy(), x_tilde=summarize(x_tilde))
+    fx.update(summarize_dict(grads, "grad:"))
+    fx.update(summarize_dict(delta, "delta:"))
+    fx.update(summarize_dict({k: v for k, v in buffers_of(model).items()}, "buf:"))
+    return fx
+
+
 def main():
     ref = import_reference()
     out = os.path.join(ROOT, "tests", "golden")
@@ -383,6 +477,8 @@ def main():
     np.savez_compressed(os.path.join(out, "stage1_betavae_B4_s2024.npz"),
                         **golden_stage1_vaegan(ref, 4, 2024, mode="beta-vae", beta=4.0), beta=np.array(4.0))
     print("wrote the beta-vae golden")
+    np.savez_compressed(os.path.join(out, "stage1_dual_B4_s606.npz"), **golden_dual_stage1(ref, 4, 606))
+    print("wrote the dual WAE/GAN Stage-I golden")
     ref100 = import_reference(O.CFG100)   # the reference's active 100x100 / latent-512 block: odd 13/25/50-pixel grids
     np.savez_compressed(os.path.join(out, "stage1_vaegan100_B2_s99.npz"), **golden_stage1_vaegan(ref100, 2, 99, O.CFG100))
     print("wrote the 100x100 golden")

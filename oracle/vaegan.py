@@ -632,3 +632,67 @@ def dual_stage3_step(P, S, fmri, image, eps, z_p, cfg=CFG64, hp=HP_VGAN, hp_lat=
                loss_discriminator_fake=loss_fake.detach(), loss_discriminator_real=loss_real.detach(),
                adam=dict(m=newm, v=newv))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- dual WAE/GAN Stage I
+def make_dual_stage1(cfg=CFG64, z=None, seed=12345, dtype=torch.float32, jitter=True):
+    """VaeGan (encoder / decoder / image discriminator) plus the latent WaeDiscriminator of a second WaeGan model
+    (train/wae_vgan_stage1.py:196-200) under the prefix latent_discriminator.*."""
+    z = z or cfg["latent_dim"]
+    P, S = make_vaegan(cfg, z, seed, dtype, jitter)
+    p, s = make_net("latent_discriminator.", wae_discriminator_spec(z), seed + 50, dtype, jitter, wae_disc=True)
+    P.update(p)
+    S.update(s)
+    return P, S
+
+
+def dual_stage1_step(P, S, x, eps, z_p, z_fake, cfg=CFG64, hp=HP_VGAN, lam=1.0, sq=None, force_gate=None):
+    """One iteration of train/wae_vgan_stage1.py:282-441 (mode 'vae-gan'), TORCH >= 2 SEMANTICS (SURVEY.md 8a row a16:
+    `zero_grad()` sets gradients to None, so the decoder `step()` of :417 on never-written gradients is a no-op; torch 1.4
+    decayed the decoder's square_avg there).
+
+      (1) the Stage-I VAE/GAN forward and losses (:290-366, = stage1_vaegan_step);
+      (2) latent discriminator phase (:380-397): z_real = encoder(x) (second encoder forward, frozen), L_fake = -lam sum
+          log(d(z_fake) + 1e-3), L_real = -lam sum log(1 - d(z_real) + 1e-3), RMSprop on the latent discriminator;
+      (3) penalty (:401-417): third encoder forward, an unused decoder(z_real) forward (BatchNorm side effects), d from the
+          UPDATED latent discriminator, L_pen = -lam sum log(d + 1e-3) backpropagated into the encoder only;
+      (4) the three Stage-I updates (:419-441) with the penalty gradient ACCUMULATED into the encoder's (:421).
+    All gradients are taken at the pre-step weights of encoder / decoder / image discriminator (torch-1.4 order)."""
+    vg = {k: v for k, v in P.items() if not k.startswith("latent_discriminator.")}
+    out = stage1_vaegan_step(vg, S, x, eps, z_p, cfg, hp, update=False, force_gate=force_gate)
+    lat = bucket(P, "latent_discriminator.")
+    sq = sq if sq is not None else OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    W = _leaf(P)
+    # (2)
+    z_real, _ = encoder(W, S, x, cfg)
+    d_real = wae_discriminator(W, z_real.detach(), pre="latent_discriminator.")
+    d_fake = wae_discriminator(W, z_fake, pre="latent_discriminator.")
+    loss_fake = -lam * torch.sum(torch.log(d_fake + 1e-3))
+    loss_real = -lam * torch.sum(torch.log(1 - d_real + 1e-3))
+    g_lat = torch.autograd.grad(loss_fake + loss_real, [W[n] for n in lat])
+    newP, newsq = OrderedDict(P), OrderedDict(sq)
+    for n, g in zip(lat, g_lat):
+        out["grads"][n] = g.detach()
+        newP[n], newsq[n] = rmsprop_update(P[n], g.detach(), sq[n], hp["lr"], hp["alpha"], hp["eps"])
+    # (3)
+    W2 = _leaf(newP)
+    z2, _ = encoder(W2, S, x, cfg)
+    decoder(W2, S, z2, cfg)                                   # x_recon: unused, BatchNorm running statistics only
+    d2 = wae_discriminator(W2, z2, pre="latent_discriminator.")
+    loss_pen = -lam * torch.sum(torch.log(d2 + 1e-3))
+    enc = bucket(P, "encoder.")
+    g_pen = torch.autograd.grad(loss_pen, [W2[n] for n in enc], allow_unused=True)
+    # (4)
+    for n, g in zip(enc, g_pen):
+        if g is not None:
+            out["grads"][n] = out["grads"][n] + g.detach()
+    active = dict(encoder=True, decoder=out["train_dec"], discriminator=out["train_dis"])
+    for b in ("encoder", "decoder", "discriminator"):
+        if not active[b]:
+            continue
+        for n in bucket(P, b + "."):
+            newP[n], newsq[n] = rmsprop_update(P[n], out["grads"][n], sq[n], hp["lr"], hp["alpha"], hp["eps"])
+    out.update(z_real=z_real.detach(), d_real=d_real.detach(), d_fake=d_fake.detach(), d_real_g=d2.detach(),
+               loss_discriminator_fake=loss_fake.detach(), loss_discriminator_real=loss_real.detach(),
+               loss_penalty=loss_pen.detach(), params=newP, square_avg=newsq)
+    return out

@@ -232,3 +232,30 @@ def test_mmd_statement_known_answers():
     same, shifted = mmd_imq(a, b, 1.0).item(), mmd_imq(a + 2.0, b, 1.0).item()
     assert abs(same) < 0.05 and shifted > 0.5
     assert abs(mmd_imq(a, b, 1.0).item() - mmd_imq(b, a, 1.0).item()) < 1e-12   # symmetric in its arguments
+
+
+def test_dual_stage1_fp64_matches_reference():
+    """train/wae_vgan_stage1.py:282-441, torch >= 2 semantics: the reference's VaeGan + a second
+    WaeGan's latent discriminator run by oracle/make_golden.py against oracle.dual_stage1_step."""
+    g = np.load(os.path.join(GOLD, "stage1_dual_B4_s606.npz"))
+    B, seed, lam = int(g["B"]), int(g["seed"]), float(g["lam"])
+    P, S = O.make_dual_stage1(O.CFG64, seed=seed, dtype=torch.float64)
+    x = O.synthetic_images(B, seed=seed).double()
+    eps, z_p = [t.double() for t in O.synthetic_noise(B, 128, seed=seed)]
+    z_fake = (O.synthetic_noise(B, 128, seed=seed + 7)[0] * 0.5).double()
+    out = O.dual_stage1_step(P, S, x, eps, z_p, z_fake, lam=lam)
+    assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
+    for k in ("mu", "kl", "mse", "loss_encoder", "loss_decoder", "loss_discriminator", "d_real", "d_fake", "d_real_g",
+              "loss_discriminator_fake", "loss_discriminator_real", "loss_penalty"):
+        assert _rel(out[k].numpy(), g[k]) < 1e-9, k
+    assert summary_error(summarize(out["x_tilde"]), g["x_tilde"]) < 1e-9
+    n = 0
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert summary_error(summarize(out["grads"][k[5:]]), g[k]) < 1e-8, k
+            n += 1
+        elif k.startswith("delta:"):
+            assert summary_error(summarize(out["params"][k[6:]] - P[k[6:]]), g[k]) < 1e-6, k
+        elif k.startswith("buf:"):
+            assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
+    assert n == len(P)     # every parameter of the four networks receives a gradient (l_var through the KL term)
