@@ -464,3 +464,58 @@ def test_stage1_beta_vae_mode_fp32():
     lerr = abs(lo["loss_encoder"] - ref["loss_encoder"].item()) / abs(ref["loss_encoder"].item())
     print("beta-vae encoder bucket", gerr, "loss_encoder", lerr)
     assert gerr < 5e-3 and lerr < 1e-4
+
+
+def run_dual1_case(B, adt, seed=808):
+    """engine.DualWaeVaeGanStage1 (train/wae_vgan_stage1.py:282-441, row a16) against oracle.dual_stage1_step, which is pinned
+    to the reference by tests/golden/stage1_dual_*."""
+    P, S = O.make_dual_stage1(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed)
+    eps, z_p = O.synthetic_noise(B, 128, seed=seed)
+    z_fake = O.synthetic_noise(B, 128, seed=seed + 7)[0] * 0.5
+    S_ref = {k: v.clone() for k, v in S.items()}
+    ref = O.dual_stage1_step(P, S_ref, x, eps, z_p, z_fake)
+    tr = engine.DualWaeVaeGanStage1(P, S, hp.CFG64, 128, adt)
+    out = tr.forward_backward(x.cuda(), eps.cuda(), z_p.cuda(), z_fake.cuda())
+    grads = {k: v.clone() for k, v in tr.named_grads().items()}
+    tr.update(B)
+    torch.cuda.synchronize()
+    lo = tr.losses()
+    fwd = dict(mu=rel(out["mu"], ref["mu"]), x_tilde=rel(out["x_tilde"], ref["x_tilde"]),
+               disc_class=rel(out["disc_class"], ref["disc_class"].reshape(-1)), z_real=rel(out["z_real"], ref["z_real"]),
+               d_real=rel(out["d_real"], ref["d_real"].reshape(-1)), d_fake=rel(out["d_fake"], ref["d_fake"].reshape(-1)),
+               d_real_g=rel(out["d_real_g"], ref["d_real_g"].reshape(-1)))
+    for k in ("loss_encoder", "loss_decoder", "loss_discriminator", "loss_discriminator_fake", "loss_discriminator_real",
+              "loss_penalty"):
+        fwd[k] = abs(lo[k] - ref[k].item()) / abs(ref[k].item())
+    gerr = {}
+    for b in ("encoder.", "decoder.", "discriminator.", "latent_discriminator."):
+        ks = [k for k in ref["grads"] if k.startswith(b)]
+        gerr[b] = rel(torch.cat([grads[k].reshape(-1) for k in ks]), torch.cat([ref["grads"][k].reshape(-1) for k in ks]))
+    newP = tr.named_parameters()
+    ks = [k for k in P if k.startswith("latent_discriminator.")]
+    lat_delta = rel(torch.cat([(newP[k].cpu() - P[k]).reshape(-1) for k in ks]),
+                    torch.cat([(ref["params"][k] - P[k]).reshape(-1) for k in ks]))
+    gate_ok = (lo["train_dis"], lo["train_dec"]) == (ref["train_dis"], ref["train_dec"])
+    berr = {k: rel(v, S_ref[k]) for k, v in tr.named_buffers().items() if v.dtype.is_floating_point}
+    nbt_ok = all(int(v) == int(S_ref[k]) for k, v in tr.named_buffers().items() if not v.dtype.is_floating_point)
+    rep = dict(B=B, dtype=str(adt), forward=fwd, grad_bucket=gerr, latent_delta=lat_delta, gate_ok=gate_ok, nbt_ok=nbt_ok,
+               bn_worst=max(berr.items(), key=lambda t: t[1]))
+    with open(f"gpurun_out/parity_stage1_dual_B{B}_{str(adt).split('.')[-1]}.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+    return rep
+
+
+def test_dual_stage1_fp32_exact_path():
+    rep = run_dual1_case(8, torch.float32)
+    assert max(rep["forward"].values()) < 1e-4, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 5e-3, rep["grad_bucket"]
+    assert rep["latent_delta"] < 1e-2 and rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 1e-4
+
+
+def test_dual_stage1_bf16_tensor_path():
+    rep = run_dual1_case(16, torch.bfloat16)
+    assert max(rep["forward"].values()) < 2e-2, rep["forward"]
+    assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
+    assert rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2

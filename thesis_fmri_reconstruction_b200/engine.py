@@ -134,7 +134,7 @@ class VaeGanStage1(_TrainerBase):
         nbe, nbd, nbc = {}, {}, {}
         sc = self.sc
         # ------------------------------------------------------------------ forward (vae_gan.py:276-286)
-        ycat, ce = self.enc.forward(be.P, Se, x, True, 1, nbe)
+        ycat, ce = self.enc.forward(be.P, Se, x, True, self._enc_bn_updates, nbe)
         mu, lv = ycat[:, :z], ycat[:, z:]
         zz, kl = E(B, z), E(B)
         L.reparam_kl_fwd(mu, lv, eps, zz, kl, B, z, ld=2 * z)
@@ -182,10 +182,16 @@ class VaeGanStage1(_TrainerBase):
         # 'beta-vae' (:359-362): loss_encoder = beta / batch_size * sum kl + sum mse, the batch being the global one here
         self._klw = self.beta / float(B * self.world) if self.mode == "beta-vae" else 1.0
         L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=self._klw)
+        self._before_encoder_backward(mu, dycat)   # hook: DualWaeVaeGanStage1 adds the latent penalty gradient here
         self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
         self._allreduce_async([be.flat_g])
         return dict(x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, z=zz, kl=kl, mse=mse,
                     bce=bce, nle=nle)
+
+    _enc_bn_updates = 1
+
+    def _before_encoder_backward(self, mu, dycat):
+        pass
 
     def _ones(self, n):
         if getattr(self, "_ones_buf", None) is None or self._ones_buf.numel() < n:
@@ -751,3 +757,89 @@ class GraphedStep:
         for k, v in self.nbt_inc.items():
             nbt[k] = nbt.get(k, 0) + v
         return self.out
+
+
+class DualWaeVaeGanStage1(VaeGanStage1):
+    """The dual WAE/GAN Stage-I step of /root/reference/train/wae_vgan_stage1.py:282-441 (mode 'vae-gan'),
+    TORCH >= 2 SEMANTICS (the decoder `step()` of :417 acts on None gradients and is a no-op): the Stage-I VAE/GAN step plus a
+    latent WaeDiscriminator (RMSprop) that is trained on z_real = encoder(x) vs z_fake (:380-397) and whose penalty
+    -lam sum log(d(z_real) + 1e-3), evaluated with the UPDATED latent discriminator (:401-411), is accumulated into the
+    encoder's gradient (:421). The script's second and third encoder forwards see unchanged weights, so the encoder runs once
+    and its BatchNorm running statistics are updated three times; the unused decoder(z_real) forward of :405 runs for its
+    BatchNorm side effects. NOTE: the latent discriminator is updated inside forward_backward (the penalty needs it).
+    Extra parameter keys: latent_discriminator.main.*; step(x, eps, z_p, z_fake)."""
+
+    _enc_bn_updates = 3
+
+    def __init__(self, params, buffers, cfg, z=128, adt=BF16, hp=None, dist_group=None, gate=True, lam=1.0):
+        super().__init__(params, buffers, cfg, z, adt, hp, dist_group, gate)
+        self.lam = float(lam)
+        self.ldis = NN.WaeDiscriminatorNet(z, adt)
+        pre = "latent_discriminator."
+        named = _split(params, pre)
+        diff = set(self.ldis.param_names()) ^ set(named)
+        if diff:
+            raise L.FmriError(f"parameter names of {pre} differ from the reference layout: {sorted(diff)}")
+        self.buckets[pre] = Bucket(pre, OrderedDict((k, named[k].to("cuda", F32)) for k in named), 1)
+        self.lr[pre] = float(self.hp["lr"])
+        self.ldis.refresh(self.buckets[pre].P, inplace=True)
+        self.lsc = Z(4)   # L_fake, L_real, L_pen (batch sums)
+        self._z_fake = None
+
+    def refresh(self):
+        super().refresh()
+        if hasattr(self, "ldis"):
+            self.ldis.refresh(self.buckets["latent_discriminator."].P, inplace=True)
+
+    def _before_encoder_backward(self, mu, dycat):
+        hp, z, lam = self.hp, self.z, self.lam
+        B = mu.shape[0]
+        bl, bd = self.buckets["latent_discriminator."], self.buckets["decoder."]
+        z_fake, ones = self._z_fake, self._ones(3 * B)
+        # ---- latent discriminator phase (:380-397)
+        p_real, cr = self.ldis.forward(bl.P, mu)
+        p_fake, cf = self.ldis.forward(bl.P, z_fake)
+        l, gp = E(2 * B), E(2 * B)
+        L.bce_fwd(p_fake, l[:B], B, True, lam)
+        L.bce_fwd(p_real, l[B:], B, False, lam)
+        L.vecsum(l[:B], B, 1.0, self.lsc[0:1])
+        L.vecsum(l[B:], B, 1.0, self.lsc[1:2])
+        L.bce_bwd(p_fake, ones, gp[:B], B, True, lam)
+        L.bce_bwd(p_real, ones, gp[B:], B, False, lam)
+        self.ldis.backward(bl.P, cf, gp[:B], bl.G, False, True, False)
+        self.ldis.backward(bl.P, cr, gp[B:], bl.G, True, True, False)
+        if self.world > 1:   # the penalty needs the globally updated latent discriminator
+            self._allreduce_async([bl.flat_g])
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        L.multi_tensor_rmsprop([bl.flat_p], [bl.flat_g], [bl.states[0]], self.lr["latent_discriminator."], hp["alpha"],
+                               hp["eps"], 0.0, None, None)
+        self.ldis.refresh(bl.P, inplace=True)
+        # ---- penalty (:401-417): the unused reconstruction forward (BatchNorm running statistics), then d with the new weights
+        nbd = {}
+        self.dec.forward(bd.P, self.Ssub["decoder."], mu, True, 1, nbd)
+        for k, v in nbd.items():
+            self.nbt["decoder." + k] = self.nbt.get("decoder." + k, 0) + v
+        p2, c2 = self.ldis.forward(bl.P, mu)
+        L.bce_fwd(p2, l[:B], B, True, lam)
+        L.vecsum(l[:B], B, 1.0, self.lsc[2:3])
+        L.bce_bwd(p2, ones, gp[:B], B, True, lam)
+        dz_pen = self.ldis.backward(bl.P, c2, gp[:B], None, False, False, True)
+        dycat[:, :z].add_(dz_pen.to(dycat.dtype))   # :421 the encoder sweep accumulates onto the penalty gradient
+        self._d = dict(z_real=mu, d_real=p_real, d_fake=p_fake, d_real_g=p2)
+
+    def forward_backward(self, x, eps, z_p, z_fake):
+        self._z_fake = z_fake
+        out = super().forward_backward(x, eps, z_p)
+        out.update(self._d)
+        return out
+
+    def step(self, x, eps, z_p, z_fake):
+        out = self.forward_backward(x, eps, z_p, z_fake)
+        self.update(x.shape[0] * self.world)
+        return out
+
+    def losses(self):
+        d = super().losses()
+        lf, lr, lp, _ = self.lsc.tolist()
+        d.update(loss_discriminator_fake=lf, loss_discriminator_real=lr, loss_penalty=lp)
+        return d
