@@ -71,3 +71,34 @@ def test_product_path_does_not_import_the_oracle():
         p = os.path.join(ROOT, "models", f)
         if os.path.exists(p):
             assert not re.search(r"^\s*(from|import)\s+oracle", open(p).read(), flags=re.M)
+
+
+def test_epoch_end_schedules_match_torch_schedulers():
+    """hp.epoch_end_vgan / epoch_end_wae against torch.optim.lr_scheduler (ExponentialLR, StepLR) and the margin /
+    equilibrium / lambda_mse rules of train/train_vgan_stage1.py:446-457."""
+    import torch
+
+    from thesis_fmri_reconstruction_b200 import hp as H
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.RMSprop([p], lr=1e-4)
+    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.98)
+    lr, h = {"encoder.": 1e-4}, dict(H.HP_VGAN)
+    for _ in range(5):
+        opt.step(); sch.step()
+        H.epoch_end_vgan(lr, h, decay_lr=0.98, decay_margin=1.5, decay_equilibrium=0.9, decay_mse=3.0)
+    assert abs(lr["encoder."] - opt.param_groups[0]["lr"]) < 1e-18
+    assert h["equilibrium"] >= h["margin"] and h["lambda_mse"] <= 1.0
+    m, e = H.HP_VGAN["margin"], H.HP_VGAN["equilibrium"]
+    for _ in range(5):
+        m *= 1.5; e *= 0.9
+        if m > e:
+            e = m
+    assert abs(h["margin"] - m) < 1e-12 and abs(h["equilibrium"] - e) < 1e-12
+    opt = torch.optim.Adam([p], lr=1e-3)
+    sch = torch.optim.lr_scheduler.StepLR(opt, step_size=30, gamma=0.5)
+    lr = {"decoder.": 1e-3}
+    for epoch in range(1, 95):
+        opt.step(); sch.step()
+        H.epoch_end_wae(lr, epoch)
+        assert abs(lr["decoder."] - opt.param_groups[0]["lr"]) < 1e-15, epoch

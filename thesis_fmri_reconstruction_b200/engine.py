@@ -67,6 +67,17 @@ class _TrainerBase:
             self.S[name] += n
         self.nbt.clear()
 
+    def end_epoch(self, epoch=None, **kw):
+        """Per-epoch schedules of the reference scripts, applied to this trainer's learning rates / gate constants:
+        VAE/GAN trainers -> hp.epoch_end_vgan (ExponentialLR 0.98, margin / equilibrium / lambda_mse decay,
+        train_vgan_stage1.py:446-457); WAE trainers -> hp.epoch_end_wae (StepLR(30, 0.5), needs `epoch`)."""
+        from . import hp as _hp
+
+        if "beta1" in self.hp:
+            _hp.epoch_end_wae(self.lr, int(epoch), **kw)
+        else:
+            _hp.epoch_end_vgan(self.lr, self.hp, **kw)
+
     def named_parameters(self):
         out = OrderedDict()
         for b in self.buckets.values():

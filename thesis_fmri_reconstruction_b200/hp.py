@@ -25,3 +25,24 @@ def cfg_from_module(mc):
                 fc_output_gan=mc.fc_output_gan, stride_gan=mc.stride_gan, latent_dim=mc.latent_dim,
                 output_pad_dec=list(mc.output_pad_dec), encoder_channels=list(mc.encoder_channels),
                 decoder_channels=list(mc.decoder_channels), discrim_channels=list(mc.discrim_channels))
+
+
+def epoch_end_vgan(lr, hp, decay_lr=0.98, decay_margin=1.0, decay_equilibrium=1.0, decay_mse=1.0):
+    """End-of-epoch schedule of the VAE/GAN scripts (train_vgan_stage1.py:446-457; defaults gan_config.py:26-31):
+    ExponentialLR(gamma=decay_lr) on every optimizer, margin / equilibrium decay with equilibrium >= margin, lambda_mse growth
+    capped at 1. `lr`: {bucket prefix: learning rate}; `hp`: the trainer's hyper-parameter dict. Both are updated in place."""
+    for k in lr:
+        lr[k] *= decay_lr
+    hp["margin"] *= decay_margin
+    hp["equilibrium"] *= decay_equilibrium
+    if hp["margin"] > hp["equilibrium"]:
+        hp["equilibrium"] = hp["margin"]
+    hp["lambda_mse"] = min(1.0, hp["lambda_mse"] * decay_mse)
+
+
+def epoch_end_wae(lr, epoch, step_size=30, decay_lr=0.5):
+    """StepLR(step_size, gamma=decay_lr) of the WAE scripts (train_wae_stage1.py:226-228, 334-336; wae_config.py:21-22;
+    stages II / III hard-code StepLR(30, 0.5), train_wae_stage2.py:241-243). `epoch` = number of finished epochs (1-based)."""
+    if epoch > 0 and epoch % step_size == 0:
+        for k in lr:
+            lr[k] *= decay_lr
