@@ -519,3 +519,44 @@ def test_dual_stage1_bf16_tensor_path():
     assert max(rep["forward"].values()) < 2e-2, rep["forward"]
     assert max(rep["grad_bucket"].values()) < 0.5, rep["grad_bucket"]
     assert rep["gate_ok"] and rep["nbt_ok"] and rep["bn_worst"][1] < 2e-2
+
+
+@pytest.mark.parametrize("kind", ["vaegan", "waegan"])
+def test_trainer_checkpoint_resume(kind):
+    """state_dict() / load_state_dict(): a resumed trainer continues exactly like the original (parameters, BatchNorm buffers,
+    RMSprop / Adam state, Adam step count), and the `model` part loads strictly into the drop-in nn.Module."""
+    B, seed = 8, 11
+    x = O.synthetic_images(B, seed=seed).cuda()
+    eps, z_p = [t.cuda() for t in O.synthetic_noise(B, 128, seed=seed)]
+    if kind == "vaegan":
+        P, S = O.make_vaegan(O.CFG64, seed=seed)
+        mk = lambda: engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
+        args = (x, eps, z_p)
+    else:
+        P, S = O.make_waegan(O.CFG64, seed=seed)
+        mk = lambda: engine.WaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
+        args = (x, eps * 0.5)
+    a = mk()
+    for _ in range(2):
+        a.step(*args)
+    a.end_epoch(epoch=30)
+    sd = a.state_dict()
+    b = mk()
+    b.load_state_dict(sd)
+    a.step(*args)
+    b.step(*args)
+    torch.cuda.synchronize()
+    pa, pb = a.named_parameters(), b.named_parameters()
+    worst = max(rel(pb[k], pa[k].cpu()) for k in pa)
+    sa, sb = a.named_buffers(), b.named_buffers()
+    assert worst < 1e-5, worst
+    assert all(int(sa[k]) == int(sb[k]) for k in sa if not sa[k].dtype.is_floating_point)
+    assert max(rel(sb[k], sa[k].cpu()) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
+    assert a.lr == b.lr and getattr(a, "t", 0) == getattr(b, "t", 0)
+    if kind == "vaegan":
+        import configs.models_config as mc
+        mc.use_resolution(64)
+        from models.vae_gan import VaeGan
+        m = VaeGan(device="cuda", z_size=128)
+        missing, unexpected = m.load_state_dict(sd["model"], strict=True)
+        assert not missing and not unexpected

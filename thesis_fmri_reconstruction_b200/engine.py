@@ -78,6 +78,42 @@ class _TrainerBase:
         else:
             _hp.epoch_end_vgan(self.lr, self.hp, **kw)
 
+    def state_dict(self):
+        """Checkpoint of the whole trainer (host tensors). `model` holds parameters and BatchNorm buffers under the
+        reference's state_dict keys (torch.save(sd["model"]) is a checkpoint the reference's load_state_dict accepts);
+        `optimizer` holds every bucket's per-parameter state (RMSprop square_avg, or Adam exp_avg / exp_avg_sq, named like the
+        parameters); plus learning rates, hyper-parameters (the decayed margin / equilibrium / lambda_mse) and Adam's step count."""
+        self._wait_comm()
+        model = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.named_parameters().items())
+        model.update((k, v.detach().cpu().clone()) for k, v in self.named_buffers().items())
+        opt = OrderedDict()
+        for pre, b in self.buckets.items():
+            opt[pre] = [OrderedDict((pre + k, b.state_view(i, k).detach().cpu().clone()) for k in b.names)
+                        for i in range(len(b.states))]
+        return dict(model=model, optimizer=opt, lr=dict(self.lr), hp=dict(self.hp), t=int(getattr(self, "t", 0)))
+
+    def load_state_dict(self, sd):
+        """Resume from state_dict(): copies into the flat device buckets, then re-derives the bf16 operand packs."""
+        self._wait_comm()
+        for k, v in self.named_parameters().items():
+            v.copy_(sd["model"][k])
+        self.nbt.clear()
+        for k, v in self.S.items():
+            v.copy_(sd["model"][k])
+        for pre, b in self.buckets.items():
+            for i, st in enumerate(sd["optimizer"].get(pre, [])):
+                for k in b.names:
+                    b.state_view(i, k).copy_(st[pre + k])
+        self.lr.update(sd["lr"])
+        self.hp.update(sd["hp"])
+        if hasattr(self, "t"):
+            self.t = int(sd["t"])
+        if hasattr(self, "nets"):
+            for pre, net in self.nets.items():
+                net.refresh(self.buckets[pre].P, inplace=True)
+        if hasattr(self, "refresh"):
+            self.refresh()
+
     def named_parameters(self):
         out = OrderedDict()
         for b in self.buckets.values():
