@@ -407,42 +407,39 @@ def test_wae_cognitive_stage_bf16_tensor_path(stage):
 
 
 def test_graphed_step_matches_eager():
-    """engine.GraphedStep (CUDA-graph replay of the Stage-I step) == the eager step. The weight-gradient kernels combine
-    their pixel splits with fp32 atomics in an unspecified order, and RMSprop's first steps move every element by
-    lr * sign(g) / sqrt(0.1) however small g is, so two EAGER runs already drift apart after a few steps; the bar is that the
-    replayed run stays as close to an eager run as a second eager run does (x3), and that losses agree to 1e-3."""
+    """engine.GraphedStep (CUDA-graph replay of the Stage-I step) == the eager step. Two runs drift apart chaotically over
+    several steps (fp32 atomics in the weight-gradient splits; RMSprop's first steps move every element by lr * sign(g) /
+    sqrt(0.1) however small g is), so the comparison is ONE step from an identical, already warmed-up state: the eager
+    trainer's checkpoint is loaded into the captured trainer (the graph reads the same flat buffers)."""
     B, seed = 8, 31
     P, S = O.make_vaegan(O.CFG64, seed=seed)
     x = O.synthetic_images(B, seed=seed).cuda()
     eps, z_p = [t.cuda() for t in O.synthetic_noise(B, 128, seed=seed)]
     a = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
-    c = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
     b = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
     g = engine.GraphedStep(b, x, eps, z_p, warmup=2)
-    for _ in range(2):          # the graphed trainer ran 2 eager warm-up steps
-        a.step(x, eps, z_p)
-        c.step(x, eps, z_p)
     for _ in range(3):
         a.step(x, eps, z_p)
-        c.step(x, eps, z_p)
+    b.load_state_dict(a.state_dict())
+    a.step(x, eps, z_p)
+    out = g(x, eps, z_p)
+    torch.cuda.synchronize()
+    pa, pb = a.named_parameters(), b.named_parameters()
+    worst = max(rel(pb[k], pa[k].cpu()) for k in pa)
+    la, lb = a.losses(), b.losses()
+    print("graphed vs eager, one step from the same state: worst parameter rel", worst, la["loss_encoder"], lb["loss_encoder"],
+          "launches/replay", g.launches)
+    assert worst < 1e-4, worst
+    assert abs(la["loss_encoder"] - lb["loss_encoder"]) <= 1e-5 * abs(la["loss_encoder"])
+    assert (la["train_dis"], la["train_dec"]) == (lb["train_dis"], lb["train_dec"])
+    sa, sb = a.named_buffers(), b.named_buffers()
+    assert all(int(sa[k]) == int(sb[k]) for k in sa if not sa[k].dtype.is_floating_point)
+    assert max(rel(sb[k], sa[k].cpu()) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
+    assert g.launches > 100 and torch.isfinite(out["x_tilde"].float()).all()
+    for _ in range(2):   # further replays keep running and stay finite
         out = g(x, eps, z_p)
     torch.cuda.synchronize()
-    pa, pb, pc = a.named_parameters(), b.named_parameters(), c.named_parameters()
-    worst_graph = max(rel(pb[k], pa[k].cpu()) for k in pa)
-    worst_eager = max(rel(pc[k], pa[k].cpu()) for k in pa)
-    la, lb = a.losses(), b.losses()
-    print("graphed vs eager", worst_graph, "eager vs eager", worst_eager, la["loss_encoder"], lb["loss_encoder"],
-          "launches/replay", g.launches)
-    assert worst_graph <= max(3 * worst_eager, 1e-5), (worst_graph, worst_eager)
-    assert abs(la["loss_encoder"] - lb["loss_encoder"]) <= 1e-3 * abs(la["loss_encoder"])
-    assert (la["train_dis"], la["train_dec"]) == (lb["train_dis"], lb["train_dec"])
-    sa, sb, sc_ = a.named_buffers(), b.named_buffers(), c.named_buffers()
-    assert all(int(sa[k]) == int(sb[k]) for k in sa if not sa[k].dtype.is_floating_point)
-    fl = [k for k in sa if sa[k].dtype.is_floating_point]
-    buf_graph = max(rel(sb[k], sa[k].cpu()) for k in fl)
-    buf_eager = max(rel(sc_[k], sa[k].cpu()) for k in fl)
-    assert buf_graph <= max(3 * buf_eager, 1e-5), (buf_graph, buf_eager)
-    assert g.launches > 100 and torch.isfinite(out["x_tilde"].float()).all()
+    assert torch.isfinite(out["x_tilde"].float()).all() and all(torch.isfinite(v).all() for v in b.named_parameters().values())
 
 
 def test_stage1_beta_vae_mode_fp32():
