@@ -429,7 +429,9 @@ def test_graphed_step_matches_eager():
     la, lb = a.losses(), b.losses()
     print("graphed vs eager, one step from the same state: worst parameter rel", worst, la["loss_encoder"], lb["loss_encoder"],
           "launches/replay", g.launches)
-    assert worst < 1e-4, worst
+    # 1e-3: an element whose gradient is below the fp32-atomics noise can change sign, and both optimizers move such an
+    # element by ~lr whatever its magnitude; a replay that lost state or inputs is off by >= 1e-2
+    assert worst < 1e-3, worst
     assert abs(la["loss_encoder"] - lb["loss_encoder"]) <= 1e-5 * abs(la["loss_encoder"])
     assert (la["train_dis"], la["train_dec"]) == (lb["train_dis"], lb["train_dec"])
     sa, sb = a.named_buffers(), b.named_buffers()
@@ -546,7 +548,9 @@ def test_trainer_checkpoint_resume(kind):
     pa, pb = a.named_parameters(), b.named_parameters()
     worst = max(rel(pb[k], pa[k].cpu()) for k in pa)
     sa, sb = a.named_buffers(), b.named_buffers()
-    assert worst < 1e-5, worst
+    # 1e-3, not 1e-5: elements with a gradient below the fp32-atomics noise may change sign and move by ~lr under RMSprop /
+    # Adam; a resume that lost the optimizer state is off by >= 1e-2 (first-step updates are lr * sign(g))
+    assert worst < 1e-3, worst
     assert all(int(sa[k]) == int(sb[k]) for k in sa if not sa[k].dtype.is_floating_point)
     assert max(rel(sb[k], sa[k].cpu()) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
     assert a.lr == b.lr and getattr(a, "t", 0) == getattr(b, "t", 0)
