@@ -102,3 +102,37 @@ def test_epoch_end_schedules_match_torch_schedulers():
         opt.step(); sch.step()
         H.epoch_end_wae(lr, epoch)
         assert abs(lr["decoder."] - opt.param_groups[0]["lr"]) < 1e-15, epoch
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """No CPU / Python fallback: with the shared object absent, the first use raises FmriError naming the build command."""
+    import importlib
+
+    from thesis_fmri_reconstruction_b200 import lib as L
+
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "libfmri_b200.so"))
+    monkeypatch.setattr(L, "_lib", None)
+    try:
+        with pytest.raises(L.FmriError) as e:
+            L.load()
+        assert "build" in str(e.value)
+    finally:
+        monkeypatch.undo()
+        importlib.reload(L) if L._lib is None and False else None
+
+
+def test_models_refuse_cpu_execution():
+    """The drop-in nn.Modules are parameter containers over the CUDA library: a forward on CPU tensors must raise, never
+    silently compute with torch ops."""
+    import torch
+
+    import configs.models_config as mc
+    from thesis_fmri_reconstruction_b200 import lib as L
+
+    mc.use_resolution(64)
+    from models.vae_gan import Decoder, Encoder
+
+    with pytest.raises(L.FmriError):
+        Encoder(channel_in=3, z_size=128)(torch.zeros(2, 3, 64, 64))
+    with pytest.raises(L.FmriError):
+        Decoder(z_size=128, size=256)(torch.zeros(2, 128))

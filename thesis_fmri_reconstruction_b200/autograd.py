@@ -364,21 +364,38 @@ def bce(p, positive, scale=1.0):
     return _BceFn.apply(p, positive, scale)
 
 
+def _on_cuda(mod, *inputs):
+    """No CPU path: refuse before anything is allocated, with the library's own error type."""
+    for t in inputs:
+        if t is not None and not t.is_cuda:
+            raise L.FmriError(f"{type(mod).__name__} input is on {t.device}: the sm_100a kernel library has no CPU path "
+                              "(move the model and data to cuda)")
+    for p in mod.parameters():
+        if not p.is_cuda:
+            raise L.FmriError(f"{type(mod).__name__} parameters are on {p.device}: the sm_100a kernel library has no CPU "
+                              "path (call .to('cuda'))")
+        break
+
+
 def run_encoder(mod, x):
+    _on_cuda(mod, x)
     _, params = _params_of(mod)
     return _EncoderFn.apply(mod, x, *params)
 
 
 def run_decoder(mod, z):
+    _on_cuda(mod, z)
     _, params = _params_of(mod)
     return _DecoderFn.apply(mod, z, *params)
 
 
 def run_discriminator(mod, mode, xo, xp, xs):
+    _on_cuda(mod, xo, xp, xs)
     _, params = _params_of(mod)
     return _DiscriminatorFn.apply(mod, mode, xo, xp, xs, *params)
 
 
 def run_wae_discriminator(mod, z):
+    _on_cuda(mod, z)
     _, params = _params_of(mod)
     return _WaeDiscriminatorFn.apply(mod, z, *params)
