@@ -420,11 +420,27 @@ static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH
     c.lim_x = GX;
     c.lim_y = GY;
     c.out_off = 0;
-    for (int t9 = 0; t9 < 9; ++t9) {
-        c.taps[t9].map = 0;
-        c.taps[t9].dy = (int16_t)(t9 / 3 - 1);
-        c.taps[t9].dx = (int16_t)(t9 % 3 - 1);
-        c.taps[t9].brow = t9 * 128;
+    // Coarse taps, the four full ones first (the first MMA of a tile must initialise every accumulator column). A tap with
+    // dy = -1 only feeds the ph = 0 classes and one with dx = -1 only the pw = 0 classes; with the column groups ordered
+    // (0,1),(0,0),(1,0),(1,1) (merge_pack_kernel) the live columns are contiguous, and the MMA warp skips the zero slabs:
+    // 4 x 128 + 4 x 64 + 1 x 32 = 800 = 25 x 32 columns per K step instead of 9 x 128 (FMRI_MERGE_SKIP=0 issues full N).
+    static int skip = -1;
+    if (skip < 0) {
+        const char* e = getenv("FMRI_MERGE_SKIP");
+        skip = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    static const int order[9] = {4, 5, 7, 8, 1, 2, 3, 6, 0};   // t9 = (dy+1)*3 + (dx+1)
+    for (int i = 0; i < 9; ++i) {
+        const int t9 = order[i], dy = t9 / 3 - 1, dx = t9 % 3 - 1;
+        c.taps[i].map = 0;
+        c.taps[i].dy = (int16_t)dy;
+        c.taps[i].dx = (int16_t)dx;
+        c.taps[i].brow = t9 * 128;
+        int g0 = 0, ng = 4;                       // column groups [g0, g0 + ng)
+        if (dy == -1 && dx == -1) { g0 = 1; ng = 1; }
+        else if (dy == -1) { g0 = 0; ng = 2; }
+        else if (dx == -1) { g0 = 1; ng = 2; }
+        c.taps[i].ncol = (int16_t)((skip && ng < 4) ? ((ng << 8) | g0) : 0);
     }
     p.num_chunks = Ck / KCH;
     p.n_total = 128;

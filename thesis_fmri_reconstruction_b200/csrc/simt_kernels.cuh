@@ -1140,7 +1140,7 @@ __global__ void scatter4_kernel(const Tin* __restrict__ src, Tout* __restrict__ 
 }
 
 // parity-merged scatter pack (see IgParams::merge): dst[(t9*128 + g*32 + n)*Ck + k] = src[((kh*5+kw)*32 + n)*Ck + k] where
-// t9 = (dy+1)*3 + (dx+1), g = ph*2 + pw, kh = ph + 2 - 2*dy, kw = pw + 2 - 2*dx; zero when (kh, kw) falls outside the 5x5 window.
+// t9 = (dy+1)*3 + (dx+1), g = column group of class (ph,pw) in the order (0,1),(0,0),(1,0),(1,1), kh = ph + 2 - 2*dy, kw = pw + 2 - 2*dx; zero when (kh, kw) falls outside the 5x5 window.
 // src is the ordinary tap-major pack [25][32][Ck].
 __global__ void merge_pack_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Ck) {
     const int total = 9 * 128 * Ck;
@@ -1149,7 +1149,10 @@ __global__ void merge_pack_kernel(const __nv_bfloat16* __restrict__ src, __nv_bf
         const int r = i / Ck;
         const int n = r & 31, g = (r >> 5) & 3, t9 = r >> 7;
         const int dy = t9 / 3 - 1, dx = t9 % 3 - 1;
-        const int kh = (g >> 1) + 2 - 2 * dy, kw = (g & 1) + 2 - 2 * dx;
+        // column groups in the order (ph,pw) = (0,1),(0,0),(1,0),(1,1): the classes with non-zero weights for a coarse tap are
+        // then always a CONTIGUOUS column range (dy = -1: groups 0-1, dx = -1: groups 1-2, both: group 1)
+        const int ph = g >> 1, pw = (g == 0 || g == 3) ? 1 : 0;
+        const int kh = ph + 2 - 2 * dy, kw = pw + 2 - 2 * dx;
         __nv_bfloat16 v = __float2bfloat16_rn(0.f);
         if (kh >= 0 && kh < 5 && kw >= 0 && kw < 5) v = src[((size_t)(kh * 5 + kw) * 32 + n) * Ck + k];
         dst[i] = v;

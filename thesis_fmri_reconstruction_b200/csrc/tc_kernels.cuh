@@ -20,7 +20,8 @@ struct TapDesc {
     int16_t map;   // which A tensor map (stride-parity plane) this tap reads
     int16_t dx;    // pixel offset added to the tile origin (x)
     int16_t dy;    // pixel offset added to the tile origin (y)
-    int16_t pad_;
+    int16_t ncol;  // 0: the MMA covers all BN columns; else (columns / 32) << 8 | (first column / 32): the parity-merged
+                   // scatter's weight slab of this coarse tap is zero outside that range (persistent kernel only)
     int32_t brow;  // first row of this tap's weights in the B pack
 };
 
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
                 int stat_col = c0;
                 if (p.merge) {  // 32-column group -> output parity class
                     const int g = (nt * BN + c0) >> 5;
-                    const int ph = g >> 1, pw = g & 1;
+                    const int ph = g >> 1, pw = (g == 0 || g == 3) ? 1 : 0;   // merged column groups: (0,1),(0,0),(1,0),(1,1)
                     valid = valid_tile && (2 * (y0[m] + yi) + ph < p.merge_oh) && (2 * (x0[m] + xi) + pw < p.merge_ow);
                     off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
                     stat_col = 0;
@@ -528,24 +529,32 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                 const int buf = lt & 1;
                 mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const int nks = p.cls[tl.cls].num_taps * p.num_chunks;
-                for (int ks = 0; ks < nks; ++ks, ++it) {
-                    const int st = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[st], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
-                    const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout);
+                const TapClass& tc_ = p.cls[tl.cls];
+                int ks = 0;
+                for (int tap = 0; tap < tc_.num_taps; ++tap) {
+                    // column range of this tap's MMAs (parity-merged scatter: the rest of its weight slab is zeros)
+                    const int nc = tc_.taps[tap].ncol;
+                    const uint32_t col0 = nc ? (uint32_t)(nc & 0xff) * 32u : 0u;
+                    const uint32_t idesc_t = nc ? umma_idesc_bf16(128, (nc >> 8) * 32, false, false) : idesc;
+                    const uint32_t brow_off = (col0 / 8u) * (sbo >> 4);   // descriptor units (16 B) to weight row col0
+                    for (int ch = 0; ch < p.num_chunks; ++ch, ++ks, ++it) {
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&full_bar[st], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
+                        const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout) + brow_off;
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        if (!tl.live[m]) continue;
-                        const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
+                        for (int m = 0; m < MT; ++m) {
+                            if (!tl.live[m]) continue;
+                            const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
 #pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k)
-                            umma_bf16_elect(tmem_u + buf * ACC_COLS + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                            (ks | k) != 0);
+                            for (int k = 0; k < KCH / 16; ++k)
+                                umma_bf16_elect(tmem_u + buf * ACC_COLS + m * BN + col0, adesc + 2 * k, bdesc + 2 * k, idesc_t,
+                                                (ks | k) != 0);
+                        }
+                        umma_commit_elect(&empty_bar[st]);
                     }
-                    umma_commit_elect(&empty_bar[st]);
                 }
                 umma_commit_elect(&tfull[buf]);
                 ++lt;
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     int stat_col = c0;
                     if (p.merge) {
                         const int g = (nt * BN + c0) >> 5;
-                        const int ph = g >> 1, pw = g & 1;
+                        const int ph = g >> 1, pw = (g == 0 || g == 3) ? 1 : 0;   // merged column groups: (0,1),(0,0),(1,0),(1,1)
                         valid = valid_tile && (2 * (tl.y0[m] + yi) + ph < p.merge_oh) && (2 * (tl.x0[m] + xi) + pw < p.merge_ow);
                         off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
                         stat_col = 0;
