@@ -97,14 +97,27 @@ def golden_stage1_vaegan(ref, B, seed, cfg=None, mode="vae-gan", beta=1.0):
     dl_o, dl_p, dl_s = disc_layer[:B], disc_layer[B:-B], disc_layer[-B:]          # :333-335
     dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]          # :337-339
     nle, kld, mse, bo, bp, bs = ref.VaeGan.loss(x, x_tilde, dl_o, dl_p, dl_s, dc_o, dc_p, dc_s, mus, lv)  # :342
+    train_dis, train_dec, train_enc = True, True, True                            # :352-356
     if mode == "beta-vae":
         kld_weight = 1 / B                                                        # :361
         loss_encoder = torch.sum(kld) * beta * kld_weight + torch.sum(mse)        # :362
-    else:
+    elif mode in ("vae-gan",):
         loss_encoder = torch.sum(kld) + torch.sum(mse)                            # :369
-    loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)            # :370
-    loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator  # :372
-    train_dis, train_dec = True, True
+    if mode in ("vae-gan", "beta-vae"):
+        loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)        # :370
+        loss_decoder = torch.sum(hp["lambda_mse"] * mse) - (1.0 - hp["lambda_mse"]) * loss_discriminator  # :372
+    if mode == "dcgan":                                                           # :374-380
+        train_enc = False
+        for param in model.encoder.parameters():
+            param.requires_grad = False
+        loss_encoder = torch.sum(kld) + torch.sum(nle)
+        loss_discriminator = torch.sum(bo) + torch.sum(bs)
+        loss_decoder = torch.sum(hp["lambda_mse"] * nle) - (1.0 - hp["lambda_mse"]) * loss_discriminator
+    if mode == "vae":                                                             # :382-387
+        loss_encoder = torch.sum(kld) + torch.sum(nle)
+        loss_discriminator = torch.sum(bo) + torch.sum(bs)
+        loss_decoder = torch.sum(hp["lambda_mse"] * nle)
+        train_dis = False
     if torch.mean(bo).item() < hp["equilibrium"] - hp["margin"] or torch.mean(bp).item() < hp["equilibrium"] - hp["margin"]:
         train_dis = False
     if torch.mean(bo).item() > hp["equilibrium"] + hp["margin"] or torch.mean(bp).item() > hp["equilibrium"] + hp["margin"]:
@@ -112,17 +125,21 @@ def golden_stage1_vaegan(ref, B, seed, cfg=None, mode="vae-gan", beta=1.0):
     if train_dec is False and train_dis is False:
         train_dis = True
         train_dec = True
+    def grab(mod):   # a parameter the loss does not reach keeps grad None (torch >= 2): recorded as zeros, RMSprop skips it
+        return {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in mod.named_parameters()}
+
     grads = {}
     model.zero_grad()                                                             # :408
-    loss_encoder.backward(retain_graph=True)                                      # :412
-    grads.update({"encoder." + k: p.grad.clone() for k, p in model.encoder.named_parameters()})
-    model.zero_grad()                                                             # :418
-    loss_decoder.backward(retain_graph=True)                                      # :422
-    grads.update({"decoder." + k: p.grad.clone() for k, p in model.decoder.named_parameters()})
+    if train_enc:                                                                 # :410
+        loss_encoder.backward(retain_graph=True)                                  # :412
+        grads.update({"encoder." + k: v for k, v in grab(model.encoder).items()})
+        model.zero_grad()                                                         # :418
+    loss_decoder.backward(retain_graph=True)                                      # :422 (the script guards it with train_dec)
+    grads.update({"decoder." + k: v for k, v in grab(model.decoder).items()})
     model.discriminator.zero_grad()                                               # :426
     loss_discriminator.backward()                                                 # :430
-    grads.update({"discriminator." + k: p.grad.clone() for k, p in model.discriminator.named_parameters()})
-    for b, on in (("encoder", True), ("decoder", train_dec), ("discriminator", train_dis)):
+    grads.update({"discriminator." + k: v for k, v in grab(model.discriminator).items()})
+    for b, on in (("encoder", train_enc), ("decoder", train_dec), ("discriminator", train_dis)):
         if not on:
             continue
         for k, p in getattr(model, b).named_parameters():
@@ -477,6 +494,10 @@ def main():
     np.savez_compressed(os.path.join(out, "stage1_betavae_B4_s2024.npz"),
                         **golden_stage1_vaegan(ref, 4, 2024, mode="beta-vae", beta=4.0), beta=np.array(4.0))
     print("wrote the beta-vae golden")
+    for m in ("dcgan", "vae"):
+        np.savez_compressed(os.path.join(out, f"stage1_{m}_B4_s31{len(m)}.npz"),
+                            **golden_stage1_vaegan(ref, 4, 310 + len(m), mode=m), mode=np.array(m))
+        print("wrote the", m, "golden")
     np.savez_compressed(os.path.join(out, "stage1_dual_B4_s606.npz"), **golden_dual_stage1(ref, 4, 606))
     print("wrote the dual WAE/GAN Stage-I golden")
     ref100 = import_reference(O.CFG100)   # the reference's active 100x100 / latent-512 block: odd 13/25/50-pixel grids

@@ -277,9 +277,10 @@ def adam_update(p, g, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
     return p - (lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps), m, v
 
 
-def gate(bce_o_mean, bce_p_mean, margin=0.35, equilibrium=0.68):
-    """Equilibrium gate (train/train_vgan_stage1.py:396-404). Returns (train_dis, train_dec)."""
-    train_dis = train_dec = True
+def gate(bce_o_mean, bce_p_mean, margin=0.35, equilibrium=0.68, train_dis_in=True):
+    """Equilibrium gate (train/train_vgan_stage1.py:396-404). Returns (train_dis, train_dec). train_dis_in: the value the
+    loss-mix block left in train_dis ('vae' mode sets it False, :387, before these lines run)."""
+    train_dis, train_dec = train_dis_in, True
     if bce_o_mean < equilibrium - margin or bce_p_mean < equilibrium - margin:
         train_dis = False
     if bce_o_mean > equilibrium + margin or bce_p_mean > equilibrium + margin:
@@ -320,20 +321,34 @@ def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update
     dl_o, dl_p = disc_layer[:B], disc_layer[B:-B]
     dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
     nle, kl, mse, bce_o, bce_p, bce_s = vaegan_loss(x, x_tilde, dl_o, dl_p, dc_o, dc_p, dc_s, mu, logvar)
-    if mode not in ("vae-gan", "beta-vae"):
-        raise ValueError("oracle restates the 'vae-gan' (:368-372) and 'beta-vae' (:359-365) loss mixes")
-    kl_w = beta / B if mode == "beta-vae" else 1.0                             # :360-362 (kld_weight = 1 / batch_size)
-    loss_enc = kl.sum() * kl_w + mse.sum()                                     # :369 / :362
-    loss_dis = bce_o.sum() + bce_p.sum() + bce_s.sum()                         # :370
-    loss_dec = (hp["lambda_mse"] * mse).sum() - (1.0 - hp["lambda_mse"]) * loss_dis  # :372
-    train_dis, train_dec = gate(bce_o.mean().item(), bce_p.mean().item(), hp["margin"], hp["equilibrium"])
+    if mode not in ("vae-gan", "beta-vae", "dcgan", "vae"):
+        raise ValueError("mode must be one of the script's four loss mixes (train_vgan_stage1.py:359-388)")
+    train_enc, pre_dis = True, True
+    if mode in ("vae-gan", "beta-vae"):
+        kl_w = beta / B if mode == "beta-vae" else 1.0                         # :360-362 (kld_weight = 1 / batch_size)
+        loss_enc = kl.sum() * kl_w + mse.sum()                                 # :369 / :362
+        loss_dis = bce_o.sum() + bce_p.sum() + bce_s.sum()                     # :370
+        loss_dec = (hp["lambda_mse"] * mse).sum() - (1.0 - hp["lambda_mse"]) * loss_dis  # :372
+    elif mode == "dcgan":                                                      # :374-380: pixel NLE, encoder not trained
+        train_enc = False
+        loss_enc = kl.sum() + nle.sum()
+        loss_dis = bce_o.sum() + bce_s.sum()
+        loss_dec = (hp["lambda_mse"] * nle).sum() - (1.0 - hp["lambda_mse"]) * loss_dis
+    else:                                                                      # 'vae' :382-387
+        loss_enc = kl.sum() + nle.sum()
+        loss_dis = bce_o.sum() + bce_s.sum()
+        loss_dec = (hp["lambda_mse"] * nle).sum()
+        pre_dis = False                                                        # :387 train_dis = False before the gate
+    train_dis, train_dec = gate(bce_o.mean().item(), bce_p.mean().item(), hp["margin"], hp["equilibrium"], pre_dis)
     if force_gate is not None:
         train_dis, train_dec = force_gate
     names = {b: bucket(W, b + ".") for b in ("encoder", "decoder", "discriminator")}
     grads = OrderedDict()
     for b, loss in (("encoder", loss_enc), ("decoder", loss_dec), ("discriminator", loss_dis)):
-        gs = torch.autograd.grad(loss, [W[n] for n in names[b]], retain_graph=True)
-        grads.update(zip(names[b], gs))
+        if b == "encoder" and not train_enc:
+            continue
+        gs = torch.autograd.grad(loss, [W[n] for n in names[b]], retain_graph=True, allow_unused=True)
+        grads.update((n, g if g is not None else torch.zeros_like(W[n])) for n, g in zip(names[b], gs))
     out = dict(x_tilde=x_tilde, x_p=x_p, disc_layer=disc_layer, disc_class=disc_class, mu=mu, logvar=logvar, z=z,
                nle=nle, kl=kl, mse=mse, bce_o=bce_o, bce_p=bce_p, bce_s=bce_s, loss_encoder=loss_enc,
                loss_decoder=loss_dec, loss_discriminator=loss_dis, train_dis=train_dis, train_dec=train_dec,
@@ -342,7 +357,7 @@ def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update
     if update:
         sq = sq if sq is not None else OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
         newP, newsq = OrderedDict(P), OrderedDict(sq)
-        active = dict(encoder=True, decoder=train_dec, discriminator=train_dis)
+        active = dict(encoder=train_enc, decoder=train_dec, discriminator=train_dis)
         for b in names:
             if not active[b]:
                 continue

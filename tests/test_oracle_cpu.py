@@ -29,7 +29,8 @@ def _cases(kind):
     return fs
 
 
-@pytest.mark.parametrize("path", _cases("stage1_vaegan") + _cases("stage1_vaegan100") + _cases("stage1_betavae"))
+@pytest.mark.parametrize("path", _cases("stage1_vaegan") + _cases("stage1_vaegan100") + _cases("stage1_betavae")
+                         + _cases("stage1_dcgan") + _cases("stage1_vae"))
 def test_stage1_vaegan_fp64_matches_reference(path):
     """64x64 fixtures and the reference's ACTIVE 100x100 / latent-512 configuration (configs/models_config.py:13-21:
     stride-2 first discriminator conv, output_padding [False, True, True], odd 13/25/50-pixel feature maps)."""
@@ -41,6 +42,8 @@ def test_stage1_vaegan_fp64_matches_reference(path):
     x = O.synthetic_images(B, size=cfg["image_size"], seed=seed).double()
     eps, z_p = [t.double() for t in O.synthetic_noise(B, z, seed=seed)]
     kw = dict(mode="beta-vae", beta=float(g["beta"])) if "betavae" in os.path.basename(path) else {}   # :359-365
+    if "mode" in g.files:                                                     # 'dcgan' / 'vae' pixel-NLE mixes, :374-387
+        kw = dict(mode=str(g["mode"]))
     out = O.stage1_vaegan_step(P, S, x, eps, z_p, cfg=cfg, **kw)
     assert out["train_dis"] == bool(g["train_dis"]) and out["train_dec"] == bool(g["train_dec"])
     for k in ("mu", "logvar", "kl", "mse", "bce_o", "bce_p", "bce_s", "disc_class", "loss_encoder", "loss_decoder",
@@ -59,7 +62,8 @@ def test_stage1_vaegan_fp64_matches_reference(path):
             assert summary_error(summarize(out["params"][name] - P[name]), g[k]) < 1e-6, k
         elif k.startswith("buf:"):
             assert summary_error(summarize(S[k[4:]]), g[k]) < 1e-9, k
-    assert n == len(P)
+    n_expected = len(P) - (sum(k.startswith("encoder.") for k in P) if kw.get("mode") == "dcgan" else 0)  # :375-377
+    assert n == n_expected
     # inference path (VaeGan.forward in eval mode, models/vae_gan.py:288-295): updated weights, the running statistics the
     # step produced, eval-mode BatchNorm
     P2 = out["params"]
