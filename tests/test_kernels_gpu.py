@@ -505,3 +505,22 @@ def test_mmd_imq_fwd_bwd(B, Z):
     gr = q64.grad.float()
     assert rel(dq.cpu(), gr) < 1e-5, rel(dq.cpu(), gr)
     assert rel(dq2.cpu() - base, gr) < 1e-4
+
+
+def test_persistent_path_subprocess():
+    """The persistent implicit-GEMM kernel (double-buffered TMEM accumulators, warp-converged producer, per-tap column ranges
+    of the parity-merged scatter) only takes over at >= 296 tiles, which the kernel-level cases above do not reach. The library
+    reads FMRI_IGEMM_PERSISTENT once per process, so the conv / convT cases are re-run in a child process with the
+    persistent kernel forced for every launch (value 2), at the same tolerances."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FMRI_IGEMM_PERSISTENT="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q",
+                        "-x", "-p", "no:cacheprovider", "-k",
+                        "conv_s2_dgrad or convT_fprop or conv_s2_fprop or fused_bn"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
