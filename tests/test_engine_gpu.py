@@ -561,3 +561,40 @@ def test_trainer_checkpoint_resume(kind):
         m = VaeGan(device="cuda", z_size=128)
         missing, unexpected = m.load_state_dict(sd["model"], strict=True)
         assert not missing and not unexpected
+
+
+def test_full_size_batch_tiling_property():
+    """BASELINE.json's full per-GPU batch (4096) through a size-independent property: a batch made of 64 copies of a 64-sample
+    batch has the same BatchNorm statistics, so every replica's forward tensors equal the 64-sample step's and the loss sums /
+    gradient buckets are 64x larger. The 64-sample step runs the one-tile-per-CTA kernels, the 4096-sample step the persistent
+    kernels, the wave-split weight gradients and the parity-merged scatter with column ranges: a cross-check of the large-batch
+    code paths against the small-batch ones the oracle certifies. bf16 tensor path; tolerances cover rounding-boundary flips."""
+    B0, R, seed = 64, 64, 404
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x0 = O.synthetic_images(B0, seed=seed).cuda()
+    eps0, zp0 = [t.cuda() for t in O.synthetic_noise(B0, 128, seed=seed)]
+    a = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
+    oa = a.forward_backward(x0, eps0, zp0)
+    ga = {k: v.clone() for k, v in a.named_grads().items()}
+    la = a.losses()
+    b = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
+    ob = b.forward_backward(x0.repeat(R, 1, 1, 1), eps0.repeat(R, 1), zp0.repeat(R, 1))
+    gb = b.named_grads()
+    lb = b.losses()
+    torch.cuda.synchronize()
+    fwd = {}
+    for k in ("x_tilde", "mu", "kl", "mse"):
+        fwd[k + "_first"] = rel(ob[k][:B0], oa[k].cpu())
+        fwd[k + "_last"] = rel(ob[k][-B0:], oa[k].cpu())
+    lerr = {k: abs(lb[k] / R - la[k]) / abs(la[k]) for k in ("loss_encoder", "loss_decoder", "loss_discriminator", "kl", "mse")}
+    gerr = {}
+    for pre in ("encoder.", "decoder.", "discriminator."):
+        ks = [k for k in ga if k.startswith(pre)]
+        gerr[pre] = rel(torch.cat([gb[k].reshape(-1) for k in ks]) / R, torch.cat([ga[k].reshape(-1) for k in ks]).cpu())
+    print("tiling property: forward", fwd, "losses", lerr, "grad buckets", gerr)
+    assert max(fwd.values()) < 2e-2, fwd
+    assert max(lerr.values()) < 1e-2, lerr
+    # measured: forward 1e-4..6e-3, loss sums 1e-5, gradient buckets 0.16 / 0.13 / 0.02 -- the end-to-end bf16 gradient noise of
+    # two different accumulation orders (ReLU-mask flips, the same 0.06..0.2 the bf16 path shows against the oracle)
+    assert max(gerr.values()) < 0.3, gerr
+    assert all(torch.isfinite(v).all() for v in gb.values())
