@@ -179,8 +179,19 @@ def synthetic_noise(B, z, seed=1234):
 
 
 # ---------------------------------------------------------------------------------------------------- layers
-def _bn(P, S, pre, x, train):
+def _tap(taps, key, t):
+    """Record an intermediate tensor for the teacher-forced backward tests (tests/test_teacher_forced_gpu.py)."""
+    if taps is not None:
+        taps[key] = t.detach()
+
+
+def _bn(P, S, pre, x, train, taps=None):
     """nn.BatchNorm{1,2}d(momentum=0.9): batch statistics in train mode, in-place running-stat update."""
+    if taps is not None and train:
+        dims = [d for d in range(x.dim()) if d != 1]
+        _tap(taps, pre + "raw", x)
+        _tap(taps, pre + "mean", x.mean(dims))
+        _tap(taps, pre + "invstd", (x.var(dims, unbiased=False) + BN_EPS).rsqrt())
     y = F.batch_norm(x, S[pre + "running_mean"], S[pre + "running_var"], P[pre + "weight"], P[pre + "bias"], train,
                      BN_MOMENTUM, BN_EPS)
     if train:
@@ -188,61 +199,73 @@ def _bn(P, S, pre, x, train):
     return y
 
 
-def _enc_block(P, S, pre, x, train):
+def _enc_block(P, S, pre, x, train, taps=None):
     """EncoderBlock.forward (models/vae_gan.py:23-35): conv 5x5 s2 p2 (no bias) -> BN -> ReLU; also returns the raw conv."""
+    _tap(taps, pre + "in", x)
     raw = F.conv2d(x, P[pre + "conv.weight"], None, stride=2, padding=2)
-    return F.relu(_bn(P, S, pre + "bn.", raw, train)), raw
+    return F.relu(_bn(P, S, pre + "bn.", raw, train, taps)), raw
 
 
-def encoder(P, S, x, cfg, train=True, pre="encoder."):
+def encoder(P, S, x, cfg, train=True, pre="encoder.", taps=None):
     """Encoder.forward (models/vae_gan.py:87-93)."""
     h = x
     for i in range(3):
-        h, _ = _enc_block(P, S, f"{pre}conv.{i}.", h, train)
+        h, _ = _enc_block(P, S, f"{pre}conv.{i}.", h, train, taps)
     h = h.reshape(len(h), -1)
-    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(h, P[pre + "fc.0.weight"]), train))
+    _tap(taps, pre + "fc.in", h)
+    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(h, P[pre + "fc.0.weight"]), train, taps))
+    _tap(taps, pre + "h", h)
     mu = F.linear(h, P[pre + "l_mu.weight"], P[pre + "l_mu.bias"])
     logvar = F.linear(h, P[pre + "l_var.weight"], P[pre + "l_var.bias"])
     return mu, logvar
 
 
-def cognitive_encoder(P, S, v, train=True, pre="encoder."):
+def cognitive_encoder(P, S, v, train=True, pre="encoder.", taps=None):
     """CognitiveEncoder.forward (models/vae_gan.py:224-229)."""
-    h = F.relu(_bn(P, S, pre + "fc1.1.", F.linear(v, P[pre + "fc1.0.weight"]), train))
+    h = F.relu(_bn(P, S, pre + "fc1.1.", F.linear(v, P[pre + "fc1.0.weight"]), train, taps))
+    _tap(taps, pre + "h", h)
     return (F.linear(h, P[pre + "l_mu.weight"], P[pre + "l_mu.bias"]),
             F.linear(h, P[pre + "l_var.weight"], P[pre + "l_var.bias"]))
 
 
-def decoder(P, S, z, cfg, train=True, pre="decoder."):
+def decoder(P, S, z, cfg, train=True, pre="decoder.", taps=None):
     """Decoder.forward (models/vae_gan.py:125-129) with DecoderBlock.forward (:56-60)."""
-    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(z, P[pre + "fc.0.weight"]), train))
+    _tap(taps, pre + "fc.in", z)
+    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(z, P[pre + "fc.0.weight"]), train, taps))
     h = h.reshape(len(h), -1, cfg["fc_input"], cfg["fc_input"])
     for i in range(3):
+        _tap(taps, f"{pre}conv.{i}.in", h)
         h = F.conv_transpose2d(h, P[f"{pre}conv.{i}.conv.weight"], None, stride=2, padding=2,
                                output_padding=1 if cfg["output_pad_dec"][i] else 0)
-        h = F.relu(_bn(P, S, f"{pre}conv.{i}.bn.", h, train))
+        h = F.relu(_bn(P, S, f"{pre}conv.{i}.bn.", h, train, taps))
+    _tap(taps, pre + "conv.3.in", h)
     return torch.tanh(F.conv2d(h, P[pre + "conv.3.0.weight"], P[pre + "conv.3.0.bias"], stride=1, padding=2))
 
 
-def discriminator(P, S, x_orig, x_pred, x_samp, cfg, mode="REC", train=True, recon_level=3, pre="discriminator."):
+def discriminator(P, S, x_orig, x_pred, x_samp, cfg, mode="REC", train=True, recon_level=3, pre="discriminator.",
+                  taps=None):
     """Discriminator.forward (models/vae_gan.py:163-183): "REC" returns the raw conv output of block `recon_level`
     flattened, anything else the sigmoid class score."""
     h = torch.cat((x_orig, x_pred, x_samp), 0)
     h = F.relu(F.conv2d(h, P[pre + "conv.0.0.weight"], P[pre + "conv.0.0.bias"], stride=cfg["stride_gan"], padding=2))
     for i in (1, 2, 3):
-        h, raw = _enc_block(P, S, f"{pre}conv.{i}.", h, train)
+        h, raw = _enc_block(P, S, f"{pre}conv.{i}.", h, train, taps)
         if mode == "REC" and i == recon_level:
             return raw.reshape(len(raw), -1)
     h = h.reshape(len(h), -1)
-    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(h, P[pre + "fc.0.weight"]), train))
+    _tap(taps, pre + "fc.in", h)
+    h = F.relu(_bn(P, S, pre + "fc.1.", F.linear(h, P[pre + "fc.0.weight"]), train, taps))
+    _tap(taps, pre + "h", h)
     return torch.sigmoid(F.linear(h, P[pre + "fc.3.weight"], P[pre + "fc.3.bias"]))
 
 
-def wae_discriminator(P, zs, pre="discriminator."):
+def wae_discriminator(P, zs, pre="discriminator.", taps=None):
     """WaeDiscriminator.forward (models/vae_gan.py:510-529)."""
     h = zs
     for i in (0, 2, 4, 6):
+        _tap(taps, f"{pre}main.{i}.in", h)
         h = F.relu(F.linear(h, P[f"{pre}main.{i}.weight"], P[f"{pre}main.{i}.bias"]))
+    _tap(taps, pre + "h", h)
     return torch.sigmoid(F.linear(h, P[pre + "main.8.weight"], P[pre + "main.8.bias"]))
 
 
@@ -300,7 +323,7 @@ def _leaf(P):
 
 # ---------------------------------------------------------------------------------------------------- Stage I VAE/GAN
 def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update=True, force_gate=None, mode="vae-gan",
-                       beta=1.0):
+                       beta=1.0, taps=None):
     """One iteration of train/train_vgan_stage1.py:316-432 (mode 'vae-gan').
 
     Forward = VaeGan.forward train branch (models/vae_gan.py:276-286): encoder, reparameterize, decoder(z), decoder(z_p),
@@ -312,12 +335,13 @@ def stage1_vaegan_step(P, S, x, eps, z_p, cfg=CFG64, hp=HP_VGAN, sq=None, update
     """
     W = _leaf(P)
     B = len(x)
-    mu, logvar = encoder(W, S, x, cfg)
+    tp = (lambda k: taps.setdefault(k, {})) if taps is not None else (lambda k: None)
+    mu, logvar = encoder(W, S, x, cfg, taps=tp("enc"))
     z = reparameterize(mu, logvar, eps)
-    x_tilde = decoder(W, S, z, cfg)
-    x_p = decoder(W, S, z_p, cfg)
+    x_tilde = decoder(W, S, z, cfg, taps=tp("dec1"))
+    x_p = decoder(W, S, z_p, cfg, taps=tp("dec2"))
     disc_layer = discriminator(W, S, x, x_tilde, x_p, cfg, "REC")
-    disc_class = discriminator(W, S, x, x_tilde, x_p, cfg, "GAN")
+    disc_class = discriminator(W, S, x, x_tilde, x_p, cfg, "GAN", taps=tp("dis"))
     dl_o, dl_p = disc_layer[:B], disc_layer[B:-B]
     dc_o, dc_p, dc_s = disc_class[:B], disc_class[B:-B], disc_class[-B:]
     nle, kl, mse, bce_o, bce_p, bce_s = vaegan_loss(x, x_tilde, dl_o, dl_p, dc_o, dc_p, dc_s, mu, logvar)

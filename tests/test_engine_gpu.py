@@ -566,35 +566,53 @@ def test_trainer_checkpoint_resume(kind):
 def test_full_size_batch_tiling_property():
     """BASELINE.json's full per-GPU batch (4096) through a size-independent property: a batch made of 64 copies of a 64-sample
     batch has the same BatchNorm statistics, so every replica's forward tensors equal the 64-sample step's and the loss sums /
-    gradient buckets are 64x larger. The 64-sample step runs the one-tile-per-CTA kernels, the 4096-sample step the persistent
-    kernels, the wave-split weight gradients and the parity-merged scatter with column ranges: a cross-check of the large-batch
-    code paths against the small-batch ones the oracle certifies. bf16 tensor path; tolerances cover rounding-boundary flips."""
+    gradient buckets are 64x larger. bf16 tensor path.
+
+    What bounds the comparison (measured layer by layer, scripts/layerdiff.py -> profiles/parity/r2_layerdiff_B64_vs_4096.txt):
+    a perturbation d entering a bf16 rounding step leaves it as ~sqrt(d * 2^-8) (a fraction d / ulp of the elements flips by one
+    ulp), so ANY difference -- the 1e-7 of a different fp32 summation order in a split-K GEMM or a BatchNorm mean -- grows
+    1e-7 -> 2e-5 -> 3e-4 -> 1e-3 -> 2e-3 -> 3e-3 across five layers and saturates at the bf16 storage noise (~4e-3). The same
+    64-sample step run TWICE differs by 2.9e-3 in x_tilde for that reason (non-deterministic order of fp32 atomics in the
+    encoder's split-K fc layer). The large-batch kernel paths are therefore certified per launch against torch
+    (tests/test_fullsize_kernels_gpu.py) and per step against the oracle (tests/test_baseline_sizes_gpu.py); this test checks the
+    property at the level it can hold: the tiled step may differ from the small one by no more than a small multiple of the
+    small step's own run-to-run noise, loss sums agree to 1e-3, and all replicas of the tiled batch are bit-identical."""
     B0, R, seed = 64, 64, 404
     P, S = O.make_vaegan(O.CFG64, seed=seed)
     x0 = O.synthetic_images(B0, seed=seed).cuda()
     eps0, zp0 = [t.cuda() for t in O.synthetic_noise(B0, 128, seed=seed)]
-    a = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
-    oa = a.forward_backward(x0, eps0, zp0)
-    ga = {k: v.clone() for k, v in a.named_grads().items()}
-    la = a.losses()
+
+    def small():
+        t = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
+        o = t.forward_backward(x0, eps0, zp0)
+        return o, {k: v.clone() for k, v in t.named_grads().items()}, t.losses()
+
+    oa, ga, la = small()
+    oa2, ga2, _ = small()
     b = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.bfloat16)
     ob = b.forward_backward(x0.repeat(R, 1, 1, 1), eps0.repeat(R, 1), zp0.repeat(R, 1))
     gb = b.named_grads()
     lb = b.losses()
     torch.cuda.synchronize()
-    fwd = {}
+    fwd, noise, spread = {}, {}, {}
     for k in ("x_tilde", "mu", "kl", "mse"):
+        noise[k] = rel(oa2[k], oa[k].cpu())
         fwd[k + "_first"] = rel(ob[k][:B0], oa[k].cpu())
         fwd[k + "_last"] = rel(ob[k][-B0:], oa[k].cpu())
+        spread[k] = rel(ob[k][-B0:], ob[k][:B0].cpu())
     lerr = {k: abs(lb[k] / R - la[k]) / abs(la[k]) for k in ("loss_encoder", "loss_decoder", "loss_discriminator", "kl", "mse")}
-    gerr = {}
+    gerr, gnoise = {}, {}
     for pre in ("encoder.", "decoder.", "discriminator."):
         ks = [k for k in ga if k.startswith(pre)]
-        gerr[pre] = rel(torch.cat([gb[k].reshape(-1) for k in ks]) / R, torch.cat([ga[k].reshape(-1) for k in ks]).cpu())
-    print("tiling property: forward", fwd, "losses", lerr, "grad buckets", gerr)
-    assert max(fwd.values()) < 2e-2, fwd
-    assert max(lerr.values()) < 1e-2, lerr
-    # measured: forward 1e-4..6e-3, loss sums 1e-5, gradient buckets 0.16 / 0.13 / 0.02 -- the end-to-end bf16 gradient noise of
-    # two different accumulation orders (ReLU-mask flips, the same 0.06..0.2 the bf16 path shows against the oracle)
-    assert max(gerr.values()) < 0.3, gerr
+        cat = lambda g: torch.cat([g[k].reshape(-1) for k in ks])
+        gerr[pre] = rel(cat(gb) / R, cat(ga).cpu())
+        gnoise[pre] = rel(cat(ga2), cat(ga).cpu())
+    print("tiling property: forward", fwd, "run-to-run", noise, "replica spread", spread, "losses", lerr, "grad buckets", gerr,
+          "grad run-to-run", gnoise)
+    assert max(spread.values()) == 0.0, spread          # every replica of the tiled batch computes the same values
+    for k in ("x_tilde", "mu", "kl", "mse"):            # forward: within 3x the small step's own run-to-run noise (floor 1e-3)
+        assert fwd[k + "_first"] < max(3 * noise[k], 1e-3) and fwd[k + "_first"] < 2e-2, (k, fwd, noise)
+    assert max(lerr.values()) < 1e-3, lerr
+    for pre in gerr:                                    # gradients: same, against the run-to-run bucket noise (floor 0.1)
+        assert gerr[pre] < max(3 * gnoise[pre], 0.1), (gerr, gnoise)
     assert all(torch.isfinite(v).all() for v in gb.values())

@@ -174,13 +174,18 @@ class VaeGanStage1(_TrainerBase):
     def forward_backward(self, x, eps, z_p):
         """x [B,3,H,W] fp32 NCHW, eps / z_p [B,z] fp32, all on the device. Leaves gradients in the buckets' flat_g and the
         loss sums in self.sc. Returns a dict of the forward tensors (device)."""
-        hp, B, z = self.hp, x.shape[0], self.z
-        lam = float(hp["lambda_mse"])
+        st = self.forward(x, eps, z_p)
+        self.backward(st)
+        return st.out
+
+    def forward(self, x, eps, z_p):
+        """Forward + losses (vae_gan.py:276-286, 302-320; train_vgan_stage1.py:369-372). Returns the saved state the backward
+        consumes (tests/test_teacher_forced_gpu.py overwrites it with the oracle's activations before calling backward)."""
+        B, z = x.shape[0], self.z
         be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
         Se, Sd, Sc = self.Ssub["encoder."], self.Ssub["decoder."], self.Ssub["discriminator."]
         nbe, nbd, nbc = {}, {}, {}
         sc = self.sc
-        # ------------------------------------------------------------------ forward (vae_gan.py:276-286)
         ycat, ce = self.enc.forward(be.P, Se, x, True, self._enc_bn_updates, nbe)
         mu, lv = ycat[:, :z], ycat[:, z:]
         zz, kl = E(B, z), E(B)
@@ -206,7 +211,17 @@ class VaeGanStage1(_TrainerBase):
         L.vecsum(mse, B, 1.0, sc[4:5])
         L.vecsum(nle, B, 1.0, sc[5:6])
         self._allreduce_async([sc[:8]])  # global loss sums: the gate must agree on every rank
-        # ------------------------------------------------------------------ backward
+        out = dict(x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, z=zz, kl=kl, mse=mse,
+                   bce=bce, nle=nle)
+        return NN.Ctx(B=B, eps=eps, ce=ce, cd1=cd1, cd2=cd2, cc=cc, raw3=raw3, p=p, mu=mu, lv=lv, out=out)
+
+    def backward(self, st):
+        """The three used gradients from the saved forward state, as four sweeps."""
+        hp, B, z = self.hp, st.B, self.z
+        lam = float(hp["lambda_mse"])
+        be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
+        ce, cd1, cd2, cc, raw3, p, mu, lv, eps = st.ce, st.cd1, st.cd2, st.cc, st.raw3, st.p, st.mu, st.lv, st.eps
+        Fd = raw3[0].numel()
         # (1) discriminator, class-score path: g_dis = d loss_discriminator / d discriminator, plus d loss_dis / d(x_tilde, x_p)
         gp = E(3 * B)
         ones = self._ones(3 * B)
@@ -232,8 +247,7 @@ class VaeGanStage1(_TrainerBase):
         self._before_encoder_backward(mu, dycat)   # hook: DualWaeVaeGanStage1 adds the latent penalty gradient here
         self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
         self._allreduce_async([be.flat_g])
-        return dict(x_tilde=x_tilde, x_p=x_p, disc_layer_nhwc=raw3, disc_class=p, mu=mu, logvar=lv, z=zz, kl=kl, mse=mse,
-                    bce=bce, nle=nle)
+        st.sweeps = dict(dimg_bce=dimg_bce, dimg_mse=dimg_mse, dz=dz, dycat=dycat)
 
     _enc_bn_updates = 1
 
