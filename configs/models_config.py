@@ -28,4 +28,9 @@ def use_resolution(size):
     return size
 
 
-use_resolution(100)
+import os as _os
+
+# The reference selects the resolution by editing this file (active block :13-21 = 100x100 / latent 512; commented block
+# :23-31 = 64x64 / latent 128). Here the default is the reference's active block, and FMRI_MODELS_CONFIG=64 selects the other
+# one for an unchanged script (the WAE scripts' defaults, configs/wae_config.py:6-7, are the 64x64 ones).
+use_resolution(int(_os.environ.get("FMRI_MODELS_CONFIG", "100")))

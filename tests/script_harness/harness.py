@@ -72,6 +72,12 @@ def make_tree(root, n_train=8, n_test=8, n_valid=8, n_bold_train=16, n_bold_vali
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "wb") as f:
             pickle.dump(items, f)
+    # fixed stimulus split (data_config.py: train_stimuli_split / valid_stimuli_split): lists of image file names
+    for rel, items in (("BOLD5000/bold_roi/stimuli_train.pickle", sets["train"]), ("BOLD5000/bold_roi/stimuli_valid.pickle", sets["valid"])):
+        p = os.path.join(ds, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        with open(p, "wb") as f:
+            pickle.dump([os.path.basename(it["image"]) for it in items], f)
     os.makedirs(os.path.join(root, "logs"), exist_ok=True)
     return root
 

@@ -435,3 +435,45 @@ def test_pixel_nle_modes_and_dcgan_module_fp32():
     errs = dict(x_tilde=rel(x_gen, xg), disc_class=rel(d_class, dc2), disc_layer=rel(d_layer, dl2))
     print("DCGan forward", errs)
     assert max(errs.values()) < 1e-4, errs
+
+
+def test_module_path_frees_saved_state_without_gc():
+    """the decoder Function once kept its own output on the saved state (output -> grad_fn -> ctx -> output), a
+    reference cycle only the cyclic GC frees. With the collector disabled, repeated script-style steps must not grow the
+    allocation: refcounting alone releases every call's saved activations and operand packs."""
+    import gc
+
+    from models.vae_gan import VaeGan
+
+    B, seed = 16, 5
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed).cuda()
+    with compute(torch.bfloat16):
+        model = build_vaegan(P, S)
+        model.train()
+        opt = torch.optim.RMSprop(model.parameters(), lr=1e-4, alpha=0.9, eps=1e-8)
+
+        def one():
+            x_tilde, disc_class, disc_layer, mus, lv = model(x)
+            nle, kld, mse, bo, bp, bs = VaeGan.loss(x, x_tilde, disc_layer[:B], disc_layer[B:-B], disc_layer[-B:],
+                                                    disc_class[:B], disc_class[B:-B], disc_class[-B:], mus, lv)
+            loss = torch.sum(kld) + torch.sum(mse) + torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+            model.zero_grad()
+            loss.backward()
+            opt.step()
+
+        gc.collect()
+        gc.disable()
+        try:
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+            m0 = torch.cuda.memory_allocated()
+            for _ in range(4):
+                one()
+            torch.cuda.synchronize()
+            m1 = torch.cuda.memory_allocated()
+        finally:
+            gc.enable()
+    print("allocated after 2 steps", m0, "after 6 steps", m1)
+    assert m1 <= m0 + (1 << 20), (m0, m1)

@@ -143,6 +143,9 @@ class _DecoderFn(torch.autograd.Function):
         nbt = {}
         img, c = net.forward(P, mod._bufs(), _cuda_f32(zin, "decoder input"), mod.training, 1, nbt)
         mod._flush_nbt(nbt)
+        # the saved state must not hold the RETURNED tensor object (output -> grad_fn -> ctx -> output is a reference cycle that
+        # only the cyclic GC frees, pinning every decoder call's activations): keep a detached alias for the tanh backward
+        c.img = img.detach()
         ctx.net, ctx.c, ctx.P, ctx.names = net, c, P, names
         return img
 
