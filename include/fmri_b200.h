@@ -149,6 +149,14 @@ int fmri_bn_apply(const void* x, int x_dtype, void* y, int y_dtype, long long ro
 int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, int C,
                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, int train,
                      float* dgamma, float* dbeta, int accumulate, double* ws, int sums_ready, void* stream);
+/* The same with dx produced for rows [row0, row0 + nrows) only (dx points at the first of them): train-mode BatchNorm couples
+ * all rows through the two sums, so those always run over the whole [rows, C] matrix, but a caller that needs the input
+ * gradient of a few samples only (the discriminator's feature-tap sweep feeds ONE of its three image sources,
+ * train_vgan_stage1.py:330-372 via vae_gan.py:163-175) skips the apply pass on the rest. */
+int fmri_bn_backward_slice(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows, long long row0,
+                           long long nrows, int C, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, int relu, int train, float* dgamma, float* dbeta, int accumulate, double* ws,
+                           int sums_ready, void* stream);
 /* bits[pixel] bit j = (y[pixel][j] > 0): ReLU mask of a channels-last bf16 tensor with exactly 32 channels, 4 B per pixel
  * (consumed by fmri_conv_dgrad through fmri_bn_fuse.mask_bits) */
 int fmri_relu_bitmask(const void* y, int dtype, long long pixels, int C, unsigned* bits, void* stream);

@@ -24,25 +24,34 @@ from thesis_fmri_reconstruction_b200.hp import cfg_from_module as _cfg
 from thesis_fmri_reconstruction_b200.lib import FmriError
 
 
-class EncoderBlock(nn.Module):
-    """Conv2d(k5, s2, p2, no bias) -> BatchNorm2d(momentum=0.9) -> ReLU (reference vae_gan.py:11-35). Parameter container;
-    the enclosing Encoder / Discriminator runs it inside its fused network."""
+class EncoderBlock(nn.Module, _ag.NetHost):
+    """Conv2d(k5, s2, p2, no bias) -> BatchNorm2d(momentum=0.9) -> ReLU (reference vae_gan.py:11-35). Inside an Encoder /
+    Discriminator the block runs in that network's fused pipeline; called on its own, forward(ten, out=False, t=False) does
+    what the reference's does: relu(bn(conv(ten))), and with out=True also the raw conv output (the feature tap, :25-30)."""
 
     def __init__(self, channel_in, channel_out):
         super(EncoderBlock, self).__init__()
+        self._host_init()
         self.conv = nn.Conv2d(in_channels=channel_in, out_channels=channel_out, kernel_size=config.kernel_size,
                               padding=config.padding, stride=config.stride, bias=False)
         self.bn = nn.BatchNorm2d(num_features=channel_out, momentum=0.9)
+        self.__dict__["_io"] = (channel_in, channel_out)
+
+    def _make_net(self, adt):
+        return _nets.BlockNet(self._io[0], self._io[1], False, 0, adt)
 
     def forward(self, ten, out=False, t=False):
-        raise FmriError("EncoderBlock is executed by its enclosing Encoder / Discriminator network; call that module")
+        return _ag.run_block(self, ten, out)
 
 
-class DecoderBlock(nn.Module):
-    """ConvTranspose2d(k5, s2, p2, output_padding=out) -> BatchNorm2d(0.9) -> ReLU (reference vae_gan.py:38-60)."""
+class DecoderBlock(nn.Module, _ag.NetHost):
+    """ConvTranspose2d(k5, s2, p2, output_padding=out) -> BatchNorm2d(0.9) -> ReLU (reference vae_gan.py:38-60); callable on
+    its own like the reference's (inside a Decoder it runs in the fused pipeline)."""
 
     def __init__(self, channel_in, channel_out, out=False):
         super(DecoderBlock, self).__init__()
+        self._host_init()
+        self.__dict__["_io"] = (channel_in, channel_out, 1 if out else 0)
         if out:
             self.conv = nn.ConvTranspose2d(channel_in, channel_out, kernel_size=config.kernel_size,
                                            padding=config.padding, stride=config.stride, output_padding=1, bias=False)
@@ -51,8 +60,11 @@ class DecoderBlock(nn.Module):
                                            padding=config.padding, stride=config.stride, bias=False)
         self.bn = nn.BatchNorm2d(channel_out, momentum=0.9)
 
+    def _make_net(self, adt):
+        return _nets.BlockNet(self._io[0], self._io[1], True, self._io[2], adt)
+
     def forward(self, ten):
-        raise FmriError("DecoderBlock is executed by its enclosing Decoder network; call that module")
+        return _ag.run_block(self, ten, False)
 
 
 class Encoder(nn.Module, _ag.NetHost):

@@ -444,6 +444,35 @@ def test_graphed_step_matches_eager():
     assert torch.isfinite(out["x_tilde"].float()).all() and all(torch.isfinite(v).all() for v in b.named_parameters().values())
 
 
+def test_graphed_step_follows_epoch_schedule():
+    """learning rates and gate constants are host scalars baked into the captured launches; after end_epoch()
+    (ExponentialLR 0.98, train_vgan_stage1.py:446-457) a replay must use the NEW values, i.e. equal the eager step."""
+    B, seed = 8, 32
+    P, S = O.make_vaegan(O.CFG64, seed=seed)
+    x = O.synthetic_images(B, seed=seed).cuda()
+    eps, z_p = [t.cuda() for t in O.synthetic_noise(B, 128, seed=seed)]
+    a = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
+    b = engine.VaeGanStage1(P, S, hp.CFG64, 128, torch.float32)
+    g = engine.GraphedStep(b, x, eps, z_p, warmup=2)
+    for _ in range(2):
+        a.step(x, eps, z_p)
+    for t in (a, b):
+        for _ in range(25):                      # 0.98^25 = 0.60: a stale learning rate would be far outside the bound
+            t.end_epoch(decay_margin=0.99, decay_equilibrium=0.99)
+    b.load_state_dict(a.state_dict())
+    before = {k: v.clone() for k, v in a.named_parameters().items()}
+    a.step(x, eps, z_p)
+    g(x, eps, z_p)
+    torch.cuda.synchronize()
+    assert g.recaptures >= 1
+    pa, pb = a.named_parameters(), b.named_parameters()
+    da = torch.cat([(pa[k] - before[k]).reshape(-1) for k in pa])
+    db = torch.cat([(pb[k] - before[k]).reshape(-1) for k in pa])
+    print("graphed vs eager parameter DELTA after end_epoch x25: rel", rel(db, da), "recaptures", g.recaptures)
+    assert rel(db, da) < 5e-2      # deltas scale with lr: a replay at the stale lr would be off by 0.67
+    assert (a.losses()["train_dis"], a.losses()["train_dec"]) == (b.losses()["train_dis"], b.losses()["train_dec"])
+
+
 def test_stage1_beta_vae_mode_fp32():
     """The 'beta-vae' loss mix of train/train_vgan_stage1.py:359-365 (KL weighted by beta / batch_size): engine vs the oracle
     (pinned to the reference by tests/golden/stage1_betavae_*). Only the encoder bucket and loss_encoder differ from 'vae-gan'."""

@@ -477,3 +477,166 @@ def test_module_path_frees_saved_state_without_gc():
             gc.enable()
     print("allocated after 2 steps", m0, "after 6 steps", m1)
     assert m1 <= m0 + (1 << 20), (m0, m1)
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_discriminator_recon_level_1_and_2_fp32(level):
+    """Discriminator(recon_level=1|2) (reference vae_gan.py:166-175): "REC" returns the raw conv output of block `level`
+    and stops there (later blocks neither run nor update their BatchNorm statistics). Output, input gradients, parameter
+    gradients and BN buffers against the oracle; fp32 exact path, 1e-4 forward / 5e-3 gradients."""
+    from models.vae_gan import Discriminator
+
+    B, seed = 4, 17
+    mc.use_resolution(64)
+    P, S = O.make_net("discriminator.", O.discriminator_spec(O.CFG64), seed)
+    xs = [O.synthetic_images(B, seed=seed + i) for i in range(3)]
+    W = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    S64 = {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in S.items()}
+    xr = [t.double().requires_grad_(True) for t in xs]
+    ref = O.discriminator(W, S64, xr[0], xr[1], xr[2], O.CFG64, "REC", recon_level=level)
+    g = torch.Generator().manual_seed(seed)
+    up = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    names = list(W)
+    gs = torch.autograd.grad((ref * up).sum(), [W[n] for n in names] + xr, allow_unused=True)
+    with compute(torch.float32):
+        m = Discriminator(channel_in=3, recon_level=level).cuda()
+        m.load_state_dict({k[len("discriminator."):]: v for k, v in {**P, **S}.items()}, strict=True)
+        m.train()
+        xd = [t.cuda().requires_grad_(True) for t in xs]
+        out = m(xd[0], xd[1], xd[2], "REC")
+        assert out.shape == ref.shape
+        (out * up.float().cuda()).sum().backward()
+        torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-4
+    for i in range(3):
+        assert rel(xd[i].grad, gs[len(names) + i]) < 5e-3, i
+    mp = dict(m.named_parameters())
+    for n, gr in zip(names, gs[:len(names)]):
+        k = n[len("discriminator."):]
+        if gr is None:      # blocks above the tap and the head take no part in this pass
+            assert mp[k].grad is None or float(mp[k].grad.abs().max()) == 0.0, k
+        else:
+            assert rel(mp[k].grad, gr) < 5e-3, k
+    sd = m.state_dict()
+    for k, v in S64.items():
+        kk = k[len("discriminator."):]
+        if v.dtype.is_floating_point:
+            assert rel(sd[kk], v) < 1e-4, kk
+        else:
+            assert int(sd[kk]) == int(v), kk      # num_batches_tracked: 1 up to the tap, 0 above it
+
+
+@pytest.mark.parametrize("kind,cin,cout,dtype", [("enc", 32, 128, torch.bfloat16), ("enc", 3, 64, torch.bfloat16),
+                                                 ("enc", 64, 128, torch.float32), ("dec", 128, 32, torch.bfloat16),
+                                                 ("dec", 256, 128, torch.float32)])
+def test_standalone_blocks(kind, cin, cout, dtype):
+    """EncoderBlock.forward(ten, out=True) / DecoderBlock.forward(ten) called ON THEIR OWN, as the reference's modules can be
+    (vae_gan.py:23-35, 56-60), against plain PyTorch: outputs, the raw-conv feature tap, input / parameter gradients, BN
+    running statistics. A 3-channel input is not tiled by the tensor path and runs on the exact fp32 path."""
+    import torch.nn.functional as F
+
+    from models.vae_gan import DecoderBlock, EncoderBlock
+
+    N, H = 4, 16
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    exact = dtype == torch.float32 or cin == 3
+    rnd = (lambda t: t) if exact else (lambda t: t.bfloat16().float())
+    x = rnd(torch.randn(N, cin, H, H, generator=g))
+    with compute(dtype):
+        m = (EncoderBlock(cin, cout) if kind == "enc" else DecoderBlock(cin, cout, out=True)).cuda()
+        with torch.no_grad():
+            m.conv.weight.copy_(rnd(m.conv.weight.cpu()))
+            m.bn.weight.add_(0.1 * torch.randn(cout, generator=g).cuda())
+            m.bn.bias.add_(0.1 * torch.randn(cout, generator=g).cuda())
+        w, gamma, beta = (t.detach().cpu().double().requires_grad_(True) for t in (m.conv.weight, m.bn.weight, m.bn.bias))
+        xr = x.double().requires_grad_(True)
+        if kind == "enc":
+            raw = F.conv2d(xr, w, stride=2, padding=2)
+        else:
+            raw = F.conv_transpose2d(xr, w, stride=2, padding=2, output_padding=1)
+        rm, rv = torch.zeros(cout, dtype=torch.float64), torch.ones(cout, dtype=torch.float64)
+        ref = torch.relu(F.batch_norm(raw, rm, rv, gamma, beta, True, 0.9, 1e-5))
+        up = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+        up_raw = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+        m.train()
+        xd = x.cuda().requires_grad_(True)
+        if kind == "enc":
+            y, tap = m(xd, True)
+            loss_ref = (ref * up).sum() + (raw * up_raw).sum()
+            (y * up.float().cuda()).sum().add((tap * up_raw.float().cuda()).sum()).backward()
+        else:
+            y, tap = m(xd), None
+            loss_ref = (ref * up).sum()
+            (y * up.float().cuda()).sum().backward()
+        gx, gw, gg, gb = torch.autograd.grad(loss_ref, (xr, w, gamma, beta))
+        torch.cuda.synchronize()
+    ft, gt = (1e-4, 2e-3) if exact else (4e-3, 2e-2)
+    assert rel(y, ref) < ft
+    if tap is not None:
+        assert rel(tap, raw) < ft
+    errs = dict(dx=rel(xd.grad, gx), dw=rel(m.conv.weight.grad, gw), dgamma=rel(m.bn.weight.grad, gg), dbeta=rel(m.bn.bias.grad, gb))
+    print(kind, cin, cout, dtype, errs)
+    assert max(errs.values()) < gt, errs
+    assert rel(m.bn.running_mean, rm) < max(ft, 1e-3) and rel(m.bn.running_var, rv) < max(ft, 1e-3)
+    assert int(m.bn.num_batches_tracked) == 1
+    m.eval()
+    with compute(dtype), torch.no_grad():
+        ye = m(xd) if kind == "dec" else m(xd, False)
+    ref_e = torch.relu(F.batch_norm(raw.detach(), rm, rv, gamma.detach(), beta.detach(), False, 0.9, 1e-5))
+    assert rel(ye, ref_e) < max(ft, 1e-3)
+
+
+def test_vaegan_cognitive_wae_mode_fp32():
+    """VaeGanCognitive(mode='wae') (reference vae_gan.py:379-387): x_tilde = decoder(mu_cog), gt_x = decoder(mu_teacher) with
+    NO sampling, then the same discriminator passes. Forward tensors and the cognitive-encoder gradient of the feature-matching
+    loss against the oracle's functions; fp32 exact path."""
+    from models.vae_gan import CognitiveEncoder, VaeGan, VaeGanCognitive
+
+    B, seed = 4, 23
+    mc.use_resolution(64)
+    P, S = O.make_cognitive(O.CFG64, seed=seed)
+    fmri, image = O.synthetic_fmri(B, seed=seed), O.synthetic_images(B, seed=seed)
+    z_p = O.synthetic_noise(B, 128, seed=seed)[1]
+    W = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    S64 = {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in S.items()}
+    mu, lv = O.cognitive_encoder(W, S64, fmri.double())
+    x_t = O.decoder(W, S64, mu, O.CFG64)
+    mu_t, _ = O.encoder(W, S64, image.double(), O.CFG64, pre="teacher_net.encoder.")
+    gt = O.decoder(W, S64, mu_t, O.CFG64)
+    x_p = O.decoder(W, S64, z_p.double(), O.CFG64)
+    dl = O.discriminator(W, S64, gt, x_t, x_p, O.CFG64, "REC")
+    dc = O.discriminator(W, S64, gt, x_t, x_p, O.CFG64, "GAN")
+    mse_ref = torch.sum(0.5 * (dl[:B] - dl[B:2 * B]) ** 2)
+    enc_names = [k for k in W if k.startswith("encoder.")]
+    g_ref = dict(zip(enc_names, torch.autograd.grad(mse_ref, [W[k] for k in enc_names], allow_unused=True)))
+    with compute(torch.float32):
+        teacher = VaeGan(device="cuda", z_size=128)
+        teacher.load_state_dict({k[len("teacher_net."):]: v for k, v in {**P, **S}.items() if k.startswith("teacher_net.")},
+                                strict=False)
+        cog = CognitiveEncoder(input_size=fmri.shape[1], z_size=128).cuda()
+        model = VaeGanCognitive(device="cuda", encoder=cog, decoder=teacher.decoder, discriminator=teacher.discriminator,
+                                teacher_net=teacher, stage=2, z_size=128, mode="wae").cuda()
+        own = {k: v for k, v in {**P, **S}.items() if not k.startswith("teacher_net.")}
+        sd = model.state_dict()
+        sd.update({k: v for k, v in own.items() if k in sd})
+        sd.update({k: v for k, v in {**P, **S}.items() if k in sd and k.startswith("teacher_net.encoder.")})
+        # decoder / discriminator are shared objects: teacher_net.decoder.* aliases decoder.*
+        for k in list(sd):
+            for a, b in (("teacher_net.decoder.", "decoder."), ("teacher_net.discriminator.", "discriminator.")):
+                if k.startswith(a) and b + k[len(a):] in own:
+                    sd[k] = own[b + k[len(a):]]
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        with patched_randn(z_p):
+            gt_x, x_tilde, disc_class, disc_layer, mus, log_variances = model({"fmri": fmri, "image": image})
+        mse = ag.row_sq_diff(disc_layer[:B], disc_layer[B:2 * B], 0.5).sum()
+        model.zero_grad()
+        mse.backward()
+        torch.cuda.synchronize()
+    fwd = dict(gt_x=rel(gt_x, gt), x_tilde=rel(x_tilde, x_t), disc_layer=rel(disc_layer, dl), disc_class=rel(disc_class, dc),
+               mus=rel(mus, mu), logvar=rel(log_variances, lv), mse=rel(mse, mse_ref))
+    print("VaeGanCognitive wae mode", fwd)
+    assert max(fwd.values()) < 1e-4, fwd
+    ge = {k: rel(dict(model.named_parameters())[k].grad, g) for k, g in g_ref.items() if g is not None}
+    print(ge)
+    assert ge and max(ge.values()) < 5e-3, ge

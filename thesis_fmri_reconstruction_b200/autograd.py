@@ -133,6 +133,43 @@ class _EncoderFn(torch.autograd.Function):
         return (None, None) + tuple(G[n] if need else None for n, need in zip(ctx.names, needs))
 
 
+# ====================================================================================================== standalone blocks
+class _BlockFn(torch.autograd.Function):
+    """EncoderBlock.forward(ten, out) / DecoderBlock.forward(ten) called on their own (vae_gan.py:23-35, 56-60)."""
+
+    @staticmethod
+    def forward(ctx, mod, want_raw, x, *params):
+        names, _ = _params_of(mod)
+        P = dict(zip(names, (p.detach() for p in params)))
+        net = mod._net(P)
+        nbt = {}
+        y, raw, c = net.forward(P, mod._bufs(), _cuda_f32(x, "block input"), mod.training, want_raw, nbt)
+        mod._flush_nbt(nbt)
+        ctx.net, ctx.c, ctx.P, ctx.names, ctx.want_raw = net, c, P, names, want_raw
+        ctx.set_materialize_grads(False)
+        if want_raw:
+            return y, raw
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, draw=None):
+        needs = ctx.needs_input_grad[3:]
+        need_dw = any(needs)
+        G = {n: torch.zeros_like(ctx.P[n]) for n in ctx.names}
+        f = lambda t: None if t is None else t.to(F32).contiguous()
+        if dy is None and draw is None:
+            return (None, None, None) + tuple(None for _ in needs)
+        dx = ctx.net.backward(ctx.P, ctx.c, f(dy), f(draw), G, need_dw, ctx.needs_input_grad[2])
+        NN.join_side()
+        return (None, None, dx) + tuple(G[n] if need else None for n, need in zip(ctx.names, needs))
+
+
+def run_block(mod, x, want_raw):
+    _on_cuda(mod, x)
+    _, params = _params_of(mod)
+    return _BlockFn.apply(mod, bool(want_raw), x, *params)
+
+
 # ====================================================================================================== decoder
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
@@ -182,10 +219,11 @@ class _DiscriminatorFn(torch.autograd.Function):
         mod._flush_nbt(nbt)
         ctx.net, ctx.c, ctx.P, ctx.names, ctx.rec = net, c, P, names, rec
         N = c.N
-        h, w = c.hw
         if rec:
-            out = torch.empty(N, net.Cl * h * w, dtype=F32, device=raw3.device)
-            L.nhwc_to_nchw(raw3, out, N, net.Cl, h, w)  # layer_ten.view(len, -1) of an NCHW tensor (vae_gan.py:173)
+            _, h, w, Ct = raw3.shape
+            out = torch.empty(N, Ct * h * w, dtype=F32, device=raw3.device)
+            L.nhwc_to_nchw(raw3, out, N, Ct, h, w)  # layer_ten.view(len, -1) of an NCHW tensor (vae_gan.py:173)
+            ctx.tap_shape = (h, w, Ct)
             return out
         return p.view(N, 1)
 
@@ -197,10 +235,10 @@ class _DiscriminatorFn(torch.autograd.Function):
         sl = _slices_needed(ctx.needs_input_grad[2:5])
         G = {n: torch.zeros_like(P[n]) for n in ctx.names} if need_dw else None
         N = c.N
-        h, w = c.hw
         if ctx.rec:
-            draw3 = torch.empty(N, h, w, net.Cl, dtype=net.adt, device=g.device)
-            L.nchw_to_nhwc(g.to(F32).contiguous(), draw3, N, net.Cl, h, w)
+            h, w, Ct = ctx.tap_shape
+            draw3 = torch.empty(N, h, w, Ct, dtype=net.adt, device=g.device)
+            L.nchw_to_nhwc(g.to(F32).contiguous(), draw3, N, Ct, h, w)
             dimg = net.backward_rec(P, c, draw3, G, False, need_dw, sl)
         else:
             dimg = net.backward_gan(P, c, g.to(F32).contiguous().view(-1), G, False, need_dw, sl)

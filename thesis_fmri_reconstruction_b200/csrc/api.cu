@@ -1556,7 +1556,9 @@ static int bn_bwd_sums(const void* x, int x_dtype, const void* dy, int g_dtype, 
 template <typename Tx, typename Tg>
 static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int C, const float* mean,
                     const float* invstd, const float* gamma, const float* beta, int relu, int train, float* dgamma,
-                    float* dbeta, int accumulate, double* ws, int sums_ready, cudaStream_t st) {
+                    float* dbeta, int accumulate, double* ws, int sums_ready, cudaStream_t st, long long row0 = 0,
+                    long long nrows = -1) {
+    // [row0, row0 + nrows): the rows dx is produced for (dx points at the first of them); the sums always run over all rows
     if (!sums_ready) {
         int rc = bn_bwd_reduce_t<Tx, Tg>(x, dy, rows, C, mean, invstd, gamma, beta, relu, ws, st);
         if (rc) return rc;
@@ -1565,6 +1567,12 @@ static int bn_bwd_t(const void* x, const void* dy, void* dx, long long rows, int
     float* mean_gx = mean_g + C;
     bn_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, ws + C, (double)rows, C, mean_g, mean_gx, dgamma, dbeta, accumulate);
     LAUNCH_OK();
+    if (nrows >= 0) {
+        x = reinterpret_cast<const Tx*>(x) + row0 * C;
+        dy = reinterpret_cast<const Tg*>(dy) + row0 * C;
+        rows = nrows;
+        if (rows == 0) return 0;
+    }
     if (dx && C % 2 == 0 && ((C / 2) >= 256 ? (C / 2) % 256 == 0 : 256 % (C / 2) == 0)) {
         const int ry = std::max(1, 256 / (C / 2));
         static int occ2 = 0;
@@ -1601,6 +1609,23 @@ extern "C" int fmri_bn_backward(const void* x, int x_dtype, const void* dy, void
     if (x_dtype == FMRI_F32 && g_dtype == FMRI_F32)
         return bn_bwd_t<float, float>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
                                       accumulate, ws, sums_ready, S(stream));
+    return fail(FMRI_ERR_UNSUPPORTED, "bn_backward dtype combination");
+}
+extern "C" int fmri_bn_backward_slice(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, long long rows,
+                                      long long row0, long long nrows, int C, const float* mean, const float* invstd,
+                                      const float* gamma, const float* beta, int relu, int train, float* dgamma,
+                                      float* dbeta, int accumulate, double* ws, int sums_ready, void* stream) {
+    if (C < 256 && (256 % C)) return fail(FMRI_ERR_UNSUPPORTED, "bn_backward C=%d", C);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > rows) return fail(FMRI_ERR_ARG, "bn_backward_slice: bad row range");
+    if (x_dtype == FMRI_BF16 && g_dtype == FMRI_BF16)
+        return bn_bwd_t<__nv_bfloat16, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train,
+                                                      dgamma, dbeta, accumulate, ws, sums_ready, S(stream), row0, nrows);
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_BF16)
+        return bn_bwd_t<float, __nv_bfloat16>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
+                                              accumulate, ws, sums_ready, S(stream), row0, nrows);
+    if (x_dtype == FMRI_F32 && g_dtype == FMRI_F32)
+        return bn_bwd_t<float, float>(x, dy, dx, rows, C, mean, invstd, gamma, beta, relu, train, dgamma, dbeta,
+                                      accumulate, ws, sums_ready, S(stream), row0, nrows);
     return fail(FMRI_ERR_UNSUPPORTED, "bn_backward dtype combination");
 }
 extern "C" int fmri_relu_backward(const void* y, const void* dy, void* dx, int dtype, long long n, void* stream) {

@@ -42,7 +42,7 @@ class _TrainerBase:
             import torch.distributed as td
 
             self.td = td
-            self.world = td.get_world_size()
+            self.world = td.get_world_size(group=dist_group)
             self.comm_stream = torch.cuda.Stream()
 
     def _allreduce_async(self, tensors):
@@ -54,7 +54,7 @@ class _TrainerBase:
         NN.side_into(self.comm_stream)   # weight gradients are produced on nets' side stream
         with torch.cuda.stream(self.comm_stream):
             for t in tensors:
-                self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+                self.td.all_reduce(t, op=self.td.ReduceOp.SUM, group=self.dist)
                 t.record_stream(self.comm_stream)
 
     def _wait_comm(self):
@@ -233,7 +233,7 @@ class VaeGanStage1(_TrainerBase):
         draw3 = torch.empty_like(raw3)
         draw3[2 * B:].zero_()
         L.rowsqdiff_bwd(raw3[:B], raw3[B:2 * B], ones, draw3[:B], draw3[B:2 * B], B, Fd, 0.5)
-        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2))
+        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2), live=(0, 2))
         # (3) decoder: g_dec = d [lambda * mse - (1 - lambda) * loss_dis] / d decoder over both decoder calls
         self.dec.backward(bd.P, cd1, lam, dimg_mse, -(1.0 - lam), dimg_bce[:B], bd.G, False, True, False)
         self.dec.backward(bd.P, cd2, -(1.0 - lam), dimg_bce[B:], 0.0, None, bd.G, True, True, False)
@@ -547,7 +547,7 @@ class VaeGanCognitiveStage(_TrainerBase):
         draw3 = torch.empty_like(raw3)
         draw3[2 * B:].zero_()
         L.rowsqdiff_bwd(raw3[:B], raw3[B:2 * B], ones, draw3[:B], draw3[B:2 * B], B, Fd, 0.5)
-        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2))
+        dimg_mse = self.dis.backward_rec(bc.P, cc, draw3, None, False, False, (1, 2), live=(0, 2))
         if stage == 2:
             dz = self.dec.backward(bd.P, cd1, 1.0, dimg_mse, 0.0, None, None, False, False, True)
             dycat = E(B, 2 * z, dtype=self.adt)
@@ -799,6 +799,14 @@ class GraphedStep:
             for _ in range(warmup):
                 trainer.step(*self.static)
         cur.wait_stream(side)
+        self.recaptures = -1
+        self._capture()
+
+    def _capture(self):
+        """Capture one step. Learning rates, margin / equilibrium and lambda_mse are HOST scalars baked into the captured
+        kernel arguments, so the values captured are remembered and __call__ re-captures when the trainer's differ
+        (end_epoch() and load_state_dict() change them: ExponentialLR 0.98 per epoch, train_vgan_stage1.py:446-457)."""
+        trainer = self.tr
         torch.cuda.synchronize()
         nbt0 = dict(trainer.nbt)
         n0 = L.launch_count()
@@ -808,8 +816,12 @@ class GraphedStep:
         self.launches = L.launch_count() - n0           # kernels per replay (the host counter only saw the capture)
         self.nbt_inc = {k: v - nbt0.get(k, 0) for k, v in trainer.nbt.items()}
         trainer.nbt = nbt0                               # the capture itself executed nothing
+        self.captured = (dict(trainer.lr), dict(trainer.hp))
+        self.recaptures += 1
 
     def __call__(self, *inputs):
+        if (self.tr.lr, self.tr.hp) != self.captured:
+            self._capture()
         for s, t in zip(self.static, inputs):
             if s is not None and t is not s:
                 s.copy_(t, non_blocking=True)
@@ -886,6 +898,7 @@ class DualWaeVaeGanStage1(VaeGanStage1):
         L.bce_bwd(p2, ones, gp[:B], B, True, lam)
         dz_pen = self.ldis.backward(bl.P, c2, gp[:B], None, False, False, True)
         dycat[:, :z].add_(dz_pen.to(dycat.dtype))   # :421 the encoder sweep accumulates onto the penalty gradient
+        self._allreduce_async([self.lsc])   # logged sums are global, like sc[0..5] (waited on in update())
         self._d = dict(z_real=mu, d_real=p_real, d_fake=p_fake, d_real_g=p2)
 
     def forward_backward(self, x, eps, z_p, z_fake):

@@ -29,15 +29,17 @@ def cfg_from_module(mc):
 
 def epoch_end_vgan(lr, hp, decay_lr=0.98, decay_margin=1.0, decay_equilibrium=1.0, decay_mse=1.0):
     """End-of-epoch schedule of the VAE/GAN scripts (train_vgan_stage1.py:446-457; defaults gan_config.py:26-31):
-    ExponentialLR(gamma=decay_lr) on every optimizer, margin / equilibrium decay with equilibrium >= margin, lambda_mse growth
-    capped at 1. `lr`: {bucket prefix: learning rate}; `hp`: the trainer's hyper-parameter dict. Both are updated in place."""
+    ExponentialLR(gamma=decay_lr) on every optimizer, margin / equilibrium decay with equilibrium >= margin. lambda_mse is NOT
+    changed: the reference only scales a local variable that its loss never reads (hp["lambda_mse_local"] mirrors it). `lr`: {bucket prefix: learning rate}; `hp`: the trainer's hyper-parameter dict. Both are updated in place."""
     for k in lr:
         lr[k] *= decay_lr
     hp["margin"] *= decay_margin
     hp["equilibrium"] *= decay_equilibrium
     if hp["margin"] > hp["equilibrium"]:
         hp["equilibrium"] = hp["margin"]
-    hp["lambda_mse"] = min(1.0, hp["lambda_mse"] * decay_mse)
+    # The script decays a LOCAL copy of lambda_mse (:456-458) while its loss mix keeps reading the constant args.lambda_mse
+    # (:372): the weight the step uses never changes. The decayed copy is kept under its own key, for logging only.
+    hp["lambda_mse_local"] = min(1.0, hp.get("lambda_mse_local", hp["lambda_mse"]) * decay_mse)
 
 
 def epoch_end_wae(lr, epoch, step_size=30, decay_lr=0.5):

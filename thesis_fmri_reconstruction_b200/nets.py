@@ -150,6 +150,23 @@ class ConvBlock:
         draw = self.bn.backward(P, c.bn, dy, G, acc, need_dw, sums_ready)
         return self.backward_raw(P, c, draw, G, acc, need_dw, need_dx, fuse)
 
+    def backward_dx_slice(self, P, c, dy, n0, n1, fuse=None):
+        """Data gradient only, for images [n0, n1) of the batch. Train-mode BatchNorm couples all samples through its two
+        backward sums, so those run over the whole batch; the BN apply pass and the conv data gradient run on the slice only
+        (the discriminator's feature-tap sweep needs the image gradient of ONE of its three sources). Returns dx of the slice."""
+        C, pre, cb = self.Cout, self.prefix + "bn.", c.bn
+        per = c.OH * c.OW
+        N = c.d.N
+        if self.bn._ws is None:
+            self.bn._ws = E(3 * C, dtype=F64)
+        draw = E(n1 - n0, c.OH, c.OW, C, dtype=dy.dtype)
+        L.bn_backward_slice(cb.raw, dy, draw, N * per, n0 * per, (n1 - n0) * per, C, cb.mean, cb.invstd, P[pre + "weight"],
+                            P[pre + "bias"], cb.relu, cb.train, self.bn._ws)
+        dsub = self.desc(n1 - n0, c.d.H, c.d.W)
+        dx = E(n1 - n0, c.d.H, c.d.W, self.Cin, dtype=self.adt)
+        L.conv_dgrad(dsub, draw, P[self.prefix + "conv.weight"], c.pack_d, dx, fuse)
+        return dx
+
     def backward_raw(self, P, c, draw, G, acc, need_dw, need_dx, fuse=None):
         """Backward from a gradient on the raw (pre-BN) conv output -- the discriminator's feature tap (vae_gan.py:169-173)."""
         w = P[self.prefix + "conv.weight"]
@@ -175,6 +192,58 @@ class ConvBlock:
             else:
                 L.conv_wgrad(c.d, c.x, draw, G[self.prefix + "conv.weight"], acc, self._ws)
         return dx
+
+
+class BlockNet:
+    """A standalone EncoderBlock / DecoderBlock (vae_gan.py:11-60) on NCHW fp32 tensors, as the reference's modules are
+    callable on their own: forward(ten, out) -> relu(bn(conv(ten))) [, raw conv output]. Inside Encoder / Decoder /
+    Discriminator the blocks run in their network's fused pipeline instead (no layout passes). Channel counts the tensor path
+    does not tile (e.g. a 3-channel input) run on the exact fp32 CUDA-core path."""
+
+    def __init__(self, Cin, Cout, transposed, output_pad, adt):
+        ok = (Cin % 64 == 0 and Cout % 32 == 0) if transposed else (Cin % 32 == 0 and Cout % 64 == 0)
+        self.adt = adt if ok else F32
+        self.Cin, self.Cout = Cin, Cout
+        self.block = ConvBlock("", Cin, Cout, transposed, output_pad, self.adt)
+
+    def refresh(self, P, inplace=True):
+        self.block.refresh(P, inplace)
+
+    def forward(self, P, S, x, train, out, nbt):
+        N, _, H, W = x.shape
+        xs = E(N, H, W, self.Cin, dtype=self.adt)
+        L.nchw_to_nhwc(x, xs, N, self.Cin, H, W)
+        y, c = self.block.forward(P, S, xs, N, H, W, train, 1, nbt)
+        yo = E(N, self.Cout, c.OH, c.OW)
+        L.nhwc_to_nchw(y, yo, N, self.Cout, c.OH, c.OW)
+        ro = None
+        if out:
+            ro = E(N, self.Cout, c.OH, c.OW)
+            L.nhwc_to_nchw(c.bn.raw, ro, N, self.Cout, c.OH, c.OW)
+        c.N, c.H, c.W = N, H, W
+        return yo, ro, c
+
+    def backward(self, P, c, dy, draw_extra, G, need_dw, need_dx):
+        """dy / draw_extra: NCHW fp32 gradients on the block output / on the raw conv output (either may be None)."""
+        N, OH, OW = c.N, c.OH, c.OW
+        draw = None
+        if dy is not None:
+            g = E(N, OH, OW, self.Cout, dtype=self.adt)
+            L.nchw_to_nhwc(dy, g, N, self.Cout, OH, OW)
+            draw = self.block.bn.backward(P, c.bn, g, G, False, need_dw)
+        elif need_dw:
+            G["bn.weight"].zero_()
+            G["bn.bias"].zero_()
+        if draw_extra is not None:
+            t = E(N, OH, OW, self.Cout, dtype=self.adt)
+            L.nchw_to_nhwc(draw_extra, t, N, self.Cout, OH, OW)
+            draw = t if draw is None else draw.add_(t)
+        dx = self.block.backward_raw(P, c, draw, G, False, need_dw, need_dx)
+        if dx is None:
+            return None
+        dxo = E(N, self.Cin, c.H, c.W)
+        L.nhwc_to_nchw(dx, dxo, N, self.Cin, c.H, c.W)
+        return dxo
 
 
 # Fusing the BN-backward reduction into the data-gradient epilogue (fmri_bn_fuse) removes 2 of BN-backward's 5 tensor passes
@@ -500,9 +569,9 @@ class DiscriminatorNet:
 
     def __init__(self, cfg, adt, recon_level=3):
         ch = cfg["discrim_channels"]
-        if recon_level != 3:
-            raise L.FmriError("only recon_level=3 (the reference default, vae_gan.py:240) is implemented")
-        self.cfg, self.adt = cfg, adt
+        if recon_level not in (1, 2, 3):   # vae_gan.py:169-173: conv[0] is a plain Sequential and cannot be the tap
+            raise L.FmriError("recon_level must be 1, 2 or 3 (the EncoderBlock whose raw conv output is the feature tap)")
+        self.cfg, self.adt, self.level = cfg, adt, int(recon_level)
         self.C0, self.stride0 = ch[0], cfg["stride_gan"]
         self.blocks = [ConvBlock(f"conv.{i}.", ch[i - 1], ch[i], False, 0, adt) for i in (1, 2, 3)]
         self.Cl = ch[3]
@@ -523,9 +592,14 @@ class DiscriminatorNet:
             m.refresh(P, inplace)
 
     def forward(self, P, S, imgs, train=True, n_updates=1, head=True, nbt=None, head_updates=1):
-        """imgs: list of 1..3 NCHW fp32 tensors of equal shape [Bs,3,H,W]. Returns (raw3 NHWC feature tap, p [N] or None, ctx).
+        """imgs: list of 1..3 NCHW fp32 tensors of equal shape [Bs,3,H,W]. Returns (NHWC feature tap = raw conv output of block
+        `recon_level`, p [N] or None, ctx). head=False is the reference's "REC" pass, which stops after block `recon_level`
+        (vae_gan.py:166-175: the later blocks neither run nor update their BatchNorm statistics).
         n_updates: BN running-stat updates of the conv blocks (2 when one pass stands for the reference's REC + GAN passes,
-        vae_gan.py:284-285); head_updates: of fc[1], which only the GAN pass reaches."""
+        vae_gan.py:284-285; only valid for recon_level 3, where both passes run every block); head_updates: of fc[1], which
+        only the GAN pass reaches."""
+        if n_updates > 1 and self.level != 3:
+            raise L.FmriError("one pass standing for REC + GAN needs recon_level 3 (lower taps update fewer BatchNorm layers)")
         Bs, _, H, W = imgs[0].shape
         N = Bs * len(imgs)
         d0 = L.edge_desc(N, H, W, self.C0, self.stride0, self.adt)
@@ -538,12 +612,12 @@ class DiscriminatorNet:
             mask0 = torch.empty(N * OH * OW, dtype=torch.int32, device=y0.device)
             L.relu_bitmask(y0, N * OH * OW, self.C0, mask0)
         cs, y, h, w = [], y0, OH, OW
-        for b in self.blocks:
+        for b in (self.blocks if head else self.blocks[:self.level]):
             y, c = b.forward(P, S, y, N, h, w, train, n_updates, nbt)
             cs.append(c)
             h, w = c.OH, c.OW
         ctx = Ctx(imgs=list(imgs), Bs=Bs, N=N, d0=d0, y0=y0, mask0=mask0, blocks=cs, hw=(h, w), H=H, W=W, hw0=(OH, OW))
-        raw3 = cs[-1].bn.raw
+        raw3 = cs[self.level - 1].bn.raw
         p = None
         if head:
             flat = E(N, self.Cl * h * w, dtype=self.adt)
@@ -586,8 +660,47 @@ class DiscriminatorNet:
         dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, relu_mask=(c.y0, c.mask0))
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
-    def backward_rec(self, P, c, draw3, G=None, acc=False, need_dw=False, img_slices=None):
-        """Backward of the feature-tap path from a gradient on the raw conv output of block 3 [N,h,w,C] (adt)."""
+    def backward_rec(self, P, c, draw3, G=None, acc=False, need_dw=False, img_slices=None, live=None):
+        """Backward of the feature-tap path from a gradient on the raw conv output of block 3 [N,h,w,C] (adt).
+        live = (s0, s1): only sources [s0, s1) of draw3 are non-zero (the feature-matching loss compares x and x_tilde; the
+        x_p third gets no gradient at the tap, train_vgan_stage1.py:369 / vae_gan.py:313).
+        Data-gradient-only fast path (need_dw False, no fused BN sums): block 3's data gradient runs on the live sources only
+        (the rest of its output is exactly zero), and block 1's BN apply + data gradient + conv[0] run on the requested image
+        slice only -- BatchNorm's coupling of the whole 3B batch is kept by running every BN's backward SUMS over all of it."""
+        top = self.level - 1
+        if top != 2:   # feature tap below block 3: plain chain from the tap's block down
+            fuse = None
+            if top > 0 and FUSE_BN_BWD:
+                fuse = self.blocks[top - 1].bn.fuse_spec(P, c.blocks[top - 1].bn)
+            elif top == 0:
+                fuse = (c.y0, None, None, None, None, 1, None, c.mask0)
+            dy = self.blocks[top].backward_raw(P, c.blocks[top], draw3, G, acc, need_dw, True, fuse)
+            if top > 0:
+                dy, _ = _backward_chain(self.blocks[:top], c.blocks[:top], P, dy, G, acc, need_dw, None, fuse is not None,
+                                        relu_mask=(c.y0, c.mask0))
+            return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
+        if not need_dw and not FUSE_BN_BWD and img_slices is not None and len(c.imgs) > 1:
+            Bs = c.Bs
+            l0, l1 = live if live is not None else (0, len(c.imgs))
+            b3, c3 = self.blocks[2], c.blocks[2]
+            dy = torch.empty(c3.x.shape, dtype=self.adt, device=draw3.device)
+            if l0 > 0:
+                dy[:l0 * Bs].zero_()
+            if l1 < len(c.imgs):
+                dy[l1 * Bs:].zero_()
+            L.conv_dgrad(b3.desc((l1 - l0) * Bs, c3.d.H, c3.d.W), draw3[l0 * Bs:l1 * Bs], P[b3.prefix + "conv.weight"],
+                         c3.pack_d, dy[l0 * Bs:l1 * Bs], None)
+            dy = self.blocks[1].backward(P, c.blocks[1], dy, None, False, False, True)
+            s0, s1 = img_slices
+            OH, OW = c.hw0
+            bits = c.mask0[s0 * Bs * OH * OW:s1 * Bs * OH * OW] if c.mask0 is not None else None
+            dy0 = self.blocks[0].backward_dx_slice(P, c.blocks[0], dy, s0 * Bs, s1 * Bs,
+                                                   (c.y0[s0 * Bs:s1 * Bs], None, None, None, None, 1, None, bits))
+            n = (s1 - s0) * Bs
+            dimg = E(n, 3, c.H, c.W)
+            L.edge_in_dgrad(L.edge_desc(n, c.H, c.W, self.C0, self.stride0, self.adt), dy0, P["conv.0.0.weight"], dimg,
+                            self._ews)
+            return dimg
         fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if FUSE_BN_BWD else None
         dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True, fuse)
         dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None,
