@@ -241,6 +241,25 @@ int fmri_vgan_gate(const float* sums, float count, float margin, float equilibri
 int fmri_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                        float* invstd, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Inference side and the step's input edge (8f-3).
+ * fmri_bn_fold: eval-mode BatchNorm folded into the preceding bias-free layer, w_out = w * gamma / sqrt(running_var + eps)
+ *   per OUTPUT channel ((i / inner) % C: Conv2d inner = Cin*25, ConvTranspose2d inner = 25, Linear inner = in_features),
+ *   b_out = beta - running_mean * that scale; the folded layer then runs conv / linear + bias + ReLU in ONE kernel
+ *   (VaeGan.forward eval branch, vae_gan.py:288-297; inference/inference_gan.py:340-442).
+ * fmri_pearson / fmri_ssim: PearsonCorrelation / StructuralSimilarity of train/train_utils.py:267-293, 295-425 on two
+ *   fp32 NCHW batches (scalar results on the device; ws: 5 / 1 doubles).
+ * fmri_image_pipeline: uint8 NHWC batch (1 or 3 channels) -> normalised fp32 NCHW: /255, GreyToColor, per-image horizontal
+ *   flip (flip[n] != 0), per-image integer shift with edge replication (shift_yx[2n], [2n+1]), (v - mean) / std
+ *   (train_vgan_stage1.py:161-171; data_preprocessing/data_loader.py:93-111, 187-217, 374-400). mean3 / std3 are HOST arrays.
+ * --------------------------------------------------------------------------------------------------------- */
+int fmri_bn_fold(const float* w, long long n, long long inner, int C, const float* running_mean, const float* running_var,
+                 const float* gamma, const float* beta, float eps, float* w_out, float* b_out, void* stream);
+int fmri_pearson(const float* a, const float* b, long long n, float* out, double* ws, void* stream);
+int fmri_ssim(const float* a, const float* b, int N, int C, int H, int W, float* out, double* ws, void* stream);
+int fmri_image_pipeline(const unsigned char* src, int N, int H, int W, int Csrc, const int* flip, const int* shift_yx,
+                        const float* mean3, const float* std3, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

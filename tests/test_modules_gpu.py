@@ -637,6 +637,10 @@ def test_vaegan_cognitive_wae_mode_fp32():
                mus=rel(mus, mu), logvar=rel(log_variances, lv), mse=rel(mse, mse_ref))
     print("VaeGanCognitive wae mode", fwd)
     assert max(fwd.values()) < 1e-4, fwd
-    ge = {k: rel(dict(model.named_parameters())[k].grad, g) for k, g in g_ref.items() if g is not None}
+    # l_mu.bias is skipped: decoder.fc is a Linear followed by train-mode BatchNorm, which removes any shift common to the
+    # whole batch, so d mse / d l_mu.bias is zero in exact arithmetic (the oracle returns 1e-17) and has no relative error
+    scale = max(float(g.norm()) for g in g_ref.values() if g is not None)
+    ge = {k: rel(dict(model.named_parameters())[k].grad, g) for k, g in g_ref.items()
+          if g is not None and float(g.norm()) > 1e-9 * scale}
     print(ge)
     assert ge and max(ge.values()) < 5e-3, ge

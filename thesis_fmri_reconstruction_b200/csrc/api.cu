@@ -12,6 +12,7 @@
 #include "hconv_kernels.cuh"
 #include "hwgrad_kernels.cuh"
 #include "mmd_kernels.cuh"
+#include "eval_kernels.cuh"
 
 using namespace fmri;
 
@@ -330,11 +331,12 @@ static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW
 // Scatter-form plan (stride 2): out[n, 2a+ph, 2b+pw, :] = sum_{kh = ph (mod 2), kw = pw (mod 2)} X[n, a+(ph+2-kh)/2, ..] * pack[tap]
 // (ConvTranspose2d fprop; Conv2d dgrad). X: [N,H,W,Ck], out: [N,OH,OW,Ng] with OH in {2H-1, 2H}.
 static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
-                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse);
+                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse, const float* bias, int act);
 static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int OW, int Ng, const void* pack, void* out,
-                       double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse = nullptr) {
+                       double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse = nullptr, const float* bias = nullptr,
+                       int act = 0) {
     if (Ck % 32 || Ng % 32) return fail(FMRI_ERR_UNSUPPORTED, "tensor path needs channels %% 32 == 0 (%d,%d)", Ck, Ng);
-    if (Ng == 32) return run_scatter_merged(X, N, H, W, Ck, OH, OW, pack, out, ssum, ssq, st, fuse);
+    if (Ng == 32) return run_scatter_merged(X, N, H, W, Ck, OH, OW, pack, out, ssum, ssq, st, fuse, bias, act);
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
     memset(&p, 0, sizeof(p));
@@ -385,6 +387,8 @@ static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int O
     p.out_fp32 = 0;
     p.stat_sum = ssum;
     p.stat_sq = ssq;
+    p.bias = bias;
+    p.act = act;
     apply_fuse(p, fuse);
     return dispatch_ig(p, BN, KCH, 4, st);
 }
@@ -392,7 +396,7 @@ static int run_scatter(const void* X, int N, int H, int W, int Ck, int OH, int O
 // Parity-merged scatter plan for Ng == 32 (IgParams::merge): one gather over the 3x3 coarse neighbourhood, N = 4 x 32.
 // `pack` is the ordinary tap-major pack [25][32][Ck] followed by the merged pack [9][128][Ck] (fmri_conv_pack_elems).
 static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH, int OW, const void* pack, void* out,
-                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse) {
+                              double* ssum, double* ssq, cudaStream_t st, const BnbFuse* fuse, const float* bias, int act) {
     const int Ng = 32;
     const int KCH = (Ck % 64 == 0) ? 64 : 32;
     IgParams p;
@@ -454,6 +458,8 @@ static int run_scatter_merged(const void* X, int N, int H, int W, int Ck, int OH
     p.out_fp32 = 0;
     p.stat_sum = ssum;
     p.stat_sq = ssq;
+    p.bias = bias;   // merged epilogue: every 32-column group is the same 32 output channels (bias index = column % 32)
+    p.act = act;
     p.merge = 1;
     p.merge_oh = OH;
     p.merge_ow = OW;
@@ -738,10 +744,9 @@ extern "C" int fmri_conv_fprop(const fmri_conv_desc* d, const void* x, const flo
     }
     if (d->dtype == FMRI_BF16) {
         if (!pack_f) return fail(FMRI_ERR_ARG, "bf16 conv needs the packed weights");
-        if (d->transposed) {
-            if (bias || act) return fail(FMRI_ERR_UNSUPPORTED, "convT epilogue: bias/act unsupported");
-            return run_scatter(x, d->N, d->H, d->W, d->Cin, OH, OW, d->Cout, pack_f, y, stat_sum, stat_sq, S(stream));
-        }
+        if (d->transposed)   // bias / act: the BatchNorm-folded inference forward (fmri_bn_fold)
+            return run_scatter(x, d->N, d->H, d->W, d->Cin, OH, OW, d->Cout, pack_f, y, stat_sum, stat_sq, S(stream), nullptr,
+                               bias, act);
         return run_gather(x, d->N, d->H, d->W, d->Cin, OH, OW, d->Cout, d->stride, pack_f, bias, act, y, 0, stat_sum,
                           stat_sq, S(stream));
     }
@@ -1948,6 +1953,61 @@ extern "C" int fmri_vgan_gate(const float* sums, float count, float margin, floa
 extern "C" int fmri_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                                   float* invstd, void* stream) {
     bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+    LAUNCH_OK();
+    return 0;
+}
+
+// ================================================================================================ inference / metrics / input
+extern "C" int fmri_bn_fold(const float* w, long long n, long long inner, int C, const float* running_mean,
+                            const float* running_var, const float* gamma, const float* beta, float eps, float* w_out,
+                            float* b_out, void* stream) {
+    if (!w || !w_out || !b_out || n <= 0 || inner <= 0 || C <= 0) return fail(FMRI_ERR_ARG, "bn_fold arguments");
+    bn_fold_kernel<<<grid1d(std::max<long long>(n, C), 256), 256, 0, S(stream)>>>(w, n, inner, C, running_mean, running_var,
+                                                                                 gamma, beta, eps, w_out, b_out);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_pearson(const float* a, const float* b, long long n, float* out, double* ws, void* stream) {
+    if (!a || !b || !out || !ws || n <= 0) return fail(FMRI_ERR_ARG, "pearson arguments");
+    CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 5, S(stream)));
+    pearson_sums_kernel<<<grid1d(n, 256, 148 * 8), 256, 0, S(stream)>>>(a, b, n, ws);
+    LAUNCH_OK();
+    pearson_final_kernel<<<1, 1, 0, S(stream)>>>(ws, (double)n, out);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_ssim(const float* a, const float* b, int N, int C, int H, int W, float* out, double* ws, void* stream) {
+    if (!a || !b || !out || !ws || N <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(FMRI_ERR_ARG, "ssim arguments");
+    // below 11 pixels the reference pads by 5 around a SMALLER window and its SSIM map outgrows the image (train_utils.py:378-390)
+    if (H < 11 || W < 11) return fail(FMRI_ERR_UNSUPPORTED, "ssim: images smaller than the 11 x 11 window (%d x %d)", H, W);
+    // gaussian(window_size, 1.5) of train_utils.py:310-323, evaluated in double and rounded to float like torch.Tensor([...])
+    const int win = std::min(11, std::min(H, W));
+    SsimWindow wd;
+    double g[11], sum = 0.0;
+    for (int x = 0; x < win; ++x) {
+        const double d = x - win / 2;
+        g[x] = (double)(float)exp(-(d * d) / (2.0 * 1.5 * 1.5));
+        sum += (double)(float)g[x];
+    }
+    float fs = 0.f;
+    for (int x = 0; x < win; ++x) fs += (float)g[x];
+    for (int x = 0; x < 11; ++x) wd.g[x] = x < win ? (float)g[x] / fs : 0.f;
+    (void)sum;
+    CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double), S(stream)));
+    const long long total = (long long)N * C * H * W;
+    ssim_kernel<<<grid1d(total, 256, 148 * 8), 256, 0, S(stream)>>>(a, b, N * C, H, W, win, wd, ws);
+    LAUNCH_OK();
+    scale_d2f_kernel<<<1, 1, 0, S(stream)>>>(ws, 1.0 / (double)total, out);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int fmri_image_pipeline(const unsigned char* src, int N, int H, int W, int Csrc, const int* flip,
+                                   const int* shift_yx, const float* mean3, const float* std3, float* dst, void* stream) {
+    if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || (Csrc != 1 && Csrc != 3)) return fail(FMRI_ERR_ARG, "image_pipeline arguments");
+    const float m[3] = {mean3 ? mean3[0] : 0.f, mean3 ? mean3[1] : 0.f, mean3 ? mean3[2] : 0.f};
+    const float sd[3] = {std3 ? std3[0] : 1.f, std3 ? std3[1] : 1.f, std3 ? std3[2] : 1.f};
+    image_pipeline_kernel<<<grid1d((long long)N * 3 * H * W, 256, 148 * 8), 256, 0, S(stream)>>>(
+        src, N, H, W, Csrc, flip, shift_yx, m[0], m[1], m[2], sd[0], sd[1], sd[2], dst);
     LAUNCH_OK();
     return 0;
 }

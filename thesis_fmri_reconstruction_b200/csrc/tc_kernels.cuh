@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgPa
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (p.bias && split == 0) {  // split-K: exactly one split adds the bias
+                    const float* bp = p.bias + (p.merge ? 0 : nt * BN + c0);  // merged: each 32-column group = channels 0..31
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(bp + j);
                 }
                 if (p.act == ACT_RELU) {
 #pragma unroll
@@ -624,8 +625,9 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     if (p.bias) {
+                        const float* bp = p.bias + (p.merge ? 0 : nt * BN + c0);  // merged: each 32-column group = channels 0..31
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nt * BN + c0 + j);
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(bp + j);
                     }
                     if (p.act == ACT_RELU) {
 #pragma unroll

@@ -469,3 +469,30 @@ def vgan_gate(sums, count, margin, equilibrium, gates):
 
 def bn_eval_stats(rm, rv, Cc, eps, mean, invstd):
     _check(load().fmri_bn_eval_stats(ptr(rm), ptr(rv), Cc, _f(eps), ptr(mean), ptr(invstd), stream()))
+
+
+# ------------------------------------------------------------------------------------------------ inference / metrics / input
+def bn_fold(w, inner, Cc, rm, rv, gamma, beta, eps, w_out, b_out):
+    _require_cuda(w, rm, rv, gamma, beta, w_out, b_out)
+    _check(load().fmri_bn_fold(ptr(w), _ll(w.numel()), _ll(inner), Cc, ptr(rm), ptr(rv), ptr(gamma), ptr(beta), _f(eps),
+                               ptr(w_out), ptr(b_out), stream()))
+
+
+def pearson(a, b, out, ws):
+    _require_cuda(a, b, out, ws)
+    _check(load().fmri_pearson(ptr(a), ptr(b), _ll(a.numel()), ptr(out), ptr(ws), stream()))
+
+
+def ssim(a, b, out, ws):
+    _require_cuda(a, b, out, ws)
+    N, Cc, H, W = a.shape
+    _check(load().fmri_ssim(ptr(a), ptr(b), N, Cc, H, W, ptr(out), ptr(ws), stream()))
+
+
+def image_pipeline(src_u8, flip, shift_yx, mean3, std3, dst):
+    """src_u8: uint8 [N, H, W, C] (C = 1 or 3) on the device; dst: fp32 [N, 3, H, W]."""
+    _require_cuda(src_u8, flip, shift_yx, dst)
+    N, H, W, Cs = src_u8.shape
+    m = (C.c_float * 3)(*[float(v) for v in mean3])
+    s = (C.c_float * 3)(*[float(v) for v in std3])
+    _check(load().fmri_image_pipeline(ptr(src_u8), N, H, W, Cs, ptr(flip), ptr(shift_yx), m, s, ptr(dst), stream()))
