@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg (child process)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (engine.GraphedStep; RMSprop "
                     "engines on one GPU): for launch-bound batch sizes such as configs[0]'s 64")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for runs under ncu)")
@@ -67,6 +68,56 @@ def peaks():
         return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, sustained bf16)")
     except Exception:
         return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+def build_hash():
+    """sha256 over the kernel sources + public header: ties a committed ncu capture to the build it was taken from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "thesis_fmri_reconstruction_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join(ROOT, "include", "fmri_b200.h")]:
+        with open(f if os.path.isabs(f) else os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(workload, per_gpu_batch, family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel family from the committed ncu capture
+    (profiles/r2_traffic.json, written by scripts/ncu_traffic.py). None unless the capture is of THIS build, workload and
+    per-GPU batch. Returns (bytes per launch or None, source string)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except Exception:
+        return None, "no committed capture (profiles/r2_traffic.json)"
+    if t.get("build_hash") != build_hash():
+        return None, "profiles/r2_traffic.json is of build %s, this build is %s: traffic withheld" % (t.get("build_hash"), build_hash())
+    if t.get("workload") != workload or int(t.get("per_gpu_batch", -1)) != int(per_gpu_batch):
+        return None, "profiles/r2_traffic.json is of %s at batch %s" % (t.get("workload"), t.get("per_gpu_batch"))
+    fam = t.get("families", {}).get(family)
+    if not fam:
+        return None, "family %s not in profiles/r2_traffic.json" % family
+    return fam["dram_bytes_per_launch"], "profiles/r2_traffic.json (%s; ncu, cold cache, %d launches)" % (t.get("source", "?"), fam["launches"])
+
+
+def stock_torch_leg(workload, B):
+    """Stock PyTorch on the same GPU (cuDNN / cuBLAS, bf16 autocast + channels_last: its best mode), in a
+    child process; the practical bar next to the hand-written path. Returns a dict or None."""
+    if workload not in ("stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive"):
+        return None
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "stock_torch_gpu_baseline.py"), "--workload", workload,
+                            "--batch", str(B), "--steps", "3", "--warmup", "2", "--modes", "bf16_cl"],
+                           capture_output=True, text=True, timeout=600)
+        line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+        if "samples_per_s" not in line:
+            return dict(error=line.get("error", "failed"))
+        return dict(value=line["samples_per_s"], unit="samples/s", ms_per_step=line["ms_per_step"], impl=line["impl"],
+                    mode="bf16 autocast + channels_last", batch=B, steps=3, warmup=2)
+    except Exception as ex:
+        return dict(error=repr(ex)[:200])
 
 
 class ClockSampler:
@@ -195,21 +246,103 @@ def cpu_reference_steps(workload, B, steps, warmup, threads=None):
     return B / dt, dt * 1e3, threads
 
 
+def find_reference_models():
+    """Root of a reference tree that holds models/vae_gan.py: /root/reference (build container) or the git-ignored staging
+    copy baseline/_ref (what travels to a GPU box; __graft_entry__.build() makes it where /root/reference exists)."""
+    for root in (os.environ.get("FMRI_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if root and os.path.exists(os.path.join(root, "models", "vae_gan.py")) and \
+                os.path.exists(os.path.join(root, "configs", "models_config.py")):
+            return root
+    return None
+
+
+def reference_modules_steps(ref_root, B, steps, warmup, threads=None):
+    """Stage-I VAE/GAN on the UNMODIFIED reference modules (models/vae_gan.py imported from `ref_root` with its own
+    configs.models_config switched to the 64x64 block, :23-31): VaeGan.forward (two discriminator passes), VaeGan.loss, the
+    loss mix of train_vgan_stage1.py:368-372, and the script's three FULL backward sweeps loss_x.backward(retain_graph=True)
+    (:408-432, discarded gradients included). The three RMSprop steps run after the third sweep: torch >= 1.5 rejects the
+    script's interleaved step order on these modules, and under the torch-1.4 semantics the script was
+    written for the result is the same (0-7). Returns (samples/s, ms/step, cores)."""
+    import importlib
+
+    import torch
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    saved = list(sys.path)
+    sys.path[:] = [ref_root] + [q for q in sys.path if os.path.abspath(q or ".") != ROOT]
+    for m in [k for k in sys.modules if k.split(".")[0] in ("configs", "models")]:
+        del sys.modules[m]
+    try:
+        mc = importlib.import_module("configs.models_config")
+        assert os.path.abspath(mc.__file__).startswith(os.path.abspath(ref_root)), mc.__file__
+        mc.image_size, mc.fc_input, mc.fc_input_gan, mc.fc_output_gan, mc.stride_gan, mc.latent_dim = 64, 8, 8, 512, 1, 128
+        mc.output_pad_dec, mc.decoder_channels = [True, True, True], [256, 128, 32, 3]
+        ref = importlib.import_module("models.vae_gan")
+        assert os.path.abspath(ref.__file__).startswith(os.path.abspath(ref_root)), ref.__file__
+    finally:
+        sys.path[:] = saved
+    torch.manual_seed(12345)
+    model = ref.VaeGan(device=torch.device("cpu"), z_size=128)
+    model.train()
+    opts = [torch.optim.RMSprop(params=m.parameters(), lr=1e-4, alpha=0.9, eps=1e-8, weight_decay=0, momentum=0, centered=False)
+            for m in (model.encoder, model.decoder, model.discriminator)]
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(B, 3, 64, 64, generator=g) * 2 - 1
+    lam = 1e-6
+
+    def one():
+        x_tilde, disc_class, disc_layer, mus, lv = model(x)
+        nle, kld, mse, bo, bp, bs = ref.VaeGan.loss(x, x_tilde, disc_layer[:B], disc_layer[B:-B], disc_layer[-B:],
+                                                    disc_class[:B], disc_class[B:-B], disc_class[-B:], mus, lv)
+        loss_encoder = torch.sum(kld) + torch.sum(mse)
+        loss_discriminator = torch.sum(bo) + torch.sum(bp) + torch.sum(bs)
+        loss_decoder = torch.sum(lam * mse) - (1.0 - lam) * loss_discriminator
+        grads = []
+        for loss, mod in ((loss_encoder, model.encoder), (loss_decoder, model.decoder), (loss_discriminator, model.discriminator)):
+            model.zero_grad()
+            loss.backward(retain_graph=True)       # a full sweep through discriminator -> decoder -> encoder, as the script does
+            grads.append([p.grad.clone() if p.grad is not None else None for p in mod.parameters()])
+        for gl, mod, opt in zip(grads, (model.encoder, model.decoder, model.discriminator), opts):
+            for p, gr in zip(mod.parameters(), gl):
+                p.grad = gr
+            opt.step()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return B / dt, dt * 1e3, threads
+
+
+def cpu_arm(workload, B, steps, warmup):
+    """(samples/s, ms/step, cores, kind, how): the unmodified reference modules when a reference tree is present and the
+    workload is the headline one, else the oracle port."""
+    ref_root = find_reference_models() if workload == "stage1_vaegan" else None
+    if ref_root is not None:
+        v, ms, cores = reference_modules_steps(ref_root, B, steps, warmup)
+        return v, ms, cores, "reference", ("unmodified reference modules (%s/models/vae_gan.py): VaeGan.forward + VaeGan.loss + the "
+                                          "script's three full backward sweeps + 3 x torch.optim.RMSprop" % ref_root)
+    v, ms, cores = cpu_reference_steps(workload, B, steps, warmup)
+    return v, ms, cores, "port", "oracle port of the reference step (needed gradients only: cheaper than the script's three full sweeps)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     B = args.cpu_batch
-    v, ms, cores = cpu_reference_steps(args.workload, B, steps, warm)
-    sample = f"{steps} timed + {warm} warm-up steps of batch {B} (bounded sample of the workload), fp32, torch CPU"
+    v, ms, cores, kind, how = cpu_arm(args.workload, B, steps, warm)
+    sample = f"{steps} timed + {warm} warm-up steps of batch {B} (bounded sample of the workload), fp32, torch CPU; {how}"
     line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})",
                             global_batch=args.batch, cpu_sample_batch=B,
-                            note="reference arm: oracle port of the reference step (two discriminator passes, three autograd "
-                                 "sweeps) on the host cores; each timed step is a batch-%d sample of the workload" % B),
-                cpu_baseline=dict(value=v, unit="samples/s", cores=cores, kind="port", sample=sample),
+                            note="reference arm on the host cores; each timed step is a batch-%d sample of the workload. %s" % (B, how)),
+                cpu_baseline=dict(value=v, unit="samples/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
@@ -272,27 +405,31 @@ def run_ours(args):
     waecog = args.workload in ("stage2_wae_cognitive", "stage3_wae_cognitive")
     fmri = fmri_host.cuda(non_blocking=True) if cog else None
 
-    def run_step(xb, a, b2, fb=None):
+    def step_inputs(xb, a, b2, fb=None):
+        """Positional inputs of this workload's trainer.step()."""
+        fb = fb if fb is not None else fmri
         if waecog:
-            tr.step(fb if fb is not None else fmri, xb)
-        elif dual:
-            tr.step(fb if fb is not None else fmri, xb, a, b2)
-        elif cog:
-            tr.step(fb if fb is not None else fmri, xb, a, eps_t, b2)
-        elif b2 is not None:
-            tr.step(xb, a, b2)
-        else:
-            tr.step(xb, a)
+            return (fb, xb)
+        if dual:
+            return (fb, xb, a, b2)
+        if cog:
+            return (fb, xb, a, eps_t, b2)
+        if b2 is not None:
+            return (xb, a, b2)
+        return (xb, a)
+
+    def run_step(xb, a, b2, fb=None):
+        tr.step(*step_inputs(xb, a, b2, fb))
 
     graphed = None
     if args.graph:
-        if world > 1 or args.workload not in ("stage1_vaegan", "stage3_cognitive"):
-            raise SystemExit("--graph: one GPU, workloads stage1_vaegan / stage3_cognitive")
-        graphed = engine.GraphedStep(tr, *((fmri, x, n1, eps_t, n2) if cog else (x, n1, n2)))
+        if world > 1:
+            raise SystemExit("--graph: one GPU")
+        graphed = engine.GraphedStep(tr, *step_inputs(x, n1, n2, fmri))
 
     def step_dev():
         if graphed is not None:
-            graphed(*((fmri, x, n1, eps_t, n2) if cog else (x, n1, n2)))
+            graphed(*step_inputs(x, n1, n2, fmri))
         else:
             run_step(x, n1, n2)
 
@@ -362,7 +499,7 @@ def run_ours(args):
         upload(slot ^ 1)  # prefetch the next batch while this step computes (the DataLoader's role in the reference)
         b = bufs[slot]
         if graphed is not None:   # the replay copies the slot into the graph's static input buffers (device to device)
-            graphed(*((b[3], b[0], b[1], eps_t, b[2]) if cog else (b[0], b[1], b[2])))
+            graphed(*step_inputs(b[0], b[1], b[2], b[3]))
         else:
             run_step(b[0], b[1], b[2], b[3])
         done[slot].record()
@@ -409,11 +546,10 @@ def run_ours(args):
         roof = dict(bound="tensor", kernel=("igemm_kernel (conv/convT fprop+dgrad, linear fprop+dgrad)" if dom == "igemm"
                                             else "wgrad_kernel (conv/convT/linear weight gradients)"),
                     achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family, averaged over its 39
-                    # launches of one step, from the committed ncu capture of THIS configuration
-                    # (profiles/r1d_ncu_launches_time_dram_B4096.csv: Stage-I, batch 4096 on one GPU); null for any other
-                    traffic=(2.124e9 if (dom == "igemm" and args.workload == "stage1_vaegan" and B == 4096) else None),
-                    traffic_source="profiles/r1d_ncu_launches_time_dram_B4096.csv (ncu, cold cache)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family (mean over its launches of
+                    # one step) from the committed ncu capture of THIS build and configuration; null otherwise
+                    traffic=committed_traffic(args.workload, B, dom)[0],
+                    traffic_source=committed_traffic(args.workload, B, dom)[1],
                     peak_source=pk["src"], kernel_ms_per_step=d["ms"] / psteps, kernel_launches_per_step=d["calls"] / psteps,
                     kernel_share_of_step=d["ms"] / tot_ms if tot_ms else None,
                     # whole job: algorithmic FLOPs of the step x samples/s over ALL ranks, against world x the per-GPU peak
@@ -423,9 +559,13 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        v, ms, cores = cpu_reference_steps(args.workload, args.cpu_batch, 2, 1)
-        cpu = dict(value=v, unit="samples/s", cores=cores, kind="port",
-                   sample=f"2 timed + 1 warm-up steps of batch {args.cpu_batch} of the same workload (oracle port, fp32, torch CPU)")
+        v, ms, cores, kind, how = cpu_arm(args.workload, args.cpu_batch, 2, 1)
+        cpu = dict(value=v, unit="samples/s", cores=cores, kind=kind,
+                   sample=f"2 timed + 1 warm-up steps of batch {args.cpu_batch} of the same workload, fp32, torch CPU; {how}")
+    stock = None
+    if rank == 0 and world == 1 and not args.no_stock_torch and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        stock = stock_torch_leg(args.workload, B)
     if rank == 0:
         act_gb = B * 3 * (64 * 64 * 32 + 32 * 32 * 128 + 16 * 16 * 256 + 8 * 8 * 256) * 2 * 2 / 1e9
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -439,7 +579,8 @@ def run_ours(args):
                                            "RMSprop (fused multi-tensor), equilibrium gate on device")
                                           + (" + Adam on the latent discriminator" if args.workload == "stage3_dual" else "")),
                     e2e=dict(value=e2e_value, unit="samples/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
-                             d2h_bytes_per_step=d2h), gpu_launches=launches, clocks=ck, roofline=roof, cpu_baseline=cpu,
+                             d2h_bytes_per_step=d2h), gpu_launches=launches, clocks=ck, roofline=roof, cpu_baseline=cpu, stock_torch=stock,
+                    build_hash=build_hash(),
                     losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in losses.items()})
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -222,6 +222,12 @@ int fmri_multi_tensor_rmsprop(int n, float* const* p, const float* const* g, flo
 int fmri_multi_tensor_adam(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                            const int64_t* numel, float lr, float beta1, float beta2, float eps, int step, float clamp,
                            const float* lr_dev, const float* gate_dev, void* stream);
+/* The same with Adam's step count read from device memory (bias corrections 1 - beta^t computed on the device), and the kernel
+ * that advances it: a training step with no host-side scalar that changes from step to step can be captured in a CUDA graph. */
+int fmri_multi_tensor_adam_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                               const int64_t* numel, float lr, float beta1, float beta2, float eps, const int* step_dev,
+                               float clamp, const float* lr_dev, const float* gate_dev, void* stream);
+int fmri_step_increment(int* step_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Glue of the fused training step (no reference counterpart as separate ops: autograd does these implicitly)

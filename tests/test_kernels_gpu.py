@@ -522,3 +522,32 @@ def test_persistent_path_subprocess():
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("N,H", [(80, 7), (148, 2), (75, 64), (200, 5)])
+def test_edge_c_to_3_gemm_gather_path(N, H):
+    """The GEMM + shift-and-add kernel of the C -> 3 convolutions (cto3_kernels.cuh; taken for C = 32, W = 64, N >= 74) on
+    shapes the full-size tests do not reach: odd heights (a last chunk of one image row, H*W not a multiple of the 128-pixel
+    chunk), images shorter than the 5x5 window, more images than CTAs. Forward (bias + tanh) and the flipped-tap data-gradient
+    use, against fp64 torch; fp32 outputs, tolerance 2e-4."""
+    C, W = 32, 64
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(70 + H)
+    x = rnd(torch.randn(N, C, H, W, generator=g).to(DEV), dtype)
+    w = rnd((torch.randn(3, C, 5, 5, generator=g) * 0.1).to(DEV), dtype)
+    b = torch.randn(3, generator=g).to(DEV)
+    d = L.edge_desc(N, H, W, C, 1, dtype)
+    ws = torch.empty(L.edge_workspace(d), dtype=torch.uint8, device=DEV)
+    img = torch.full((N, 3, H, W), float("nan"), dtype=torch.float32, device=DEV)
+    L.edge_out_fprop(d, nhwc(x).to(dtype), w, b, L.ACT_TANH, img, ws)
+    torch.cuda.synchronize()
+    ref = torch.tanh(F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=2))
+    assert rel(img, ref) < 2e-4
+    # data gradient of a 3 -> C convolution: dimg = conv_transpose(dy, w_in) -- same kernel, flipped taps, other weight layout
+    w_in = rnd((torch.randn(C, 3, 5, 5, generator=g) * 0.1).to(DEV), dtype)
+    dy = rnd(torch.randn(N, C, H, W, generator=g).to(DEV), dtype)
+    dimg = torch.full((N, 3, H, W), float("nan"), dtype=torch.float32, device=DEV)
+    L.edge_in_dgrad(d, nhwc(dy).to(dtype), w_in, dimg, ws)
+    torch.cuda.synchronize()
+    ref_d = torch.nn.grad.conv2d_input((N, 3, H, W), w_in.double(), dy.double(), stride=1, padding=2)
+    assert rel(dimg, ref_d) < 2e-4

@@ -11,6 +11,7 @@
 #include "tc_kernels.cuh"
 #include "hconv_kernels.cuh"
 #include "hwgrad_kernels.cuh"
+#include "cto3_kernels.cuh"
 #include "mmd_kernels.cuh"
 #include "eval_kernels.cuh"
 
@@ -1014,6 +1015,14 @@ static int hc_launch(const HcParams& p_in, cudaStream_t st) {
     }
     HcParams p = p_in;
     p.issuers_max = issuers;
+    {
+        static int skip = -1;
+        if (skip < 0) {
+            const char* e = getenv("FMRI_HC_SKIP");
+            skip = e ? atoi(e) : 0;
+        }
+        p.skip = skip;
+    }
     const int smem = hc_smem_bytes(p, BN);
     static int attr_smem = 0;
     if (smem > attr_smem) {
@@ -1044,11 +1053,48 @@ static int hc_run(HcParams& p, const HcPackSpec& spec, int BN, const float* w, i
     return fail(FMRI_ERR_UNSUPPORTED, "hconv BN=%d", BN);
 }
 
+// C -> 3 convolution as one GEMM per 128-pixel chunk + shift-and-add gather (cto3_kernels.cuh): C = 32, W = 64, enough images
+// to give every SM whole images. Returns 1 when the shape does not fit (caller falls back to the halo-tile kernel).
+static int cto3_run(const void* X, int N, int H, int W, int C, const float* w, long long s_co, long long s_c, int flip,
+                    const float* bias, int act, float* img, void* ws, cudaStream_t st) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("FMRI_CTO3");
+        enabled = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!enabled || C != 32 || W != C3_W || H < 3 || N < 74) return 1;
+    C3Params p;
+    memset(&p, 0, sizeof(p));
+    __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(ws);
+    c3_pack_weights_kernel<<<cdiv(C3_NB * C, 256), 256, 0, st>>>(w, wt, s_co, s_c, flip, C);
+    LAUNCH_OK();
+    if (make_act_map(&p.mapX, X, C, H * W, 1, N, C, (long long)H * W * C, (long long)H * W * C, C, 128, 1, 1)) return 1;
+    {
+        const long long dims[2] = {C, C3_NB};
+        const long long stv[1] = {C};
+        const int box[2] = {C, C3_NB};
+        if (make_map(&p.mapW, wt, 2, dims, stv, box, C * 2)) return 1;
+    }
+    p.N = N; p.H = H; p.out = img; p.bias = bias; p.act = act;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(cto3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
+        attr_done = true;
+    }
+    cto3_kernel<<<std::min(N, 148), C3_THREADS, C3_SMEM, st>>>(p);
+    LAUNCH_OK();
+    return 0;
+}
+
 // C -> 3 convolution, stride 1: img[n,co,y,x] = act(bias + sum_{taps,c} X[n,y+kh-2,x+kw-2,c] * w[co*s_co + c*s_c + tap]);
 // flip uses tap 24-tap (data gradient of a 3 -> C convolution). Returns 1 when the shape does not fit (fall back).
 static int hconv_c_to_3(const void* X, int N, int H, int W, int C, const float* w, long long s_co, long long s_c, int flip,
                         const float* bias, int act, float* img, void* ws, cudaStream_t st) {
     if (C != 32 && C != 64) return 1;
+    {
+        const int rc = cto3_run(X, N, H, W, C, w, s_co, s_c, flip, bias, act, img, ws, st);
+        if (rc <= 0) return rc;
+    }
     HcParams p;
     HcPackSpec spec;
     if (!hc_build(p, spec, N, H, W, C / 8, 1, H, W, 16, flip != 0)) return 1;
@@ -1919,9 +1965,30 @@ extern "C" int fmri_multi_tensor_adam(int n, float* const* p, const float* const
         int64_t mx;
         mt_fill(a, base, n, p, g, m, v, numel, &mx);
         dim3 grid(std::max(1, std::min(148 * 8, cdiv(mx, 256 * 4))), a.count);
-        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, bc1, bc2, clamp, lr_dev, gate_dev);
+        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, bc1, bc2, clamp, lr_dev, gate_dev, nullptr);
         LAUNCH_OK();
     }
+    return 0;
+}
+extern "C" int fmri_multi_tensor_adam_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                          const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                                          const int* step_dev, float clamp, const float* lr_dev, const float* gate_dev,
+                                          void* stream) {
+    if (!step_dev) return fail(FMRI_ERR_ARG, "multi_tensor_adam_dev needs the device step counter");
+    for (int base = 0; base < n; base += FMRI_MT_MAX) {
+        MtArgs a;
+        int64_t mx;
+        mt_fill(a, base, n, p, g, m, v, numel, &mx);
+        dim3 grid(std::max(1, std::min(148 * 8, cdiv(mx, 256 * 4))), a.count);
+        mt_adam_kernel<<<grid, 256, 0, S(stream)>>>(a, lr, beta1, beta2, eps, 1.f, 1.f, clamp, lr_dev, gate_dev, step_dev);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+extern "C" int fmri_step_increment(int* step_dev, void* stream) {
+    if (!step_dev) return fail(FMRI_ERR_ARG, "step_increment needs a device counter");
+    step_increment_kernel<<<1, 1, 0, S(stream)>>>(step_dev);
+    LAUNCH_OK();
     return 0;
 }
 

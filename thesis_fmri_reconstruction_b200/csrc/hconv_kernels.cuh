@@ -16,8 +16,8 @@
 //   * the weights of ALL steps stay resident in shared memory for the life of the (persistent) CTA.
 // Roles (384 threads): warps 0-2 = MMA issuers (sub-tile m is issued by warp m % 3: the MMAs here are small, N = 16..64, so
 // the kernel is bound by how fast tcgen05.mma can be ISSUED; each issuer runs warp-converged with uniform operands and an
-// ELECTED lane, see umma_bf16_elect), warps 3-7 = halo producers (cp.async 16 B with zero fill = conv padding), warps 8-11 =
-// epilogue (TMEM -> registers -> bias / activation -> global). Halo slabs and TMEM accumulators are double buffered, so
+// ELECTED lane, see umma_bf16_elect), the next 5 warps = halo producers (cp.async 16 B with zero fill = conv padding), the last
+// 8 warps = epilogue (TMEM -> registers -> bias / activation -> global). Halo slabs and TMEM accumulators are double buffered, so
 // producer, tensor pipe and epilogue of consecutive tiles overlap.
 //
 // Reference ops: Decoder.conv[3] Conv2d(C,3,5,s1,p2)+bias+tanh (/root/reference/models/vae_gan.py:118-121) fprop / dgrad,
@@ -55,6 +55,8 @@ struct HcParams {
     const float* bias;           // [n_out] / [BN] or null
     int act;
     int n_out;
+    int skip;                    // diagnostic (FMRI_HC_SKIP): bit 0 producers skip the halo copies, bit 1 epilogue skips its global
+                                 // stores, bit 2 issuers skip the MMAs -- which role bounds the kernel (results are garbage)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -81,7 +83,8 @@ __device__ __forceinline__ float hc_act(float v, int act) {
 
 constexpr int HC_ISSUERS = 5;                       // MMA-issuing warps (one per 128-row sub-tile, MT <= 5)
 constexpr int HC_PRODUCERS = 160;                   // the next 5 warps: halo producers
-constexpr int HC_THREADS = 32 * HC_ISSUERS + HC_PRODUCERS + 128;  // + 4 epilogue warps (TMEM lane quarter = warp % 4)
+constexpr int HC_EPI_WARPS = 8;                     // two per TMEM lane quarter (quarter = warp % 4): they alternate sub-tiles
+constexpr int HC_THREADS = 32 * HC_ISSUERS + HC_PRODUCERS + 32 * HC_EPI_WARPS;
 
 // shared-memory plan (host and device agree through these helpers)
 __host__ __device__ inline int hc_slab_bytes(const HcParams& p) { return p.slab_rows * 16; }
@@ -92,7 +95,7 @@ __host__ __device__ inline int hc_smem_bytes(const HcParams& p, int BN) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant__ HcParams p) {
+__global__ void __launch_bounds__(HC_THREADS, 2) hconv_kernel(const __grid_constant__ HcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_buf = hc_a_buffer_bytes(p);
@@ -105,11 +108,13 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
     uint64_t* slab_full = bars;       // [2] count = producers
     uint64_t* slab_empty = bars + 2;  // [2] count = active issuers (one tcgen05.commit each)
     uint64_t* tmem_full = bars + 4;   // [2] count = active issuers
-    uint64_t* tmem_empty = bars + 6;  // [2] count = 4 (epilogue warps)
+    uint64_t* tmem_empty = bars + 6;  // [2] count = HC_EPI_WARPS
     uint64_t* b_full = bars + 8;      // count = producers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_bias = reinterpret_cast<float*>(bars + 10);   // [64] bias of the NHWC epilogue (zeros when there is none)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && p.epi == 1 && (int)threadIdx.x < BN) ? p.bias[threadIdx.x] : 0.f;
     const int total_tiles = p.N * p.tiles_y;
     const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
     const int issuers_cap = p.issuers_max < HC_ISSUERS ? p.issuers_max : HC_ISSUERS;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
             mbar_init(&slab_full[i], HC_PRODUCERS);
             mbar_init(&slab_empty[i], issuers);
             mbar_init(&tmem_full[i], issuers);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], HC_EPI_WARPS);
         }
         mbar_init(b_full, HC_PRODUCERS);
         fence_barrier_init();
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
                     const HcStep stp = p.steps[s];
                     const uint64_t ad = (a_base | (static_cast<uint64_t>(stp.a_lbo & 0x3FFF) << 16)) + stp.a_off;
                     const uint64_t bd = b_base + stp.b_off;
+                    if (p.skip & 4) continue;
                     for (int m = warp; m < p.MT; m += issuers)  // this warp's sub-tiles: independent accumulators
                         umma_bf16_elect(d0 + m * BN, ad + (uint32_t)(m * 128), bd, idesc, acc);
                     acc = 1;
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
             mbar_wait(&slab_empty[sb], par ^ 1);
             const uint32_t a0 = smem_u32(sA + sb * a_buf);
             const __nv_bfloat16* Xn = p.X + (size_t)n * p.H * p.W * Cx;
-            for (int pl = 0; pl < p.num_planes; ++pl) {
+            for (int pl = 0; pl < ((p.skip & 1) ? 0 : p.num_planes); ++pl) {
                 const int ys = p.pl_ys[pl], xs = p.pl_xs[pl], yo = p.pl_yoff[pl], xo = p.pl_xoff[pl];
                 const uint32_t pbase = a0 + pl * chunks * slab;
                 // item i = row * chunks + j; HC_PRODUCERS is a multiple of chunks, so j is fixed per thread and the halo
@@ -220,7 +226,11 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
         }
     } else {
         // ======================================================== epilogue
+        // The epilogue is a latency chain per warp (TMEM load -> convert -> store); a probe with the other roles switched off
+        // (FMRI_HC_SKIP=7) left hconv_kernel<32> at 80 % of its time. So: two warps per TMEM lane quarter alternate the
+        // sub-tiles (at <= 56 registers, so that two CTAs still share an SM), and the bias comes from shared memory.
         const int q = warp & 3;
+        const int egrp = (warp - (HC_ISSUERS + HC_PRODUCERS / 32)) >> 2;   // 0 / 1: which of the quarter's two warps
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int sb = it & 1;
@@ -229,10 +239,10 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
             const int oy0 = (t - n * p.tiles_y) * p.THt;
             mbar_wait(&tmem_full[sb], par);
             tc_fence_after();
-            for (int m = 0; m < p.MT; ++m) {
+            for (int m = egrp; m < p.MT; m += HC_EPI_WARPS / 4) {
                 const int r = m * 128 + q * 32 + lane;
                 const int yy = r / p.PW, xx = r - yy * p.PW;
-                const bool valid = yy < p.THt && (oy0 + yy) < p.OH && xx < p.OW;
+                const bool valid = yy < p.THt && (oy0 + yy) < p.OH && xx < p.OW && !(p.skip & 2);
                 const uint32_t tad = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sb * acc_cols + m * BN;
                 if (p.epi == 0) {
                     uint32_t v[16];
@@ -260,8 +270,8 @@ __global__ void __launch_bounds__(HC_THREADS) hconv_kernel(const __grid_constant
                         uint32_t pk[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            float f0 = __uint_as_float(v[2 * c]), f1 = __uint_as_float(v[2 * c + 1]);
-                            if (p.bias) { f0 += __ldg(p.bias + c0 + 2 * c); f1 += __ldg(p.bias + c0 + 2 * c + 1); }
+                            const float f0 = __uint_as_float(v[2 * c]) + s_bias[c0 + 2 * c];
+                            const float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[c0 + 2 * c + 1];
                             pk[c] = pack_bf16x2(hc_act(f0, p.act), hc_act(f1, p.act));
                         }
                         if (valid) {

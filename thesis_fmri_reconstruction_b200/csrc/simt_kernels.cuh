@@ -1320,9 +1320,14 @@ __global__ void __launch_bounds__(256) mt_rmsprop_kernel(const __grid_constant__
 __global__ void __launch_bounds__(256) mt_adam_kernel(const __grid_constant__ MtArgs a, float lr, float beta1,
                                                       float beta2, float eps, float bc1, float bc2, float clamp,
                                                       const float* __restrict__ lr_dev,
-                                                      const float* __restrict__ gate) {
+                                                      const float* __restrict__ gate, const int* __restrict__ step_dev) {
     if (gate && *gate == 0.f) return;
     if (lr_dev) lr = *lr_dev;
+    if (step_dev) {   // step count kept on the device (CUDA-graph replays advance it): bias corrections in double, like the host
+        const double st = (double)*step_dev;
+        bc1 = (float)(1.0 - pow((double)beta1, st));
+        bc2 = (float)(1.0 - pow((double)beta2, st));
+    }
     const MtChunk t = a.t[blockIdx.y];
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
         float g = t.g[i];
@@ -1335,6 +1340,8 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(const __grid_constant__ Mt
         t.p[i] = t.p[i] - (lr / bc1) * m / denom;
     }
 }
+
+__global__ void step_increment_kernel(int* step) { *step += 1; }
 
 // ------------------------------------------------------------------------------------------------
 // small glue kernels of the fused training step

@@ -35,6 +35,20 @@ def _split(full, prefix):
 
 
 class _TrainerBase:
+    # Adam's step count lives in a device int32 (advanced by fmri_step_increment, read by fmri_multi_tensor_adam_dev): the step has
+    # no host-side scalar that changes from call to call, so it can be captured in a CUDA graph (GraphedStep).
+    t_dev = None
+
+    @property
+    def t(self):
+        return int(self.t_dev.item()) if self.t_dev is not None else 0
+
+    @t.setter
+    def t(self, v):
+        if self.t_dev is None:
+            self.t_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.t_dev.fill_(int(v))
+
     def _setup_dist(self, dist_group):
         self.dist = dist_group
         self.world = 1
@@ -90,7 +104,7 @@ class _TrainerBase:
         for pre, b in self.buckets.items():
             opt[pre] = [OrderedDict((pre + k, b.state_view(i, k).detach().cpu().clone()) for k in b.names)
                         for i in range(len(b.states))]
-        return dict(model=model, optimizer=opt, lr=dict(self.lr), hp=dict(self.hp), t=int(getattr(self, "t", 0)))
+        return dict(model=model, optimizer=opt, lr=dict(self.lr), hp=dict(self.hp), t=self.t)
 
     def load_state_dict(self, sd):
         """Resume from state_dict(): copies into the flat device buckets, then re-derives the bf16 operand packs."""
@@ -106,7 +120,7 @@ class _TrainerBase:
                     b.state_view(i, k).copy_(st[pre + k])
         self.lr.update(sd["lr"])
         self.hp.update(sd["hp"])
-        if hasattr(self, "t"):
+        if self.t_dev is not None:
             self.t = int(sd["t"])
         if hasattr(self, "nets"):
             for pre, net in self.nets.items():
@@ -245,8 +259,17 @@ class VaeGanStage1(_TrainerBase):
         self._klw = self.beta / float(B * self.world) if self.mode == "beta-vae" else 1.0
         L.reparam_kl_bwd(mu, lv, eps, dz, None, dycat[:, :z], dycat[:, z:], B, z, ld=2 * z, ldd=2 * z, gkl_const=self._klw)
         self._before_encoder_backward(mu, dycat)   # hook: DualWaeVaeGanStage1 adds the latent penalty gradient here
-        self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
-        self._allreduce_async([be.flat_g])
+        # encoder bucket in two parts: fc.0 / fc.1 / l_mu / l_var (67.6 MB, the tail of the flat buffer)
+        # are complete after the first three backward kernels and reduce while the conv backward still runs; only the conv
+        # part (4.1 MB) is exchanged after the last kernel
+        split = min(off for k, (off, _) in be.offsets.items() if not k.startswith("conv."))
+        if self.world > 1 and all(off < split for k, (off, _) in be.offsets.items() if k.startswith("conv.")):
+            self.enc.backward(be.P, ce, dycat, be.G, False, True, True,
+                              after_fc=lambda: self._allreduce_async([be.flat_g[split:]]))
+            self._allreduce_async([be.flat_g[:split]])
+        else:
+            self.enc.backward(be.P, ce, dycat, be.G, False, True, True)
+            self._allreduce_async([be.flat_g])
         st.sweeps = dict(dimg_bce=dimg_bce, dimg_mse=dimg_mse, dz=dz, dycat=dycat)
 
     _enc_bn_updates = 1
@@ -345,8 +368,8 @@ class WaeGanStage1(_TrainerBase):
 
     def _adam(self, pre):
         b, hp = self.buckets[pre], self.hp
-        L.multi_tensor_adam([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], self.lr[pre], hp["beta1"], hp["beta2"],
-                            hp["eps"], self.t)
+        L.multi_tensor_adam_dev([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], self.lr[pre], hp["beta1"], hp["beta2"],
+                                hp["eps"], self.t_dev)
         self.nets[pre].refresh(b.P, inplace=True)
 
     def step(self, x, z_fake):
@@ -355,7 +378,7 @@ class WaeGanStage1(_TrainerBase):
             return self._step_mmd(x, z_fake)
         B, z = x.shape[0], self.z
         be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
-        self.t += 1
+        L.step_increment(self.t_dev)
         sc, ones = self.sc, self._ones(B)
         nbe, nbd = {}, {}
         # ---------------- discriminator phase (:271-288)
@@ -411,7 +434,7 @@ class WaeGanStage1(_TrainerBase):
         forward. Everything else as train_wae_stage1.py:292-311."""
         B, z = x.shape[0], self.z
         be, bd = self.buckets["encoder."], self.buckets["decoder."]
-        self.t += 1
+        L.step_increment(self.t_dev)
         sc, ones = self.sc, self._ones(B)
         nbe, nbd = {}, {}
         ycat, ce = self.enc.forward(be.P, self.Ssub["encoder."], x, True, 1, nbe)
@@ -569,7 +592,8 @@ class VaeGanCognitiveStage(_TrainerBase):
             L.vgan_gate(self.sc, float(B_global), hp["margin"], hp["equilibrium"], gates)
             plan = (("decoder.", gates[1:2]), ("discriminator.", gates[0:1]))
         else:
-            gates.copy_(torch.tensor([1.0, 0.0], device="cuda"))
+            gates[0:1].fill_(1.0)   # stage 2: train_dis = True, train_dec = False, no gate (train_vgan_stage2.py:375-376)
+            gates[1:2].fill_(0.0)
             plan = (("encoder.", None), ("discriminator.", None))
         for pre, g in plan:
             b = self.buckets[pre]
@@ -629,10 +653,10 @@ class DualCognitiveStage3(VaeGanCognitiveStage):
 
     def update(self, B_global):
         super().update(B_global)
-        self.t += 1
+        L.step_increment(self.t_dev)
         b, hp = self.buckets["latent_discriminator."], self.hp_lat
-        L.multi_tensor_adam([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], float(hp["lr_dis"]), hp["beta1"],
-                            hp["beta2"], hp["eps"], self.t)
+        L.multi_tensor_adam_dev([b.flat_p], [b.flat_g], [b.states[0]], [b.states[1]], float(hp["lr_dis"]), hp["beta1"],
+                                hp["beta2"], hp["eps"], self.t_dev)
         self.ldis.refresh(b.P, inplace=True)
 
     def step(self, fmri, image, eps, z_p):
@@ -705,7 +729,7 @@ class WaeCognitiveStage(_TrainerBase):
         Bg = float(B * self.world)
         be, bd, bc = self.buckets["encoder."], self.buckets["decoder."], self.buckets["discriminator."]
         bt = self.buckets["teacher_net.encoder."]
-        self.t += 1
+        L.step_increment(self.t_dev)
         sc, ones = self.sc, self._ones(B)
         nb = {pre: {} for pre in self.buckets}
         # teacher encoder: stage 2 runs it twice on the same input (:284 and the D-phase), stage 3 once
@@ -774,10 +798,9 @@ class WaeCognitiveStage(_TrainerBase):
 
 class GraphedStep:
     """One training step captured in a CUDA graph and replayed: for launch-bound batch sizes (Stage I at batch 64 is 276
-    kernel launches in 5 ms, i.e. the host's launch rate, not the GPU, sets the step time). Works for the trainers whose
-    step has no host-side scalar that changes from step to step (the RMSprop engines: VaeGanStage1 with the device-side gate,
-    VaeGanCognitiveStage(3)); the Adam engines pass the step count for the bias correction as a kernel argument and are not
-    capturable as they stand.
+    kernel launches in 5 ms, i.e. the host's launch rate, not the GPU, sets the step time). Every trainer of this module is
+    capturable on one GPU: the equilibrium gate is decided on the device (fmri_vgan_gate) and Adam's step count lives in
+    device memory (fmri_step_increment / fmri_multi_tensor_adam_dev), so no host-side scalar changes from step to step.
 
         g = GraphedStep(trainer, x, eps, z_p)      # warms up (3 eager steps), then captures
         out = g(x, eps, z_p)                       # copies the inputs into the graph's static buffers and replays
@@ -785,9 +808,8 @@ class GraphedStep:
     The tensors in `out` live in the graph's memory pool and are overwritten by the next replay."""
 
     def __init__(self, trainer, *inputs, warmup=3):
-        if not isinstance(trainer, (VaeGanStage1, VaeGanCognitiveStage)) or getattr(trainer, "stage", 3) == 2 or \
-                isinstance(trainer, DualCognitiveStage3):
-            raise L.FmriError("GraphedStep supports VaeGanStage1 and VaeGanCognitiveStage(stage=3)")
+        if not isinstance(trainer, _TrainerBase) or trainer.world != 1:
+            raise L.FmriError("GraphedStep captures a single-GPU trainer of this module (NCCL collectives are not captured)")
         if isinstance(trainer, VaeGanStage1) and not trainer.gate_on:
             raise L.FmriError("GraphedStep needs the device-side gate (gate=True)")
         self.tr = trainer

@@ -449,6 +449,19 @@ def multi_tensor_adam(params, grads, ms, vs, lr, beta1, beta2, eps, step, clamp=
                                          ptr(lr_dev), ptr(gate_dev), stream()))
 
 
+def multi_tensor_adam_dev(params, grads, ms, vs, lr, beta1, beta2, eps, step_dev, clamp=0.0, lr_dev=None, gate_dev=None):
+    """Adam with the step count in a device int32 (see step_increment): capturable in a CUDA graph."""
+    n = len(params)
+    numel = (C.c_int64 * n)(*[p.numel() for p in params])
+    _check(load().fmri_multi_tensor_adam_dev(n, _ptr_array(params), _ptr_array(grads), _ptr_array(ms), _ptr_array(vs),
+                                             numel, _f(lr), _f(beta1), _f(beta2), _f(eps), ptr(step_dev), _f(clamp),
+                                             ptr(lr_dev), ptr(gate_dev), stream()))
+
+
+def step_increment(step_dev):
+    _check(load().fmri_step_increment(ptr(step_dev), stream()))
+
+
 # ------------------------------------------------------------------------------------------------ step glue
 def axpby_tanh_bwd(a, x, b, y, img, out):
     _require_cuda(x, y, img, out)

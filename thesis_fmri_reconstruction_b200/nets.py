@@ -475,11 +475,15 @@ class EncoderNet:
         ycat, ch = self.heads.forward(P, hfc, B)
         return ycat, Ctx(x=x, d0=d0, c0=c0, blocks=cs, fc=cfc, heads=ch, B=B, hw=(h, w))
 
-    def backward(self, P, c, dycat, G, acc=False, need_dw=True, need_lv=True):
-        """dycat [B, 2z] in adt. Parameter gradients into G (no image gradient: the input is data)."""
+    def backward(self, P, c, dycat, G, acc=False, need_dw=True, need_lv=True, after_fc=None):
+        """dycat [B, 2z] in adt. Parameter gradients into G (no image gradient: the input is data). after_fc(): called once the
+        gradients of fc / l_mu / l_var (93 % of the encoder's parameters) are issued -- the data-parallel engine starts their
+        all-reduce there, so that only the small conv part is exchanged after the last backward kernel."""
         B = c.B
         dh = self.heads.backward(P, c.heads, dycat, G, acc, need_dw, need_lv)
         dflat = self.fc.backward(P, c.fc, dh, G, acc, need_dw, True)
+        if after_fc is not None:
+            after_fc()
         h, w = c.hw
         dy = E(B, h, w, self.Clast, dtype=self.adt)
         L.nchw_to_nhwc(dflat, dy, B, self.Clast, h, w)
