@@ -335,12 +335,12 @@ def bn_backward(x, dy, dx, rows, Cc, mean, invstd, gamma, beta, relu, train, dga
                                    int(accumulate), ptr(ws), int(sums_ready), stream()))
 
 
-def bn_backward_slice(x, dy, dx, rows, row0, nrows, Cc, mean, invstd, gamma, beta, relu, train, ws):
+def bn_backward_slice(x, dy, dx, rows, row0, nrows, Cc, mean, invstd, gamma, beta, relu, train, ws, sums_ready=False):
     """BatchNorm backward whose sums run over all `rows` but whose dx is produced for rows [row0, row0 + nrows) only."""
     _require_cuda(x, dy, dx, mean, invstd, gamma, beta, ws)
     _check(load().fmri_bn_backward_slice(ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), _ll(rows), _ll(row0), _ll(nrows), Cc,
                                          ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), int(relu), int(train), None, None,
-                                         0, ptr(ws), 0, stream()))
+                                         0, ptr(ws), int(sums_ready), stream()))
 
 
 def relu_backward(y, dy, dx):

@@ -150,7 +150,7 @@ class ConvBlock:
         draw = self.bn.backward(P, c.bn, dy, G, acc, need_dw, sums_ready)
         return self.backward_raw(P, c, draw, G, acc, need_dw, need_dx, fuse)
 
-    def backward_dx_slice(self, P, c, dy, n0, n1, fuse=None):
+    def backward_dx_slice(self, P, c, dy, n0, n1, fuse=None, sums_ready=False):
         """Data gradient only, for images [n0, n1) of the batch. Train-mode BatchNorm couples all samples through its two
         backward sums, so those run over the whole batch; the BN apply pass and the conv data gradient run on the slice only
         (the discriminator's feature-tap sweep needs the image gradient of ONE of its three sources). Returns dx of the slice."""
@@ -161,7 +161,7 @@ class ConvBlock:
             self.bn._ws = E(3 * C, dtype=F64)
         draw = E(n1 - n0, c.OH, c.OW, C, dtype=dy.dtype)
         L.bn_backward_slice(cb.raw, dy, draw, N * per, n0 * per, (n1 - n0) * per, C, cb.mean, cb.invstd, P[pre + "weight"],
-                            P[pre + "bias"], cb.relu, cb.train, self.bn._ws)
+                            P[pre + "bias"], cb.relu, cb.train, self.bn._ws, sums_ready)
         dsub = self.desc(n1 - n0, c.d.H, c.d.W)
         dx = E(n1 - n0, c.d.H, c.d.W, self.Cin, dtype=self.adt)
         L.conv_dgrad(dsub, draw, P[self.prefix + "conv.weight"], c.pack_d, dx, fuse)
@@ -251,7 +251,17 @@ class BlockNet:
 # (+15.6 ms/step on the data-gradient launches), so it is OFF by default until the epilogue is spread over more warps.
 import os as _os
 
-FUSE_BN_BWD = _os.environ.get("FMRI_FUSE_BN", "0") == "1"
+# FMRI_FUSE_BN: "0" never, "1" always, "auto" (default): only in data-gradient launches whose contraction is deep enough
+# (>= 128 channels x 25 taps per tile) that the persistent kernel's heavier epilogue still hides behind the next tile's main loop.
+FUSE_BN_MODE = _os.environ.get("FMRI_FUSE_BN", "auto")
+FUSE_BN_BWD = FUSE_BN_MODE != "0"
+
+
+def _want_fuse(block):
+    """Should `block`'s data-gradient kernel also produce the BatchNorm-backward sums of the layer below it?"""
+    if FUSE_BN_MODE == "1":
+        return True
+    return FUSE_BN_MODE == "auto" and block.Cout >= 128   # the data gradient contracts over the block's output channels
 
 # Tensor-core weight gradients on a side stream: OFF by default (FMRI_WGRAD_STREAM=1 enables). Measured on one B200: -0.7 % step
 # time at batch 4096 (the GPU is power-capped, so overlapping tensor-pipe and HBM-bound kernels buys little), but 2x slower at
@@ -285,7 +295,7 @@ def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_read
     lower = (BatchNorm, ctx) of the BN below blocks[0], if any. Returns (dx of blocks[0], sums_ready for `lower`)."""
     ready = first_ready
     for i in range(len(blocks) - 1, -1, -1):
-        if not FUSE_BN_BWD:
+        if not _want_fuse(blocks[i]):
             fuse = None
         elif i > 0:
             fuse = blocks[i - 1].bn.fuse_spec(P, ctxs[i - 1].bn)
@@ -674,7 +684,7 @@ class DiscriminatorNet:
         top = self.level - 1
         if top != 2:   # feature tap below block 3: plain chain from the tap's block down
             fuse = None
-            if top > 0 and FUSE_BN_BWD:
+            if top > 0 and _want_fuse(self.blocks[top]):
                 fuse = self.blocks[top - 1].bn.fuse_spec(P, c.blocks[top - 1].bn)
             elif top == 0:
                 fuse = (c.y0, None, None, None, None, 1, None, c.mask0)
@@ -683,7 +693,7 @@ class DiscriminatorNet:
                 dy, _ = _backward_chain(self.blocks[:top], c.blocks[:top], P, dy, G, acc, need_dw, None, fuse is not None,
                                         relu_mask=(c.y0, c.mask0))
             return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
-        if not need_dw and not FUSE_BN_BWD and img_slices is not None and len(c.imgs) > 1:
+        if not need_dw and img_slices is not None and len(c.imgs) > 1:
             Bs = c.Bs
             l0, l1 = live if live is not None else (0, len(c.imgs))
             b3, c3 = self.blocks[2], c.blocks[2]
@@ -692,20 +702,23 @@ class DiscriminatorNet:
                 dy[:l0 * Bs].zero_()
             if l1 < len(c.imgs):
                 dy[l1 * Bs:].zero_()
+            # fused BN-backward sums of block 2 over the live rows only: the other rows of dy are exactly zero
+            f2 = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if _want_fuse(b3) else None
             L.conv_dgrad(b3.desc((l1 - l0) * Bs, c3.d.H, c3.d.W), draw3[l0 * Bs:l1 * Bs], P[b3.prefix + "conv.weight"],
-                         c3.pack_d, dy[l0 * Bs:l1 * Bs], None)
-            dy = self.blocks[1].backward(P, c.blocks[1], dy, None, False, False, True)
+                         c3.pack_d, dy[l0 * Bs:l1 * Bs], f2)
+            f1 = self.blocks[0].bn.fuse_spec(P, c.blocks[0].bn) if _want_fuse(self.blocks[1]) else None
+            dy = self.blocks[1].backward(P, c.blocks[1], dy, None, False, False, True, f2 is not None, f1)
             s0, s1 = img_slices
             OH, OW = c.hw0
             bits = c.mask0[s0 * Bs * OH * OW:s1 * Bs * OH * OW] if c.mask0 is not None else None
             dy0 = self.blocks[0].backward_dx_slice(P, c.blocks[0], dy, s0 * Bs, s1 * Bs,
-                                                   (c.y0[s0 * Bs:s1 * Bs], None, None, None, None, 1, None, bits))
+                                                   (c.y0[s0 * Bs:s1 * Bs], None, None, None, None, 1, None, bits), f1 is not None)
             n = (s1 - s0) * Bs
             dimg = E(n, 3, c.H, c.W)
             L.edge_in_dgrad(L.edge_desc(n, c.H, c.W, self.C0, self.stride0, self.adt), dy0, P["conv.0.0.weight"], dimg,
                             self._ews)
             return dimg
-        fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if FUSE_BN_BWD else None
+        fuse = self.blocks[1].bn.fuse_spec(P, c.blocks[1].bn) if _want_fuse(self.blocks[2]) else None
         dy = self.blocks[2].backward_raw(P, c.blocks[2], draw3, G, acc, need_dw, True, fuse)
         dy, _ = _backward_chain(self.blocks[:2], c.blocks[:2], P, dy, G, acc, need_dw, None, fuse is not None,
                                 relu_mask=(c.y0, c.mask0))
