@@ -251,9 +251,12 @@ class BlockNet:
 # (+15.6 ms/step on the data-gradient launches), so it is OFF by default until the epilogue is spread over more warps.
 import os as _os
 
-# FMRI_FUSE_BN: "0" never, "1" always, "auto" (default): only in data-gradient launches whose contraction is deep enough
-# (>= 128 channels x 25 taps per tile) that the persistent kernel's heavier epilogue still hides behind the next tile's main loop.
-FUSE_BN_MODE = _os.environ.get("FMRI_FUSE_BN", "auto")
+# FMRI_FUSE_BN: "0" never (default), "1" always, "auto": only in data-gradient launches with a deep contraction (>= 128 channels
+# x 25 taps per tile). Measured at batch 4096 on one B200 (round 2, same box): off 110.9 ms/step (igemm 47.4, BN backward 18.6),
+# auto 113.5 (56.2 / 13.3), always 114.7 (57.8 / 11.9). Even where the epilogue hides behind the next tile's MMAs the fused
+# launch still has to read the pre-BN tensor (the same bytes the separate reduction pass reads at 4.8 TB/s) and that traffic
+# competes with the TMA operand stream of an L2-bandwidth-bound kernel: the pass it removes is cheaper than the slowdown it causes.
+FUSE_BN_MODE = _os.environ.get("FMRI_FUSE_BN", "0")
 FUSE_BN_BWD = FUSE_BN_MODE != "0"
 
 
