@@ -42,6 +42,33 @@ CONFIG_OF = {"stage1_vaegan": "configs[4] (configs[0] at --batch 64)", "stage1_w
 METRIC = "stage1_vaegan_train_samples_per_sec_64x64"  # BASELINE.json metric; other workloads rename it below
 
 
+def stage1_alg_mflop(cfg, z):
+    """Algorithmic MFLOP per sample of the Stage-I VAE/GAN step for an architecture dict (same accounting as ALG_MFLOP /
+    tests/test_flops_cpu.py: 2 x MACs of the necessary contractions; a transposed conv counts its input grid)."""
+    def conv(cin, cout, oh, ow):
+        return 2.0 * oh * ow * cin * cout * 25
+
+    half = lambda v: (v - 1) // 2 + 1
+    s = cfg["image_size"]
+    e, d, c = cfg["encoder_channels"], cfg["decoder_channels"], cfg["discrim_channels"]
+    h1, h2, h3 = half(s), half(half(s)), half(half(half(s)))
+    enc_c = [conv(3, e[0], h1, h1), conv(e[0], e[1], h2, h2), conv(e[1], e[2], h3, h3)]
+    E = sum(enc_c) + 2.0 * h3 * h3 * e[2] * cfg["fc_output"] + 2 * 2.0 * cfg["fc_output"] * z
+    f = cfg["fc_input"]
+    g1 = 2 * f - 1 + int(cfg["output_pad_dec"][0])
+    g2 = 2 * g1 - 1 + int(cfg["output_pad_dec"][1])
+    g3 = 2 * g2 - 1 + int(cfg["output_pad_dec"][2])
+    fc = 2.0 * z * f * f * 256
+    D = fc + conv(256, 256, f, f) + conv(256, d[1], g1, g1) + conv(d[1], d[2], g2, g2) + conv(d[2], 3, g3, g3)
+    d0 = (s - 1) // cfg["stride_gan"] + 1
+    d1, d2, d3 = half(d0), half(half(d0)), half(half(half(d0)))
+    c0, c1, c2, c3 = conv(3, c[0], d0, d0), conv(c[0], c[1], d1, d1), conv(c[1], c[2], d2, d2), conv(c[2], c[3], d3, d3)
+    S = c0 + c1 + c2 + c3 + 2.0 * d3 * d3 * c[3] * cfg["fc_output_gan"] + 2.0 * cfg["fc_output_gan"]
+    total = (E + 2 * D + 3 * S) + (3 * S + 3 * (S - c0) + 2 * c0) + (2 * c3 + 3 * (c2 + c1) + c0) + 2 * (2 * D - fc) + D + \
+            (2 * E - enc_c[0])
+    return total / 1e6
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -51,6 +78,9 @@ def parse():
     ap.add_argument("--workload", default="stage1_vaegan", choices=["stage1_vaegan", "stage1_waegan", "stage2_cognitive", "stage3_cognitive", "stage3_dual", "stage1_wae_mmd",
                                                                     "stage2_wae_cognitive", "stage3_wae_cognitive"])
     ap.add_argument("--batch", type=int, default=4096, help="GLOBAL batch (BASELINE.json configs[4]: 4096, strong scaling)")
+    ap.add_argument("--resolution", type=int, default=64, choices=[64, 100], help="architecture block of the reference's "
+                    "configs/models_config.py: 64 (the BASELINE.json configs) or 100 (its ACTIVE 100x100 / latent-512 block; "
+                    "stage1_vaegan only)")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample (BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -367,8 +397,15 @@ def run_ours(args):
         raise SystemExit(f"global batch {args.batch} not divisible by {world} ranks")
     B = args.batch // world
     cfg, z = hp.CFG64, 128
+    if args.resolution == 100:
+        if args.workload != "stage1_vaegan":
+            raise SystemExit("--resolution 100: workload stage1_vaegan only")
+        cfg, z = hp.CFG100, 512
+        ALG_MFLOP["stage1_vaegan"] = stage1_alg_mflop(cfg, z)
+        args.no_cpu_baseline = True      # the CPU / stock-torch legs are the 64x64 restatements
+    IMG = cfg["image_size"]
     gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = (torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1).pin_memory()
+    x_host = (torch.rand(B, 3, IMG, IMG, generator=gen) * 2 - 1).pin_memory()
     if args.workload == "stage1_vaegan":
         P, S = init.init_vaegan(cfg, z, seed=12345)
         tr = engine.VaeGanStage1(P, S, cfg, z, torch.bfloat16, dist_group=group, gate=True)
@@ -567,11 +604,14 @@ def run_ours(args):
         torch.cuda.empty_cache()
         stock = stock_torch_leg(args.workload, B)
     if rank == 0:
-        act_gb = B * 3 * (64 * 64 * 32 + 32 * 32 * 128 + 16 * 16 * 256 + 8 * 8 * 256) * 2 * 2 / 1e9
+        act_gb = B * 3 * (64 * 64 * 32 + 32 * 32 * 128 + 16 * 16 * 256 + 8 * 8 * 256) * 2 * 2 / 1e9 * (IMG / 64.0) ** 2
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
                     data="synthetic", impl="ours",
-                    config=dict(workload=f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})",
+                    config=dict(workload=(f"{args.workload} 64x64 z=128 (BASELINE.json {CONFIG_OF[args.workload]}: global batch {args.batch})"
+                                          if args.resolution == 64 else
+                                          f"{args.workload} 100x100 z=512 (the reference's ACTIVE configs/models_config.py block, "
+                                          f"not a BASELINE.json config: global batch {args.batch})"),
                                 global_batch=args.batch, per_gpu_batch=B, parallelism=f"dp{world}",
                                 l2="inputs larger than L2: per-step activation working set ~%.1f GB per GPU >> 126 MB" % act_gb,
                                 cuda_graph=bool(args.graph),
@@ -590,7 +630,7 @@ def run_ours(args):
 def main():
     global METRIC
     args = parse()
-    METRIC = f"{args.workload}_train_samples_per_sec_64x64"
+    METRIC = f"{args.workload}_train_samples_per_sec_{args.resolution}x{args.resolution}"
     if args.impl == "reference":
         run_reference(args)
     else:
