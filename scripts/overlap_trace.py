@@ -32,13 +32,22 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
 
+    from thesis_fmri_reconstruction_b200 import lib as L
+
+    marker = torch.zeros(1, dtype=torch.int32, device="cuda")
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        tr.step(x, eps, zp)
+        for _ in range(4):          # the first profiled steps absorb CUPTI start-up skew between the ranks; the LAST one is reported
+            td.barrier()
+            torch.cuda.synchronize()
+            L.step_increment(marker)    # a marker kernel the RMSprop step never launches: splits the trace into steps
+            tr.step(x, eps, zp)
         torch.cuda.synchronize()
     td.barrier()
     if rank == 0:
         ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.device_time > 0]
         ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in ev), key=lambda t: t[0])
+        marks = [i for i, k in enumerate(ks) if "step_increment" in k[2]]
+        ks = ks[marks[-1] + 1:]
         t0, t1 = ks[0][0], max(k[1] for k in ks)
         comp = [(a, b) for a, b, n in ks if "fmri::" in n]
         nccl = [(a, b, n) for a, b, n in ks if "nccl" in n.lower()]
