@@ -57,14 +57,18 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
     const int total_tiles = p.N * p.tiles_y;
     const int rows = p.bh * p.PWp;
     constexpr uint32_t TMEM_COLS = 256;           // 5 x 48 + 16
+    // MMA issuers: one warp per filter row kh (warps 1, 7, 8, 9, 10) + warp 11 for the bias-gradient column. The kernel sat at
+    // 54 % tensor-pipe activity with two issuing warps (each tcgen05.mma costs its warp ~40 issue cycles against a 24-cycle
+    // dispatch floor for N = 48); warps 8-11 are the epilogue warps, idle until the single flush at the end.
+    const int n_issuers = p.dbias ? 6 : 5;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&p.mapT);
         for (int s = 0; s < HW_STAGES; ++s) {
             mbar_init(&full_bar[s], 1 + HW_PRODUCERS);
-            mbar_init(&empty_bar[s], 2);   // two issuing warps commit
+            mbar_init(&empty_bar[s], n_issuers);   // every issuing warp commits
         }
-        mbar_init(tmem_full, 2);
+        mbar_init(tmem_full, n_issuers);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -95,11 +99,15 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             }
         }
         __syncwarp();
-    } else if (warp == 1 || warp == 7) {
-        // ================= MMA issuers (warp-converged, elected lane): warp 1 issues kh 0,2,4, warp 7 kh 1,3 + bias ======
-        const int w2 = warp == 1 ? 0 : 1;
-        const uint32_t idesc = umma_idesc_bf16(128, 48, true, true);
-        const uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
+    }
+    const int issuer = warp == 1 ? 0 : (warp == 7 ? 1 : (warp >= 8 ? warp - 6 : -1));   // 0..4 = kh, 5 = bias column
+    if (issuer >= 0 && issuer < n_issuers) {
+        // ================= MMA issuers (warp-converged, elected lane) =================
+        // M = 64: the T tile has at most 64 channels, and an M = 128 instruction would read (and multiply) a second, all-zero
+        // 64-row half of A from shared memory on every MMA -- the kernel ran at 97 % shared-memory throughput. With M = 64
+        // the accumulator row r sits in TMEM lane 32 * (r / 16) + r % 16 (scripts/probes/m64_layout_probe.cu, measured).
+        const uint32_t idesc = umma_idesc_bf16(64, 48, true, true);
+        const uint32_t idesc1 = umma_idesc_bf16(64, 16, true, true);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         // B (image slab, MN-major, no swizzle): 16-byte N chunks one slab row apart; K advances in 8-pixel groups of 128 B.
         const uint32_t b_lbo = p.desc_variant ? 16 : 128, b_sbo = p.desc_variant ? 128 : 16;
@@ -113,20 +121,23 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             const uint32_t sd = smem_u32(smem + st * stage_bytes);
             const uint32_t ss = sd + 2 * p.d_chunk;
             const uint64_t adesc = umma_smem_desc(sd, p.d_chunk, 8 * 128, UMMA_SW128);   // as wgrad_kernel: LBO = 64-channel chunk
-            const uint64_t bdesc = umma_smem_desc(ss, b_lbo, b_sbo, 0);
-            const uint64_t odesc = umma_smem_desc(smem_u32(s_ones), b_lbo, b_sbo, 0);
-            for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ak = adesc + ((k * 16 * 128) >> 4);
-                const uint32_t acc = (it | k) != 0;
-#pragma unroll
-                for (int kh = w2; kh < 5; kh += 2)
-                    umma_bf16_elect(tmem_u + kh * 48, ak, bdesc + (uint32_t)(k * 16 + kh * p.PWp), idesc, acc);
-                if (p.dbias && w2 == 1) umma_bf16_elect(tmem_u + 240, ak, odesc + (uint32_t)(k * 16), idesc1, acc);
+            if (issuer < 5) {
+                const uint64_t bdesc = umma_smem_desc(ss, b_lbo, b_sbo, 0) + (uint32_t)(issuer * p.PWp);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16_elect(tmem_u + issuer * 48, adesc + ((k * 16 * 128) >> 4), bdesc + (uint32_t)(k * 16), idesc,
+                                    (it | k) != 0);
+            } else {
+                const uint64_t odesc = umma_smem_desc(smem_u32(s_ones), b_lbo, b_sbo, 0);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16_elect(tmem_u + 240, adesc + ((k * 16 * 128) >> 4), odesc + (uint32_t)(k * 16), idesc1, (it | k) != 0);
             }
             umma_commit_elect(&empty_bar[st]);
         }
         umma_commit_elect(tmem_full);
         __syncwarp();
+    }
+    if (warp == 0 || warp == 1 || warp == 7) {
+        // (TMA producer / pure issuer warps: nothing else to do)
     } else if (warp >= 2 && warp < 2 + HW_PRODUCERS / 32) {
         // ================= image halo producers (cp.async 16 B per pixel, zero fill = padding) =================
         const int ptid = threadIdx.x - 64;
@@ -152,13 +163,14 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[st]);
         }
-    } else if (warp >= 8) {
+    }
+    if (warp >= 8) {
         // ================= epilogue: one flush of the accumulators =================
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;
-        const int c = q * 32 + lane;
-        const bool valid = c < p.C;
+        const int c = q * 16 + lane;                 // M = 64 layout: lanes 0..15 of quarter q hold rows 16 q .. 16 q + 15
+        const bool valid = lane < 16 && c < p.C;
         for (int kh = 0; kh < 5; ++kh) {
 #pragma unroll 1
             for (int part = 0; part < 3; ++part) {   // 48 columns = 3 x 16: chunks (2 part, 2 part + 1) of 8 columns
