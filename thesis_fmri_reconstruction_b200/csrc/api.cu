@@ -1125,8 +1125,10 @@ static int hconv_3_to_c(const float* i0, const float* i1, const float* i2, int n
 // up to three fp32 NCHW sources and is repacked to NHWC-8 in the workspace. dwk: fp32 [75][C] (zeroed by the caller).
 // Returns 1 when the shape does not fit (caller falls back to the CUDA-core kernel).
 static int g_hw_variant = -1;
+// plane < 0: stride-1 convolution (images packed here). plane = ph * 2 + pw: one stride-parity plane of a stride-2 convolution --
+// (IH, IW) is the image, (PH, PW) the T grid = the conv output; see HwParams::plane.
 static int hwgrad_run(const void* T, const float* i0, const float* i1, const float* i2, int nps, int N, int PH, int PW, int C,
-                      float* dwk, float* dbias, int flip, void* ws, cudaStream_t st) {
+                      float* dwk, float* dbias, int flip, void* ws, cudaStream_t st, int plane = -1, int IH = 0, int IW = 0) {
     if (g_hw_variant < 0) {
         const char* e = getenv("FMRI_HWGRAD");   // -1/unset: default variant 0; 0/1: descriptor variant; 2: disable
         g_hw_variant = e ? atoi(e) : 0;
@@ -1161,7 +1163,15 @@ static int hwgrad_run(const void* T, const float* i0, const float* i1, const flo
     const int box[4] = {64, p.PWp, p.bh, 1};
     if (make_map(&p.mapT, T, 4, dims, strides, box, 128)) return 1;  // e.g. a box the driver rejects: CUDA-core fallback
     __nv_bfloat16* img8 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ws) + HC_WS_PACK);
-    img8_pack_kernel<<<grid1d((long long)N * PH * PW, 256), 256, 0, st>>>(i0, i1, i2, nps, N, (long long)PH * PW, img8);
+    p.kh0 = 0; p.nkh = 5;
+    if (plane < 0) {
+        img8_pack_kernel<<<grid1d((long long)N * PH * PW, 256), 256, 0, st>>>(i0, i1, i2, nps, N, (long long)PH * PW, img8);
+    } else {
+        p.plane = 1; p.ph = plane >> 1; p.pw = plane & 1;
+        p.kh0 = 1; p.nkh = p.ph ? 2 : 3;      // virtual filter rows kh5 = a + 1 with real kh = 2 a + ph <= 4
+        img8_plane_pack_kernel<<<grid1d((long long)N * PH * PW, 256), 256, 0, st>>>(i0, i1, i2, nps, N, IH, IW, PH, PW, p.ph,
+                                                                                   p.pw, img8);
+    }
     LAUNCH_OK();
     p.img8 = img8;
     p.dwk = dwk; p.dbias = dbias; p.flip = flip; p.desc_variant = g_hw_variant;
@@ -1307,6 +1317,14 @@ extern "C" int fmri_edge_in_wgrad(const fmri_edge_desc* d, const float* img0, co
     rc = 1;
     if (d->dtype == FMRI_BF16 && d->stride == 1 && fmri_tensor_path_available())
         rc = hwgrad_run(dy, img0, img1, img2, n_per_src, d->N, d->H, d->W, d->C, dwk, dbias, 0, ws, S(stream));
+    else if (d->dtype == FMRI_BF16 && d->stride == 2 && !dbias && fmri_tensor_path_available()) {
+        // stride 2 (Encoder.conv[0], vae_gan.py:74): four stride-parity planes of the image, each a unit-shift problem
+        for (int plane = 0; plane < 4; ++plane) {
+            rc = hwgrad_run(dy, img0, img1, img2, n_per_src, d->N, OH, OW, d->C, dwk, nullptr, 0, ws, S(stream), plane, d->H, d->W);
+            if (rc) break;
+        }
+        if (rc == 1) CUDA_OK(cudaMemsetAsync(dwk, 0, sizeof(float) * 75 * (size_t)d->C, S(stream)));   // partial planes: start over
+    }
     if (rc == 1)
         rc = d->C == 32 ? edge_wgrad_t<32>(d->dtype, dy, img0, img1, img2, n_per_src, dwk, dbias, d->N, OH, OW, d->H, d->W,
                                            d->stride, 1, S(stream))

@@ -331,4 +331,28 @@ __global__ void img8_pack_kernel(const float* __restrict__ s0, const float* __re
     }
 }
 
+// One stride-parity plane of 3-channel fp32 NCHW image(s) as bf16 NHWC-8 on the [PH][PW] grid of a stride-2 convolution's
+// output: dst[n][y][x][ci] = img[n][ci][2y + ph][2x + pw] (zero outside the image).
+__global__ void img8_plane_pack_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
+                                       int n_per_src, int N, int IH, int IW, int PH, int PW, int ph, int pw,
+                                       __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)N * PH * PW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % PW);
+        const int y = (int)((i / PW) % PH);
+        const int n = (int)(i / ((long long)PW * PH));
+        const int iy = 2 * y + ph, ix = 2 * x + pw;
+        uint32_t a = 0u, b = 0u;
+        if (iy < IH && ix < IW) {
+            const int si = n / n_per_src;
+            const float* img = (si == 0 ? s0 : (si == 1 ? s1 : s2)) + (long long)(n - si * n_per_src) * 3 * IH * IW +
+                               (long long)iy * IW + ix;
+            const long long HW = (long long)IH * IW;
+            a = pack_bf16x2(__ldg(img), __ldg(img + HW));
+            b = pack_bf16x2(__ldg(img + 2 * HW), 0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(a, b, 0u, 0u);
+    }
+}
+
 }  // namespace fmri

@@ -33,6 +33,12 @@ struct HwParams {
     int desc_variant;            // B descriptor stride assignment (see kernel)
     int stages;                  // pipeline depth (<= HW_MAX_STAGES): the tiles are small, so depth hides the L2 latency
     int d_chunk;                 // bytes between the two 64-channel chunks of an A stage (rows*128 rounded up to 1 KB)
+    // Stride-2 convolutions run as four launches, one per input parity plane (ph, pw): img8 then holds the plane
+    // img[2y + ph][2x + pw] on the T grid, the plane's taps are unit shifts, and virtual tap (kh5, kw5) of this stride-1 kernel
+    // is the real tap (2 (kh5 - 1) + ph, 2 (kw5 - 1) + pw). Only filter rows [kh0, kh0 + nkh) are issued and flushed.
+    int kh0, nkh;                // filter rows handled (0, 5 for a stride-1 convolution)
+    int plane;                   // 0: stride 1; 1: parity-plane launch (remap below)
+    int ph, pw;
 };
 
 constexpr int HW_MAX_STAGES = 8;
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
     // MMA issuers: one warp per filter row kh (warps 1, 7, 8, 9, 10) + warp 11 for the bias-gradient column. The kernel sat at
     // 54 % tensor-pipe activity with two issuing warps (each tcgen05.mma costs its warp ~40 issue cycles against a 24-cycle
     // dispatch floor for N = 48); warps 8-11 are the epilogue warps, idle until the single flush at the end.
-    const int n_issuers = p.dbias ? 6 : 5;
+    const int n_issuers = p.nkh + (p.dbias ? 1 : 0);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&p.mapT);
@@ -121,10 +127,11 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
             const uint32_t sd = smem_u32(smem + st * stage_bytes);
             const uint32_t ss = sd + 2 * p.d_chunk;
             const uint64_t adesc = umma_smem_desc(sd, p.d_chunk, 8 * 128, UMMA_SW128);   // as wgrad_kernel: LBO = 64-channel chunk
-            if (issuer < 5) {
-                const uint64_t bdesc = umma_smem_desc(ss, b_lbo, b_sbo, 0) + (uint32_t)(issuer * p.PWp);
+            if (issuer < p.nkh) {
+                const int kh = p.kh0 + issuer;
+                const uint64_t bdesc = umma_smem_desc(ss, b_lbo, b_sbo, 0) + (uint32_t)(kh * p.PWp);
                 for (int k = 0; k < ksteps; ++k)
-                    umma_bf16_elect(tmem_u + issuer * 48, adesc + ((k * 16 * 128) >> 4), bdesc + (uint32_t)(k * 16), idesc,
+                    umma_bf16_elect(tmem_u + kh * 48, adesc + ((k * 16 * 128) >> 4), bdesc + (uint32_t)(k * 16), idesc,
                                     (it | k) != 0);
             } else {
                 const uint64_t odesc = umma_smem_desc(smem_u32(s_ones), b_lbo, b_sbo, 0);
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
         const int q = warp & 3;
         const int c = q * 16 + lane;                 // M = 64 layout: lanes 0..15 of quarter q hold rows 16 q .. 16 q + 15
         const bool valid = lane < 16 && c < p.C;
-        for (int kh = 0; kh < 5; ++kh) {
+        for (int kh = p.kh0; kh < p.kh0 + p.nkh; ++kh) {
 #pragma unroll 1
             for (int part = 0; part < 3; ++part) {   // 48 columns = 3 x 16: chunks (2 part, 2 part + 1) of 8 columns
                 uint32_t v[16];
@@ -183,6 +190,11 @@ __global__ void __launch_bounds__(HW_THREADS) hwgrad_kernel(const __grid_constan
                     const int kw = part * 2 + h;
                     if (kw >= 5) continue;
                     int tap = kh * 5 + kw;
+                    if (p.plane) {   // virtual tap of the parity plane -> real tap of the stride-2 filter
+                        const int rkh = 2 * (kh - 1) + p.ph, rkw = 2 * (kw - 1) + p.pw;
+                        if (kh < 1 || kw < 1 || rkh > 4 || rkw > 4) continue;
+                        tap = rkh * 5 + rkw;
+                    }
                     if (p.flip) tap = 24 - tap;
 #pragma unroll
                     for (int ci = 0; ci < 3; ++ci)
