@@ -267,13 +267,25 @@ __global__ void __launch_bounds__(HC_THREADS, 2) hconv_kernel(const __grid_const
                         uint32_t v[16];
                         tmem_ld16(tad + c0, v);
                         tmem_ld_wait();
+                        // the epilogue warps' instruction chain is what bounds this kernel: bias and activation are applied
+                        // under warp-uniform branches, so the plain data-gradient use (no bias, no activation) pays for neither
+                        float f[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(v[c]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) f[c] += s_bias[c0 + c];
+                        }
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) f[c] = fmaxf(f[c], 0.f);
+                        } else if (p.act != 0) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) f[c] = hc_act(f[c], p.act);
+                        }
                         uint32_t pk[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float f0 = __uint_as_float(v[2 * c]) + s_bias[c0 + 2 * c];
-                            const float f1 = __uint_as_float(v[2 * c + 1]) + s_bias[c0 + 2 * c + 1];
-                            pk[c] = pack_bf16x2(hc_act(f0, p.act), hc_act(f1, p.act));
-                        }
+                        for (int c = 0; c < 8; ++c) pk[c] = pack_bf16x2(f[2 * c], f[2 * c + 1]);
                         if (valid) {
                             *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
