@@ -10,8 +10,6 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests", "script_harness", "stubs"))
-sys.path.insert(1, "/root/reference")
 
 CASES = {"64": (6, 3, 64, 64, 11), "100": (4, 3, 100, 100, 12), "ragged": (3, 3, 11, 37, 13), "grey": (5, 1, 32, 48, 14)}
 
@@ -24,6 +22,9 @@ def inputs(N, C, H, W, seed):
 
 
 def main():
+    # only here: the tests import `inputs` from this module and must not get the reference tree on their sys.path
+    sys.path.insert(0, os.path.join(ROOT, "tests", "script_harness", "stubs"))
+    sys.path.insert(1, "/root/reference")
     from train.train_utils import PearsonCorrelation, StructuralSimilarity
 
     pc, ss = PearsonCorrelation(), StructuralSimilarity()
