@@ -50,6 +50,8 @@ CONV_CASES = [
     (8, 8, 8, 128, 256),
     (3, 16, 16, 256, 256),
     (3, 25, 25, 32, 128),   # 100x100 config: odd grid, 32-channel side -> parity-merged data gradient with ragged classes
+    (40, 64, 64, 32, 128),  # Discriminator block 1 at its real grid, >= 296 tiles: the row-reuse gather (tall TMA boxes)
+    (5, 64, 64, 32, 128),   # the same below the persistent threshold (row reuse only in the forced-persistent child run)
 ]
 
 
@@ -129,6 +131,7 @@ CONVT_CASES = [
     (2, 32, 32, 128, 32, 1),
     (3, 13, 13, 64, 64, 0),
     (3, 13, 13, 128, 32, 0),  # odd output (25x25) through the parity-merged scatter
+    (40, 32, 32, 64, 32, 1),  # Decoder block 3 at its real grid: its data gradient is a row-reuse gather with N = 64
 ]
 
 

@@ -131,12 +131,12 @@ static int launch_ig(const IgParams& p, int classes, cudaStream_t st) {
     LAUNCH_OK();
     return 0;
 }
-template <int BN, int KCH, int STAGES, int MT, bool EXTRA>
+template <int BN, int KCH, int STAGES, int MT, bool EXTRA, bool YR = false>
 static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t st) {
-    using L = IgSmem<BN, KCH, STAGES, MT>;
+    using L = IgSmem<BN, KCH, STAGES, MT, YR, EXTRA, true>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA>,
+        CUDA_OK(cudaFuncSetAttribute(igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA, YR>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_done = true;
     }
@@ -144,15 +144,15 @@ static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t s
     const long long tiles = m_groups * p.n_tiles * classes;
     const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), (227 * 1024) / L::TOTAL));
     const int grid = (int)std::min<long long>(tiles, 148LL * per_sm);
-    igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
+    igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA, YR><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
     LAUNCH_OK();
     return 0;
 }
-template <int BN, int KCH, int STAGES, int MT>
+template <int BN, int KCH, int STAGES, int MT, bool YR = false>
 static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
     // the fused BN-backward-sums / ReLU-mask epilogues live in their own instantiation (register pressure of the common case)
-    if (p.bnb_x || p.mask_y || p.mask_bits) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true>(p, classes, st);
-    return launch_ig_persistent_x<BN, KCH, STAGES, MT, false>(p, classes, st);
+    if (p.bnb_x || p.mask_y || p.mask_bits) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true, YR>(p, classes, st);
+    return launch_ig_persistent_x<BN, KCH, STAGES, MT, false, YR>(p, classes, st);
 }
 static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
 static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)
@@ -164,6 +164,17 @@ static int dispatch_ig_persistent(const IgParams& p_in, int BN, int KCH, int cla
     }
     IgParams p = p_in;
     p.legacy_producer = legacy;
+    static int skip = -1;
+    if (skip < 0) {
+        const char* e = getenv("FMRI_IG_SKIP");
+        skip = e ? atoi(e) : 0;
+    }
+    p.skip = skip;
+    if (p.yr) {   // row-reuse gather (run_gather decided; two M sub-tiles = 8 output rows of one image)
+        if (KCH == 32 && BN == 128) return launch_ig_persistent<128, 32, 4, 2, true>(p, classes, st);
+        if (KCH == 32 && BN == 64) return launch_ig_persistent<64, 32, 3, 2, true>(p, classes, st);
+        return fail(FMRI_ERR_UNSUPPORTED, "row-reuse igemm tile BN=%d KCH=%d not instantiated", BN, KCH);
+    }
     if (KCH == 64) {
         switch (BN) {
             case 256: return launch_ig_persistent<256, 64, 4, 1>(p, classes, st);
@@ -181,17 +192,20 @@ static int dispatch_ig_persistent(const IgParams& p_in, int BN, int KCH, int cla
     }
     return fail(FMRI_ERR_UNSUPPORTED, "persistent igemm tile BN=%d KCH=%d not instantiated", BN, KCH);
 }
+static bool ig_goes_persistent(const IgParams& p, int classes) {
+    static bool env_done = false;
+    if (!env_done) {
+        const char* e = getenv("FMRI_IGEMM_PERSISTENT");
+        if (e) g_ig_persistent = atoi(e);
+        env_done = true;
+    }
+    const long long all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * classes;
+    return g_ig_persistent && p.splits == 1 && (all >= 2 * 148 || g_ig_persistent == 2);  // 2: always (tests)
+}
 static int dispatch_ig(const IgParams& p, int BN, int KCH, int classes, cudaStream_t st) {
     {
-        static bool env_done = false;
-        if (!env_done) {
-            const char* e = getenv("FMRI_IGEMM_PERSISTENT");
-            if (e) g_ig_persistent = atoi(e);
-            env_done = true;
-        }
-        const long long all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * classes;
         g_last_ig_was_persistent = false;
-        if (g_ig_persistent && p.splits == 1 && (all >= 2 * 148 || g_ig_persistent == 2)) {  // 2: always (tests)
+        if (ig_goes_persistent(p, classes)) {
             g_last_ig_was_persistent = true;
             return dispatch_ig_persistent(p, BN, KCH, classes, st);
         }
@@ -272,12 +286,24 @@ static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW
     const int BN = pick_bn(Ng, (long long)p.tiles_x * p.tiles_y * p.tiles_n);
     if (!BN) return fail(FMRI_ERR_UNSUPPORTED, "no N tile for %d", Ng);
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(X);
+    // row reuse (IgSmem YR): thin K side, 32-pixel output rows, two vertically adjacent sub-tiles per CTA
+    p.n_tiles = Ng / BN;
+    p.splits = 1;
+    static int yr_env = -1;
+    if (yr_env < 0) {
+        const char* e = getenv("FMRI_IG_YR");
+        yr_env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool yr = yr_env && stride == 2 && Ck == 32 && p.bw == 32 && p.bh == 4 && p.bn == 1 && OW == 32 && OH % 8 == 0 &&
+                    (BN == 64 || BN == 128) && ig_goes_persistent(p, 1);
+    p.yr = yr ? 1 : 0;
+    const int box_h = yr ? 2 * p.bh + 2 : p.bh;
     if (stride == 2) {
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw) {
                 const int Wp = (W - pw + 1) / 2, Hp = (H - ph + 1) / 2;
                 int rc = make_act_map(&p.mapA[ph * 2 + pw], xb + ((long long)ph * W + pw) * Ck, Ck, Wp, Hp, N,
-                                      2LL * Ck, 2LL * W * Ck, (long long)H * W * Ck, KCH, p.bw, p.bh, p.bn);
+                                      2LL * Ck, 2LL * W * Ck, (long long)H * W * Ck, KCH, p.bw, box_h, p.bn);
                 if (rc) return rc;
             }
     } else {
@@ -315,7 +341,7 @@ static int run_gather(const void* X, int N, int H, int W, int Ck, int OH, int OW
     p.n_total = Ng;
     p.n_tiles = Ng / BN;
     p.splits = 1;
-    p.a_bytes = p.bw * p.bh * p.bn * KCH * 2;
+    p.a_bytes = p.bw * box_h * p.bn * KCH * 2;
     p.out_sn = (long long)OH * OW * Ng;
     p.out_sy = (long long)OW * Ng;
     p.out_sx = Ng;
@@ -1532,13 +1558,18 @@ extern "C" int fmri_colstats(const void* x, int dtype, long long rows, int C, do
     CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double) * C, S(stream)));
     CUDA_OK(cudaMemsetAsync(sq, 0, sizeof(double) * C, S(stream)));
     if (C % 8 == 0 && ((C / 8) >= 256 ? (C / 8) % 256 == 0 : 256 % (C / 8) == 0)) {
-        dim3 g8(cdiv(rows, rpb), std::max(1, std::min(8, (C / 8) / 256)));
+        // wide matrices (the 16384-feature BatchNorm1d of the fc layers): the column blocks already fill the machine, so
+        // each block takes more rows -- with 8 rows per block the 2 x 8 fp64 atomics per thread outweighed the loads
+        // (4096 x 16384 fp32: 0.36 ms, 0.75 TB/s)
+        const int gy = std::max(1, std::min(8, (C / 8) / 256));
+        const int rpb8 = (int)std::max<long long>(rpb, cdiv(rows, std::max(1, (148 * 4) / gy)));
+        dim3 g8(cdiv(rows, rpb8), gy);
         if (dtype == FMRI_BF16)
             bn_reduce8_kernel<0, __nv_bfloat16, __nv_bfloat16><<<g8, 256, 0, S(stream)>>>(
-                reinterpret_cast<const __nv_bfloat16*>(x), nullptr, rows, C, nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb);
+                reinterpret_cast<const __nv_bfloat16*>(x), nullptr, rows, C, nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb8);
         else
             bn_reduce8_kernel<0, float, float><<<g8, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(x), nullptr, rows, C,
-                                                                          nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb);
+                                                                          nullptr, nullptr, nullptr, nullptr, 0, sum, sq, rpb8);
         LAUNCH_OK();
         return 0;
     }

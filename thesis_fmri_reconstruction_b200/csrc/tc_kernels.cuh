@@ -62,6 +62,10 @@ struct IgParams {
                             // (ReLU backward of a bias+ReLU layer fused into the data-gradient epilogue)
     const uint32_t* mask_bits;  // same mask as 1 bit per element of a 32-channel pixel (bits[(offset) >> 5]); preferred over mask_y
     int legacy_producer;    // persistent kernel: 1 = single-lane TMA producer (A/B switch), 0 = warp-converged elected issue
+    int yr;                 // persistent kernel, row-reuse gather (see IgSmem): mapA[plane] boxes are MT*bh+2 rows tall
+    int skip;               // diagnostic (FMRI_IG_SKIP, persistent kernel): bit 0 the producer issues no TMA loads, bit 1 the
+                            // epilogue does nothing but hand the accumulators back, bit 2 no MMAs are issued, bit 3 the
+                            // epilogue skips only its global stores -- which role bounds a launch (results are garbage)
     int merge_oh, merge_ow; // fine output extent
     long long merge_sy;     // fine row stride (elements)
     // Fused BatchNorm-backward statistics (persistent kernel, bf16 output): when this launch is the data gradient that
@@ -78,17 +82,29 @@ struct IgParams {
 
 // MT = number of 128-row M sub-tiles one CTA accumulates against the SAME B (weight) tile: the kernels are bound by
 // L2 -> shared-memory bandwidth (~43 B/clk/SM measured chip-wide), and MT = 2 halves the weight bytes per FLOP.
-template <int BN, int KCH, int STAGES, int MT = 1>
+//
+// YR ("row reuse", stride-2 gather with a thin K side and 32-pixel-wide output rows): the taps kh = py, py+2, py+4 of one
+// filter column read the SAME stride-parity plane shifted by whole rows, so ONE tall box of MT*4+2 rows x 32 pixels per
+// (kw, py) feeds up to three taps: tap i of sub-tile m starts (4m + i) rows (= a multiple of the swizzle period) into the
+// box. 10 boxes of 10 rows instead of 25 x 8 rows: the activation bytes per tile halve, the weights are fetched as before.
+// EXTRA / PERS: what the persistent kernel adds behind the stage ring -- the [4][256] BatchNorm-backward coefficients of its
+// EXTRA instantiations, and a 2 KB per epilogue warp staging buffer through which bf16 output rows are re-ordered into
+// full 32-byte sectors before they are stored (dropped where it does not fit beside four stages, BN = 256 + EXTRA).
+template <int BN, int KCH, int STAGES, int MT = 1, bool YR = false, bool EXTRA = false, bool PERS = false>
 struct IgSmem {
     static constexpr int A_SUB = 128 * KCH * 2;
-    static constexpr int A_BYTES = MT * A_SUB;
-    static constexpr int B_BYTES = BN * KCH * 2;
+    static constexpr int A_BYTES = YR ? (MT * 4 + 2) * 32 * KCH * 2 : MT * A_SUB;
+    static constexpr int B_TAP = BN * KCH * 2;
+    static constexpr int B_BYTES = (YR ? 3 : 1) * B_TAP;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr int STAT_SLOTS = 8;                        // persistent kernel: one private [2][BN] slot per epilogue warp
     static constexpr int BNP_OFF = STAT_OFF + STAT_SLOTS * 2 * BN * 4;  // [4][256] BN-backward coefficients (mean, scale, beta, invstd)
-    static constexpr int TOTAL = BNP_OFF + 4 * 256 * 4 + 1024;  // +1024: manual base alignment
+    static constexpr int BNP_BYTES = (EXTRA || !PERS) ? 4 * 256 * 4 : 0;
+    static constexpr int STG_OFF = (BNP_OFF + BNP_BYTES + 127) & ~127;
+    static constexpr int STG_BYTES = (PERS && STG_OFF + 8 * 2048 + 1024 <= 227 * 1024) ? 8 * 2048 : 0;
+    static constexpr int TOTAL = STG_OFF + STG_BYTES + 1024;  // +1024: manual base alignment
 };
 
 // transposing butterfly: on exit lane l holds the sum over the 32 lanes of f[l]
@@ -395,9 +411,9 @@ constexpr int IGP_THREADS = 64 + 32 * IGP_EPI_WARPS;
 
 // EXTRA = the rarely used epilogue paths (fused BatchNorm-backward sums, fused ReLU mask) are compiled in; the plain
 // instantiation keeps them out of the register allocation of the common case (the epilogue sits at the 168-register cap).
-template <int BN, int KCH, int STAGES, int MT, bool EXTRA = false>
+template <int BN, int KCH, int STAGES, int MT, bool EXTRA = false, bool YR = false>
 __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
-    using L = IgSmem<BN, KCH, STAGES, MT>;
+    using L = IgSmem<BN, KCH, STAGES, MT, YR, EXTRA, true>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -452,6 +468,28 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
         // counters are nested loops instead of a per-stage integer division. A stage of the 32-channel K-chunk layers is
         // only 128-256 tensor-pipe cycles, which the previous single-lane producer (~130 dependent instructions per
         // stage) could not keep up with.
+        if constexpr (YR) {   // one tall activation box + the weights of its (up to) three taps per stage
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
+                if (!tl.any) continue;
+                const int brow0 = tl.nt * BN;
+                for (int g = 0; g < 10; ++g, ++it) {
+                    const int kw = g >> 1, py = g & 1, ntap = 3 - py;
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    if (p.skip & 1) { mbar_arrive_expect_tx_elect(&full_bar[st], 0); continue; }
+                    mbar_arrive_expect_tx_elect(&full_bar[st], p.a_bytes + ntap * L::B_TAP);
+                    uint8_t* sa = smem + st * L::STAGE_BYTES;
+                    tma_load_4d_elect(sa, &p.mapA[py * 2 + (kw & 1)], &full_bar[st], 0, tl.x0[0] + (kw - 2 - (kw & 1)) / 2,
+                                      tl.y0[0] - 1, tl.n0[0]);
+                    for (int i = 0; i < ntap; ++i)
+                        tma_load_2d_elect(sa + L::A_BYTES + i * L::B_TAP, &p.mapB, &full_bar[st], 0,
+                                          ((py + 2 * i) * 5 + kw) * p.n_total + brow0);
+                }
+            }
+        } else
         if (p.legacy_producer) {   // single-lane producer (A/B switch FMRI_IG_PRODUCER=0)
             if (lane == 0) {
                 int it = 0;
@@ -500,6 +538,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                         const int st = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
                         mbar_wait(&empty_bar[st], ph ^ 1);
+                        if (p.skip & 1) { mbar_arrive_expect_tx_elect(&full_bar[st], 0); continue; }
                         mbar_arrive_expect_tx_elect(&full_bar[st], tx_bytes);
                         uint8_t* sa = smem + st * L::STAGE_BYTES;
 #pragma unroll
@@ -530,6 +569,31 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                 const int buf = lt & 1;
                 mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
+                if constexpr (YR) {
+                    for (int g = 0; g < 10; ++g, ++it) {
+                        const int ntap = 3 - (g & 1);
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&full_bar[st], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + st * L::STAGE_BYTES);
+                        for (int i = 0; i < ((p.skip & 4) ? 0 : ntap); ++i) {
+                            const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES + i * L::B_TAP, 16, sbo, layout);
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+                                const uint64_t adesc = umma_smem_desc(sa + (m * 4 + i) * 32 * KCH * 2, 16, sbo, layout);
+#pragma unroll
+                                for (int k = 0; k < KCH / 16; ++k)
+                                    umma_bf16_elect(tmem_u + buf * ACC_COLS + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                                    (g | i | k) != 0);
+                            }
+                        }
+                        umma_commit_elect(&empty_bar[st]);
+                    }
+                    umma_commit_elect(&tfull[buf]);
+                    ++lt;
+                    continue;
+                }
                 const TapClass& tc_ = p.cls[tl.cls];
                 int ks = 0;
                 for (int tap = 0; tap < tc_.num_taps; ++tap) {
@@ -547,7 +611,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                         const uint64_t bdesc = umma_smem_desc(sa + L::A_BYTES, 16, sbo, layout) + brow_off;
 #pragma unroll
                         for (int m = 0; m < MT; ++m) {
-                            if (!tl.live[m]) continue;
+                            if (!tl.live[m] || (p.skip & 4)) continue;
                             const uint64_t adesc = umma_smem_desc(sa + m * L::A_SUB, 16, sbo, layout);
 #pragma unroll
                             for (int k = 0; k < KCH / 16; ++k)
@@ -574,6 +638,28 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
         const int ni = row / (p.bw * p.bh);
         const bool do_stats = p.stat_sum != nullptr;
         const int etid = threadIdx.x - 64;
+        const uint32_t stage_u32 = smem_u32(smem + L::STG_OFF) + (warp - 2) * 2048;   // this warp's store staging (2 KB)
+        // per-channel sums of the tiles processed so far wait in the warps' shared-memory slots and go to the fp64 global
+        // accumulators every 16 tiles (or when the column block changes): two named barriers + BN atomics per flush
+        int stat_nt = -1, stat_cnt = 0;
+        auto flush_stats = [&](int fnt) {
+            named_bar_sync(1, 32 * IGP_EPI_WARPS);
+            const int ncol = p.merge ? 32 : BN;
+            const int cbase = p.merge ? 0 : fnt * BN;
+            for (int i = etid; i < ncol; i += 32 * IGP_EPI_WARPS) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int w = 0; w < L::STAT_SLOTS; ++w) {
+                    a += s_stat[w * 2 * BN + i];
+                    b += s_stat[w * 2 * BN + BN + i];
+                    s_stat[w * 2 * BN + i] = 0.f;
+                    s_stat[w * 2 * BN + BN + i] = 0.f;
+                }
+                atomicAdd(p.stat_sum + cbase + i, (double)a);
+                atomicAdd(p.stat_sq + cbase + i, (double)b);
+            }
+            named_bar_sync(1, 32 * IGP_EPI_WARPS);
+        };
         int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const IgTile tl = ig_decode_tile<MT>(p, t, m_groups);
@@ -581,6 +667,11 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
             const TapClass& c = p.cls[tl.cls];
             const int buf = lt & 1;
             const int nt = tl.nt;
+            if (do_stats && stat_cnt > 0 && (nt != stat_nt || stat_cnt >= 16)) {
+                flush_stats(stat_nt);
+                stat_cnt = 0;
+            }
+            stat_nt = nt;
             mbar_wait(&tfull[buf], (lt >> 1) & 1);
             tc_fence_after();
             // BatchNorm statistics: a warp owns the same 32-column chunk in every M sub-tile (and, for the parity-merged
@@ -595,7 +686,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
             for (int j = 0; j < 32; ++j) sacc[j] = qacc[j] = 0.f;
             float* my_stat = s_stat + (warp - 2) * 2 * BN;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < ((p.skip & 2) ? 0 : BN); c0 += 32) {
 #pragma unroll 1
                 for (int m = 0; m < MT; ++m) {
                     if (!tl.live[m]) continue;
@@ -605,13 +696,14 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     const long long off_tile = c.out_off + (long long)(tl.n0[m] + ni) * p.out_sn +
                                                (long long)(tl.y0[m] + yi) * p.out_sy +
                                                (long long)(tl.x0[m] + xi) * p.out_sx + (long long)nt * BN;
-                    bool valid = valid_tile;
+                    bool valid = valid_tile && !(p.skip & 8);
                     long long off = off_tile;
                     int stat_col = c0;
                     if (p.merge) {
                         const int g = (nt * BN + c0) >> 5;
                         const int ph = g >> 1, pw = (g == 0 || g == 3) ? 1 : 0;   // merged column groups: (0,1),(0,0),(1,0),(1,1)
-                        valid = valid_tile && (2 * (tl.y0[m] + yi) + ph < p.merge_oh) && (2 * (tl.x0[m] + xi) + pw < p.merge_ow);
+                        valid = valid_tile && !(p.skip & 8) && (2 * (tl.y0[m] + yi) + ph < p.merge_oh) &&
+                                (2 * (tl.x0[m] + xi) + pw < p.merge_ow);
                         off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
                         stat_col = 0;
                     }
@@ -672,7 +764,29 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                         uint32_t pk[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                        if (valid) {
+                        if constexpr (L::STG_BYTES > 0) {
+                            // A lane holds 64 contiguous bytes of ONE output row; stored directly, every warp-wide 16-byte
+                            // store touches 32 rows = 32 half-written sectors (the L2 write requests, not the bytes, bound the
+                            // thin-K launches: switching the stores off took 25-43 % off them). Through the warp's staging
+                            // buffer (16-byte chunks XOR-swizzled by row pair: conflict-free both ways) four lanes store one
+                            // row's 64 bytes = two whole sectors per row.
+                            const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                sts_v4(stage_u32 + lane * 64 + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                            const long long offc = off + c0;
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = 8 * j + (lane >> 2);
+                                const long long o_r = __shfl_sync(0xffffffffu, offc, r);
+                                const uint4 v4 = lds_v4(stage_u32 + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
+                                if ((vmask >> r) & 1u)
+                                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_r + (lane & 3) * 8) = v4;
+                            }
+                            __syncwarp();
+                        } else if (valid) {
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -748,26 +862,10 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
-            if (do_stats) {  // flush this tile's per-channel sums (the next tile may belong to another channel block)
-                named_bar_sync(1, 32 * IGP_EPI_WARPS);
-                const int ncol = p.merge ? 32 : BN;
-                const int cbase = p.merge ? 0 : nt * BN;
-                for (int i = etid; i < ncol; i += 32 * IGP_EPI_WARPS) {
-                    float a = 0.f, b = 0.f;
-#pragma unroll
-                    for (int w = 0; w < L::STAT_SLOTS; ++w) {
-                        a += s_stat[w * 2 * BN + i];
-                        b += s_stat[w * 2 * BN + BN + i];
-                        s_stat[w * 2 * BN + i] = 0.f;
-                        s_stat[w * 2 * BN + BN + i] = 0.f;
-                    }
-                    atomicAdd(p.stat_sum + cbase + i, (double)a);
-                    atomicAdd(p.stat_sq + cbase + i, (double)b);
-                }
-                named_bar_sync(1, 32 * IGP_EPI_WARPS);
-            }
+            if (do_stats) ++stat_cnt;
             ++lt;
         }
+        if (do_stats && stat_cnt > 0) flush_stats(stat_nt);
     }
     tc_fence_before();
     __syncthreads();
