@@ -164,6 +164,7 @@ static int dispatch_ig_persistent(const IgParams& p_in, int BN, int KCH, int cla
     }
     IgParams p = p_in;
     p.legacy_producer = legacy;
+    if (p.stat_sum && p.out_fp32) return fail(FMRI_ERR_UNSUPPORTED, "fused column statistics need a bf16 output");
     static int skip = -1;
     if (skip < 0) {
         const char* e = getenv("FMRI_IG_SKIP");

@@ -639,6 +639,9 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
         const bool do_stats = p.stat_sum != nullptr;
         const int etid = threadIdx.x - 64;
         const uint32_t stage_u32 = smem_u32(smem + L::STG_OFF) + (warp - 2) * 2048;   // this warp's store staging (2 KB)
+        // BatchNorm statistics of the stored values: with the staging buffer a lane reads ONE COLUMN of the staged chunk
+        // (32 two-byte loads, conflict-free) -- no 2 x 32 per-thread accumulators, no transposing shuffle reduction
+        constexpr bool SMEM_STATS = (L::STG_BYTES > 0) && !EXTRA;
         // per-channel sums of the tiles processed so far wait in the warps' shared-memory slots and go to the fp64 global
         // accumulators every 16 tiles (or when the column block changes): two named barriers + BN atomics per flush
         int stat_nt = -1, stat_cnt = 0;
@@ -771,6 +774,10 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                             // buffer (16-byte chunks XOR-swizzled by row pair: conflict-free both ways) four lanes store one
                             // row's 64 bytes = two whole sectors per row.
                             const uint32_t sw = (lane >> 1) & 3;
+                            if (SMEM_STATS && do_stats && !valid) {   // rows outside the output do not count
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 sts_v4(stage_u32 + lane * 64 + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -785,6 +792,19 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                                 if ((vmask >> r) & 1u)
                                     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_r + (lane & 3) * 8) = v4;
                             }
+                            if (SMEM_STATS && do_stats) {   // lane = column c0 + lane of the staged (= stored) values
+                                const uint32_t cb = stage_u32 + (lane & 7) * 2;
+                                const uint32_t ch = lane >> 3;
+                                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) {
+                                    const float v = __uint_as_float(lds_u16(cb + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)) << 16);
+                                    s1 += v;
+                                    s2 = fmaf(v, v, s2);
+                                }
+                                my_stat[stat_col + lane] += s1;
+                                my_stat[BN + stat_col + lane] += s2;
+                            }
                             __syncwarp();
                         } else if (valid) {
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + c0;
@@ -793,7 +813,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                                 *reinterpret_cast<uint4*>(o + 8 * j) =
                                     make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                         }
-                        if (do_stats) {
+                        if (!SMEM_STATS && do_stats) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 f[2 * j] = __uint_as_float(pk[j] << 16);
@@ -801,7 +821,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                             }
                         }
                     }
-                    if (do_stats) {
+                    if (!SMEM_STATS && do_stats) {
                         float g2[32];
                         if (EXTRA && p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
                             const int cb = (p.merge ? 0 : nt * BN) + stat_col;
@@ -842,7 +862,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                         pending = true;
                     }
                 }
-                if (do_stats && pending && !p.merge) {   // this chunk's columns are complete for the tile
+                if (!SMEM_STATS && do_stats && pending && !p.merge) {   // this chunk's columns are complete for the tile
                     const float s1 = warp_colsum32(sacc, lane);
                     const float s2 = warp_colsum32(qacc, lane);
                     my_stat[c0 + lane] += s1;
@@ -852,7 +872,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     pending = false;
                 }
             }
-            if (do_stats && pending) {   // merged scatter: every chunk of the tile folded onto channels 0..31
+            if (!SMEM_STATS && do_stats && pending) {   // merged scatter: every chunk of the tile folded onto channels 0..31
                 const float s1 = warp_colsum32(sacc, lane);
                 const float s2 = warp_colsum32(qacc, lane);
                 my_stat[lane] += s1;
