@@ -462,21 +462,35 @@ def test_module_path_frees_saved_state_without_gc():
             loss.backward()
             opt.step()
 
+        def census():
+            n = 0
+            for o in gc.get_objects():
+                try:
+                    if isinstance(o, torch.Tensor) and o.is_cuda:
+                        n += 1
+                except Exception:
+                    pass
+            return n
+
         gc.collect()
         gc.disable()
         try:
             for _ in range(2):
                 one()
             torch.cuda.synchronize()
-            m0 = torch.cuda.memory_allocated()
-            for _ in range(4):
+            m0, n0 = torch.cuda.memory_allocated(), census()
+            for _ in range(6):
                 one()
             torch.cuda.synchronize()
-            m1 = torch.cuda.memory_allocated()
+            m1, n1 = torch.cuda.memory_allocated(), census()
         finally:
             gc.enable()
-    print("allocated after 2 steps", m0, "after 6 steps", m1)
-    assert m1 <= m0 + (1 << 20), (m0, m1)
+    print("allocated after 2 steps", m0, "after 8 steps", m1, "live CUDA tensors", n0, n1)
+    # no tensor survives a step (a trapped cycle would add its tensors every step) ...
+    assert n1 == n0, (n0, n1)
+    # ... and the allocation does not grow: one step's saved state is > 100 MB, the caching allocator's block rounding
+    # moves memory_allocated() by a few MB from step to step (measured +-3.7 MB with an unchanged tensor census)
+    assert m1 <= m0 + (8 << 20), (m0, m1)
 
 
 @pytest.mark.parametrize("level", [1, 2])

@@ -81,10 +81,19 @@ def put(dst, src):
     dst.copy_(s.reshape(dst.shape).to(dst.dtype))
 
 
+def put_flat(dst, src, chw):
+    """A flattened conv output feeding an fc layer: the oracle flattens NCHW, the kernels keep (h, w, c) columns when the
+    layer's packs are permuted (nets.LinearOp chw)."""
+    C_, h, w = chw
+    s = src.cuda() if not src.is_cuda else src
+    dst.copy_(s.reshape(-1, C_, h, w).permute(0, 2, 3, 1).reshape(dst.shape).to(dst.dtype))
+
+
 class Forcer:
     def __init__(self, P):
         self.P = {k: v.cuda() for k, v in P.items()}
         self.moved, self.total = 0, 0
+        self.enc_chw = self.dis_chw = None   # set by the test from nets.*.fc.lin.chw
 
     def bn(self, c, taps, pre):
         """c: nets BatchNorm ctx (raw, mean, invstd); taps[pre + 'raw' / 'mean' / 'invstd'] from the oracle."""
@@ -104,7 +113,10 @@ class Forcer:
         for i, c in enumerate(ce.blocks, start=1):
             put(c.x, taps[f"{pre}conv.{i}.in"])
             self.bn(c.bn, taps, f"{pre}conv.{i}.bn.")
-        put(ce.fc.x, taps[pre + "fc.in"])
+        if self.enc_chw is not None:
+            put_flat(ce.fc.x, taps[pre + "fc.in"], self.enc_chw)
+        else:
+            put(ce.fc.x, taps[pre + "fc.in"])
         self.bn(ce.fc.bn, taps, pre + "fc.1.")
         put(ce.heads.h, taps[pre + "h"])
 
@@ -128,7 +140,10 @@ class Forcer:
             if i > 1:
                 put(c.x, taps[f"{pre}conv.{i}.in"])
             self.bn(c.bn, taps, f"{pre}conv.{i}.bn.")
-        put(cc.fc.x, taps[pre + "fc.in"])
+        if self.dis_chw is not None:
+            put_flat(cc.fc.x, taps[pre + "fc.in"], self.dis_chw)
+        else:
+            put(cc.fc.x, taps[pre + "fc.in"])
         self.bn(cc.fc.bn, taps, pre + "fc.1.")
         put(cc.hfc, taps[pre + "h"])
         put(cc.p, p.reshape(-1))
@@ -149,6 +164,7 @@ def test_stage1_teacher_forced_backward_bf16(B):
     tr = engine.VaeGanStage1(P, S, hp.CFG64, 128, BF)
     st = tr.forward(x.cuda(), eps.cuda(), z_p.cuda())
     f = Forcer(P)
+    f.enc_chw, f.dis_chw = tr.enc.fc.lin.chw, tr.dis.fc.lin.chw
     f.encoder(st.ce, taps["enc"])
     put(st.mu, ref32["mu"])
     put(st.lv, ref32["logvar"])

@@ -316,12 +316,22 @@ def _backward_chain(blocks, ctxs, P, dy, G, acc, need_dw, lower=None, first_read
 # ====================================================================================================== linear pieces
 class LinearOp:
     """nn.Linear on [M, K] row-major activations. bf16 mode keeps two bf16 packs of the fp32 master weight: wp [N, Kp]
-    (fprop) and wpt [K, Np] (dgrad), pitches padded to 8 elements (16-byte TMA pitch; K = 3620 voxels -> 3624)."""
+    (fprop) and wpt [K, Np] (dgrad), pitches padded to 8 elements (16-byte TMA pitch; K = 3620 voxels -> 3624).
 
-    def __init__(self, wname, bname, N, K, adt):
+    chw = (C, h, w): the layer consumes a flattened conv output. The reference flattens NCHW (vae_gan.py:89,180), the conv
+    kernels here produce NHWC; instead of transposing the activations (and their gradients) every step, the PACKS carry the
+    columns in (h, w, c) order -- the [M, K] activation matrix is then just a view of the NHWC tensor -- and the weight
+    gradient is computed in that order and transposed back into the reference layout once (a pass over K*N weights instead
+    of four passes over M*K activations)."""
+
+    def __init__(self, wname, bname, N, K, adt, chw=None):
         self.wname, self.bname, self.N, self.K, self.adt = wname, bname, N, K, adt
         self.Kp, self.Np = _pad8(K), _pad8(N)
         self.wp = self.wpt = None
+        self.chw = chw if adt == BF16 else None
+        if self.chw is not None and (self.Kp != K or self.Np != N or chw[0] * chw[1] * chw[2] != K):
+            raise L.FmriError("permuted linear packs need unpadded K and N")
+        self._dw = None
 
     def names(self):
         return [self.wname] + ([self.bname] if self.bname else [])
@@ -331,6 +341,11 @@ class LinearOp:
             return
         if self.wp is None or not inplace:
             self.wp, self.wpt = Z(self.N, self.Kp, dtype=BF16), Z(self.K, self.Np, dtype=BF16)
+        if self.chw is not None:
+            C_, h, w = self.chw
+            L.nchw_to_nhwc(P[self.wname], self.wp, self.N, C_, h, w)      # every weight row: [C][hw] -> [hw][C], bf16
+            L.nchw_to_nhwc(self.wp, self.wpt, 1, self.N, 1, self.K)       # [N][K] -> [K][N]
+            return
         L.linear_pack_weights(L.linear_desc(1, self.N, self.K, BF16), P[self.wname], self.wp, self.Kp, self.wpt, self.Np)
 
     def packs(self):
@@ -347,7 +362,14 @@ class LinearOp:
                        accumulate)
 
     def wgrad(self, x, ldx, dy, lddy, M, G, acc):
-        L.linear_wgrad(L.linear_desc(M, self.N, self.K, self.adt), x, ldx, dy, lddy, G[self.wname], acc)
+        if self.chw is not None:   # gradient in (h, w, c) column order, then back to the reference's (c, h, w)
+            if self._dw is None:
+                self._dw = E(self.N, self.K)
+            C_, h, w = self.chw
+            L.linear_wgrad(L.linear_desc(M, self.N, self.K, self.adt), x, ldx, dy, lddy, self._dw, False)
+            L.nhwc_to_nchw(self._dw, G[self.wname], self.N, C_, h, w, acc)
+        else:
+            L.linear_wgrad(L.linear_desc(M, self.N, self.K, self.adt), x, ldx, dy, lddy, G[self.wname], acc)
         if self.bname:
             if not acc:
                 G[self.bname].zero_()
@@ -360,10 +382,11 @@ class LinearBlock:
     """nn.Linear(bias=False) -> BatchNorm1d -> ReLU (Encoder.fc, Decoder.fc, Discriminator.fc[0:3], CognitiveEncoder.fc1).
     The pre-BN output is kept in fp32 (split-K accumulates in fp32; BN statistics from unrounded values)."""
 
-    def __init__(self, wname, bn_prefix, N, K, adt):
-        self.lin = LinearOp(wname, None, N, K, adt)
+    def __init__(self, wname, bn_prefix, N, K, adt, chw=None):
+        self.lin = LinearOp(wname, None, N, K, adt, chw)
         self.bn = BatchNorm(bn_prefix, N)
         self.N, self.K, self.adt = N, K, adt
+        self.nhwc_in = self.lin.chw is not None   # the input matrix is the NHWC conv output itself
 
     def names(self):
         return self.lin.names() + self.bn.names()
@@ -447,7 +470,7 @@ class EncoderNet:
         self.bn0 = BatchNorm("conv.0.bn.", ch[0])
         self.blocks = [ConvBlock(f"conv.{i}.", ch[i - 1], ch[i], False, 0, adt) for i in (1, 2)]
         self.fi = cfg["fc_input"]
-        self.fc = LinearBlock("fc.0.weight", "fc.1.", cfg["fc_output"], self.fi ** 2 * ch[2], adt)
+        self.fc = LinearBlock("fc.0.weight", "fc.1.", cfg["fc_output"], self.fi ** 2 * ch[2], adt, (ch[2], self.fi, self.fi))
         self.heads = LatentHeads(z, cfg["fc_output"], adt)
         self.Clast = ch[2]
         self._ews = None
@@ -482,8 +505,11 @@ class EncoderNet:
             y, c = b.forward(P, S, y, B, h, w, train, n_updates, nbt)
             cs.append(c)
             h, w = c.OH, c.OW
-        flat = E(B, self.Clast * h * w, dtype=self.adt)
-        L.nhwc_to_nchw(y, flat, B, self.Clast, h, w)  # the reference flattens NCHW (vae_gan.py:89)
+        if self.fc.nhwc_in:   # the fc packs carry their columns in (h, w, c) order: no activation transpose
+            flat = y.view(B, -1)
+        else:
+            flat = E(B, self.Clast * h * w, dtype=self.adt)
+            L.nhwc_to_nchw(y, flat, B, self.Clast, h, w)  # the reference flattens NCHW (vae_gan.py:89)
         hfc, cfc = self.fc.forward(P, S, flat, flat.shape[1], B, train, n_updates, nbt)
         ycat, ch = self.heads.forward(P, hfc, B)
         return ycat, Ctx(x=x, d0=d0, c0=c0, blocks=cs, fc=cfc, heads=ch, B=B, hw=(h, w))
@@ -498,8 +524,11 @@ class EncoderNet:
         if after_fc is not None:
             after_fc()
         h, w = c.hw
-        dy = E(B, h, w, self.Clast, dtype=self.adt)
-        L.nchw_to_nhwc(dflat, dy, B, self.Clast, h, w)
+        if self.fc.nhwc_in:
+            dy = dflat.view(B, h, w, self.Clast)
+        else:
+            dy = E(B, h, w, self.Clast, dtype=self.adt)
+            L.nchw_to_nhwc(dflat, dy, B, self.Clast, h, w)
         dy, ready = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, (self.bn0, c.c0))
         draw0 = self.bn0.backward(P, c.c0, dy, G, acc, need_dw, ready)
         if need_dw:
@@ -593,7 +622,7 @@ class DiscriminatorNet:
         self.blocks = [ConvBlock(f"conv.{i}.", ch[i - 1], ch[i], False, 0, adt) for i in (1, 2, 3)]
         self.Cl = ch[3]
         self.fg = cfg["fc_input_gan"]
-        self.fc = LinearBlock("fc.0.weight", "fc.1.", cfg["fc_output_gan"], self.fg ** 2 * ch[3], adt)
+        self.fc = LinearBlock("fc.0.weight", "fc.1.", cfg["fc_output_gan"], self.fg ** 2 * ch[3], adt, (ch[3], self.fg, self.fg))
         self.F = cfg["fc_output_gan"]
         self._ews = None
         self._ewsm = _EdgeWs()
@@ -637,8 +666,11 @@ class DiscriminatorNet:
         raw3 = cs[self.level - 1].bn.raw
         p = None
         if head:
-            flat = E(N, self.Cl * h * w, dtype=self.adt)
-            L.nhwc_to_nchw(y, flat, N, self.Cl, h, w)  # ten.view(len(ten), -1) on NCHW (vae_gan.py:180)
+            if self.fc.nhwc_in:
+                flat = y.view(N, -1)
+            else:
+                flat = E(N, self.Cl * h * w, dtype=self.adt)
+                L.nhwc_to_nchw(y, flat, N, self.Cl, h, w)  # ten.view(len(ten), -1) on NCHW (vae_gan.py:180)
             hfc, cfc = self.fc.forward(P, S, flat, flat.shape[1], N, train, head_updates, nbt)
             p = E(N)
             L.head_sigmoid_fwd(hfc, P["fc.3.weight"], P["fc.3.bias"], p, N, self.F)
@@ -672,8 +704,11 @@ class DiscriminatorNet:
                            G["fc.3.bias"] if need_dw else None, N, self.F)
         dflat = self.fc.backward(P, c.fc, dh, G, acc, need_dw, True)
         h, w = c.hw
-        dy = E(N, h, w, self.Cl, dtype=self.adt)
-        L.nchw_to_nhwc(dflat, dy, N, self.Cl, h, w)
+        if self.fc.nhwc_in:
+            dy = dflat.view(N, h, w, self.Cl)
+        else:
+            dy = E(N, h, w, self.Cl, dtype=self.adt)
+            L.nchw_to_nhwc(dflat, dy, N, self.Cl, h, w)
         dy, _ = _backward_chain(self.blocks, c.blocks, P, dy, G, acc, need_dw, relu_mask=(c.y0, c.mask0))
         return self._conv0_backward(P, c, dy, G, acc, need_dw, img_slices)
 
