@@ -131,7 +131,7 @@ static int launch_ig(const IgParams& p, int classes, cudaStream_t st) {
     LAUNCH_OK();
     return 0;
 }
-template <int BN, int KCH, int STAGES, int MT, bool EXTRA, bool YR = false>
+template <int BN, int KCH, int STAGES, int MT, int EXTRA, bool YR = false>
 static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t st) {
     using L = IgSmem<BN, KCH, STAGES, MT, YR, EXTRA, true>;
     static bool attr_done = false;
@@ -151,8 +151,9 @@ static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t s
 template <int BN, int KCH, int STAGES, int MT, bool YR = false>
 static int launch_ig_persistent(const IgParams& p, int classes, cudaStream_t st) {
     // the fused BN-backward-sums / ReLU-mask epilogues live in their own instantiation (register pressure of the common case)
-    if (p.bnb_x || p.mask_y || p.mask_bits) return launch_ig_persistent_x<BN, KCH, STAGES, MT, true, YR>(p, classes, st);
-    return launch_ig_persistent_x<BN, KCH, STAGES, MT, false, YR>(p, classes, st);
+    if (p.bnb_x) return launch_ig_persistent_x<BN, KCH, STAGES, MT, 2, YR>(p, classes, st);
+    if (p.mask_y || p.mask_bits) return launch_ig_persistent_x<BN, KCH, STAGES, MT, 1, YR>(p, classes, st);
+    return launch_ig_persistent_x<BN, KCH, STAGES, MT, 0, YR>(p, classes, st);
 }
 static bool g_last_ig_was_persistent = false;  // set by dispatch_ig (host-thread confined, like g_launches)
 static int g_ig_persistent = 1;  // FMRI_IGEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel (A/B comparison)

@@ -90,7 +90,7 @@ struct IgParams {
 // EXTRA / PERS: what the persistent kernel adds behind the stage ring -- the [4][256] BatchNorm-backward coefficients of its
 // EXTRA instantiations, and a 2 KB per epilogue warp staging buffer through which bf16 output rows are re-ordered into
 // full 32-byte sectors before they are stored (dropped where it does not fit beside four stages, BN = 256 + EXTRA).
-template <int BN, int KCH, int STAGES, int MT = 1, bool YR = false, bool EXTRA = false, bool PERS = false>
+template <int BN, int KCH, int STAGES, int MT = 1, bool YR = false, int EXTRA = 0, bool PERS = false>
 struct IgSmem {
     static constexpr int A_SUB = 128 * KCH * 2;
     static constexpr int A_BYTES = YR ? (MT * 4 + 2) * 32 * KCH * 2 : MT * A_SUB;
@@ -101,7 +101,7 @@ struct IgSmem {
     static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr int STAT_SLOTS = 8;                        // persistent kernel: one private [2][BN] slot per epilogue warp
     static constexpr int BNP_OFF = STAT_OFF + STAT_SLOTS * 2 * BN * 4;  // [4][256] BN-backward coefficients (mean, scale, beta, invstd)
-    static constexpr int BNP_BYTES = (EXTRA || !PERS) ? 4 * 256 * 4 : 0;
+    static constexpr int BNP_BYTES = (EXTRA == 2 || !PERS) ? 4 * 256 * 4 : 0;
     static constexpr int STG_OFF = (BNP_OFF + BNP_BYTES + 127) & ~127;
     static constexpr int STG_BYTES = (PERS && STG_OFF + 8 * 2048 + 1024 <= 227 * 1024) ? 8 * 2048 : 0;
     static constexpr int TOTAL = STG_OFF + STG_BYTES + 1024;  // +1024: manual base alignment
@@ -409,9 +409,10 @@ __device__ __forceinline__ IgTile ig_decode_tile(const IgParams& p, int t, int m
 constexpr int IGP_EPI_WARPS = 8;
 constexpr int IGP_THREADS = 64 + 32 * IGP_EPI_WARPS;
 
-// EXTRA = the rarely used epilogue paths (fused BatchNorm-backward sums, fused ReLU mask) are compiled in; the plain
+// EXTRA = 1: the fused ReLU-mask epilogue is compiled in; EXTRA = 2: also the fused BatchNorm-backward sums (which keep the
+// register-accumulated statistics path and its 64 accumulators); the plain
 // instantiation keeps them out of the register allocation of the common case (the epilogue sits at the 168-register cap).
-template <int BN, int KCH, int STAGES, int MT, bool EXTRA = false, bool YR = false>
+template <int BN, int KCH, int STAGES, int MT, int EXTRA = 0, bool YR = false>
 __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __grid_constant__ IgParams p, int num_classes) {
     using L = IgSmem<BN, KCH, STAGES, MT, YR, EXTRA, true>;
     extern __shared__ uint8_t smem_raw[];
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     for (int i = threadIdx.x; i < L::STAT_SLOTS * 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
     float* s_bnp = reinterpret_cast<float*>(smem + L::BNP_OFF);
-    if (EXTRA && p.bnb_x) {
+    if (EXTRA == 2 && p.bnb_x) {
         const int nch = p.merge ? 32 : p.n_total;  // channels of the BN layer (<= 256)
         for (int i = threadIdx.x; i < nch; i += blockDim.x) {
             const float is = p.bnb_invstd[i];
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
         const uint32_t stage_u32 = smem_u32(smem + L::STG_OFF) + (warp - 2) * 2048;   // this warp's store staging (2 KB)
         // BatchNorm statistics of the stored values: with the staging buffer a lane reads ONE COLUMN of the staged chunk
         // (32 two-byte loads, conflict-free) -- no 2 x 32 per-thread accumulators, no transposing shuffle reduction
-        constexpr bool SMEM_STATS = (L::STG_BYTES > 0) && !EXTRA;
+        constexpr bool SMEM_STATS = (L::STG_BYTES > 0) && EXTRA != 2;
         // per-channel sums of the tiles processed so far wait in the warps' shared-memory slots and go to the fp64 global
         // accumulators every 16 tiles (or when the column block changes): two named barriers + BN atomics per flush
         int stat_nt = -1, stat_cnt = 0;
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     }
                     // fused ReLU mask as a bit word (one 4-byte load, issued before the TMEM load so its latency hides)
                     uint32_t mbits = 0xffffffffu;
-                    if (EXTRA && p.mask_bits && valid) mbits = __ldg(p.mask_bits + ((off + c0) >> 5));
+                    if (EXTRA >= 1 && p.mask_bits && valid) mbits = __ldg(p.mask_bits + ((off + c0) >> 5));
                     uint32_t v[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + m * BN + c0, v);
                     tmem_ld_wait();
@@ -734,11 +735,11 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
                     }
-                    if (EXTRA && p.mask_bits) {
+                    if (EXTRA >= 1 && p.mask_bits) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (!((mbits >> j) & 1u)) f[j] = 0.f;
-                    } else if (EXTRA && p.mask_y && valid) {
+                    } else if (EXTRA >= 1 && p.mask_y && valid) {
                         const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mask_y) + off + c0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
                     }
                     if (!SMEM_STATS && do_stats) {
                         float g2[32];
-                        if (EXTRA && p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
+                        if (EXTRA == 2 && p.bnb_x) {  // BN-backward sums: f <- g = dy * relu-mask, g2 <- g * xhat
                             const int cb = (p.merge ? 0 : nt * BN) + stat_col;
                             float xv[32];
                             if (valid) {
