@@ -512,13 +512,14 @@ def test_persistent_path_subprocess():
     """The persistent implicit-GEMM kernel (double-buffered TMEM accumulators, warp-converged producer, per-tap column ranges
     of the parity-merged scatter) only takes over at >= 296 tiles, which the kernel-level cases above do not reach. The library
     reads FMRI_IGEMM_PERSISTENT once per process, so the conv / convT cases are re-run in a child process with the
-    persistent kernel forced for every launch (value 2), at the same tolerances."""
+    persistent kernel forced for every launch (value 2), at the same tolerances. The child also forces the chunk-pair
+    (128-byte-line) store path of the epilogue for every form (FMRI_IG_PAIR=2; by default only the BN = 128 gathers take it)."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FMRI_IGEMM_PERSISTENT="2")
+    env = dict(os.environ, FMRI_IGEMM_PERSISTENT="2", FMRI_IG_PAIR="2")   # and the 128-byte-line store path in every form
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q",
                         "-x", "-p", "no:cacheprovider", "-k",
                         "conv_s2_dgrad or convT_fprop or conv_s2_fprop or fused_bn"],

@@ -142,7 +142,14 @@ static int launch_ig_persistent_x(const IgParams& p, int classes, cudaStream_t s
     }
     const long long m_groups = cdiv((long long)p.tiles_x * p.tiles_y * p.tiles_n, MT);
     const long long tiles = m_groups * p.n_tiles * classes;
-    const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), (227 * 1024) / L::TOTAL));
+    // resident CTAs per SM: TMEM columns, shared memory and registers (asked from the runtime once per instantiation)
+    static int occ = 0;
+    if (!occ) {
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA, YR>,
+                                                              IGP_THREADS, L::TOTAL));
+        occ = std::max(1, occ);
+    }
+    const int per_sm = std::max(1, std::min<int>(std::min(2, 512 / (2 * MT * BN)), occ));
     const int grid = (int)std::min<long long>(tiles, 148LL * per_sm);
     igemm_persistent_kernel<BN, KCH, STAGES, MT, EXTRA, YR><<<grid, IGP_THREADS, L::TOTAL, st>>>(p, classes);
     LAUNCH_OK();
@@ -172,6 +179,15 @@ static int dispatch_ig_persistent(const IgParams& p_in, int BN, int KCH, int cla
         skip = e ? atoi(e) : 0;
     }
     p.skip = skip;
+    static int pair = -1;
+    if (pair < 0) {
+        const char* e = getenv("FMRI_IG_PAIR");
+        pair = e ? atoi(e) : 1;
+    }
+    // measured per form (scripts/igemm_probe.py, FMRI_IG_PAIR=0/1): 128-byte-line stores take 11 % off the BN = 128 gathers
+    // (two-pass staging hides behind their short K loop) but cost 5-7 % on the parity-merged scatter and on BN = 256,
+    // where holding two chunks before the first store lengthens the epilogue's critical path; 2 = force everywhere (tests)
+    p.pair = (pair == 2 || (pair && !p.merge && BN == 128)) ? 1 : 0;
     if (p.yr) {   // row-reuse gather (run_gather decided; two M sub-tiles = 8 output rows of one image)
         if (KCH == 32 && BN == 128) return launch_ig_persistent<128, 32, 4, 2, true>(p, classes, st);
         if (KCH == 32 && BN == 64) return launch_ig_persistent<64, 32, 3, 2, true>(p, classes, st);

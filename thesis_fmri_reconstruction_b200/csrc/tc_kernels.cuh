@@ -63,6 +63,7 @@ struct IgParams {
     const uint32_t* mask_bits;  // same mask as 1 bit per element of a 32-channel pixel (bits[(offset) >> 5]); preferred over mask_y
     int legacy_producer;    // persistent kernel: 1 = single-lane TMA producer (A/B switch), 0 = warp-converged elected issue
     int yr;                 // persistent kernel, row-reuse gather (see IgSmem): mapA[plane] boxes are MT*bh+2 rows tall
+    int pair;               // persistent kernel: 128-byte-line stores through chunk pairs (A/B switch FMRI_IG_PAIR, default on)
     int skip;               // diagnostic (FMRI_IG_SKIP, persistent kernel): bit 0 the producer issues no TMA loads, bit 1 the
                             // epilogue does nothing but hand the accumulators back, bit 2 no MMAs are issued, bit 3 the
                             // epilogue skips only its global stores -- which role bounds a launch (results are garbage)
@@ -689,8 +690,150 @@ __global__ void __launch_bounds__(IGP_THREADS) igemm_persistent_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 32; ++j) sacc[j] = qacc[j] = 0.f;
             float* my_stat = s_stat + (warp - 2) * 2 * BN;
+            // PAIR path (bf16 output, BN >= 64): a warp takes two ADJACENT 32-column chunks of its 32 rows, so that a row's
+            // 128 contiguous output bytes (for the parity-merged scatter: the two fine pixels 2x, 2x+1 of a coarse pixel) leave
+            // as ONE whole 128-byte line written by eight lanes. The 2 KB staging buffer holds 16 rows x 128 B per pass
+            // (16-byte pieces XOR-swizzled by row: conflict-free stores, loads and column reads); two passes per pair.
+            constexpr bool PAIR = SMEM_STATS && BN >= 64;
+            bool pair_done = false;
+            if constexpr (PAIR) {
+                if (!p.out_fp32 && p.pair) {
+                    pair_done = true;
+                    constexpr int PPM = BN / 64;        // pairs per M sub-tile
+                    constexpr int NP = MT * PPM;
 #pragma unroll 1
-            for (int c0 = 0; c0 < ((p.skip & 2) ? 0 : BN); c0 += 32) {
+                    for (int pi = half; pi < ((p.skip & 2) ? 0 : NP); pi += 2) {
+                        const int m = pi / PPM;
+                        const int c0p = (pi - m * PPM) * 64;
+                        if (!tl.live[m]) continue;
+                        const bool valid_tile = (ni < p.bn) && (tl.n0[m] + ni < p.lim_n) && (tl.y0[m] + yi < c.lim_y) &&
+                                                (tl.x0[m] + xi < c.lim_x);
+                        const long long off_tile = c.out_off + (long long)(tl.n0[m] + ni) * p.out_sn +
+                                                   (long long)(tl.y0[m] + yi) * p.out_sy +
+                                                   (long long)(tl.x0[m] + xi) * p.out_sx + (long long)nt * BN;
+                        uint32_t pkA[16], pkB[16];
+                        bool vA, vB;
+                        long long aA, aB;   // element offset of this row's 32 channels of chunk A / B in the output
+                        auto chunk = [&](const int c0, uint32_t (&pk)[16], bool& valid, long long& addr) {
+                            valid = valid_tile && !(p.skip & 8);
+                            long long off = off_tile;
+                            if (p.merge) {
+                                const int g = (nt * BN + c0) >> 5;
+                                const int ph = g >> 1, pw = (g == 0 || g == 3) ? 1 : 0;
+                                valid = valid && (2 * (tl.y0[m] + yi) + ph < p.merge_oh) && (2 * (tl.x0[m] + xi) + pw < p.merge_ow);
+                                off = off_tile - (long long)nt * BN + ph * p.merge_sy + pw * 32 - c0;
+                            }
+                            addr = off + c0;
+                            uint32_t mbits = 0xffffffffu;
+                            if (EXTRA >= 1 && p.mask_bits && valid) mbits = __ldg(p.mask_bits + (addr >> 5));
+                            uint32_t v[32];
+                            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + m * BN + c0, v);
+                            tmem_ld_wait();
+                            float f[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                            if (p.bias) {
+                                const float* bp = p.bias + (p.merge ? 0 : nt * BN + c0);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] += __ldg(bp + j);
+                            }
+                            if (p.act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                            } else if (p.act == ACT_TANH) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                            } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+                            }
+                            if (EXTRA >= 1 && p.mask_bits) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (!((mbits >> j) & 1u)) f[j] = 0.f;
+                            } else if (EXTRA >= 1 && p.mask_y && valid) {
+                                const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mask_y) + addr;
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(yp + 8 * j4));
+                                    const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (!(__uint_as_float(rr[j] << 16) > 0.f)) f[8 * j4 + 2 * j] = 0.f;
+                                        if (!(__uint_as_float(rr[j] & 0xffff0000u) > 0.f)) f[8 * j4 + 2 * j + 1] = 0.f;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) pk[j] = (do_stats && !valid) ? 0u : pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                        };
+                        chunk(c0p, pkA, vA, aA);
+                        chunk(c0p + 32, pkB, vB, aB);
+                        const bool a_first = aA < aB;    // warp-uniform: which chunk holds the lower 64 bytes of the run
+                        const long long run = a_first ? aA : aB;
+                        const uint32_t vmF = __ballot_sync(0xffffffffu, a_first ? vA : vB);
+                        const uint32_t vmS = __ballot_sync(0xffffffffu, a_first ? vB : vA);
+                        float sF = 0.f, qF = 0.f, sS = 0.f, qS = 0.f;
+#pragma unroll 1
+                        for (int ps = 0; ps < 2; ++ps) {
+                            if ((lane >> 4) == ps) {
+                                const uint32_t x = lane & 7, base = stage_u32 + (lane & 15) * 128;
+                                if (a_first) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        sts_v4(base + ((j ^ x) << 4), pkA[4 * j], pkA[4 * j + 1], pkA[4 * j + 2], pkA[4 * j + 3]);
+                                        sts_v4(base + (((4 + j) ^ x) << 4), pkB[4 * j], pkB[4 * j + 1], pkB[4 * j + 2], pkB[4 * j + 3]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        sts_v4(base + ((j ^ x) << 4), pkB[4 * j], pkB[4 * j + 1], pkB[4 * j + 2], pkB[4 * j + 3]);
+                                        sts_v4(base + (((4 + j) ^ x) << 4), pkA[4 * j], pkA[4 * j + 1], pkA[4 * j + 2], pkA[4 * j + 3]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r16 = 4 * j + (lane >> 3);
+                                const int src = 16 * ps + r16;
+                                const int piece = lane & 7;
+                                const long long o_r = __shfl_sync(0xffffffffu, run, src);
+                                const uint4 v4 = lds_v4(stage_u32 + r16 * 128 + ((piece ^ (r16 & 7)) << 4));
+                                if ((((piece < 4) ? vmF : vmS) >> src) & 1u)
+                                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_r + piece * 8) = v4;
+                            }
+                            if (do_stats) {   // lane = column `lane` of the first and of the second chunk
+                                const uint32_t cb = stage_u32 + (lane & 7) * 2;
+                                const uint32_t ch = lane >> 3;
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) {
+                                    const float a = __uint_as_float(lds_u16(cb + r * 128 + ((ch ^ (r & 7)) << 4)) << 16);
+                                    const float b = __uint_as_float(lds_u16(cb + r * 128 + (((4 + ch) ^ (r & 7)) << 4)) << 16);
+                                    sF += a;
+                                    qF = fmaf(a, a, qF);
+                                    sS += b;
+                                    qS = fmaf(b, b, qS);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (do_stats) {
+                            if (p.merge) {      // both chunks fold onto channels 0..31
+                                my_stat[lane] += sF + sS;
+                                my_stat[BN + lane] += qF + qS;
+                            } else {            // a_first is true here: first = columns c0p.., second = c0p + 32..
+                                my_stat[c0p + lane] += sF;
+                                my_stat[BN + c0p + lane] += qF;
+                                my_stat[c0p + 32 + lane] += sS;
+                                my_stat[BN + c0p + 32 + lane] += qS;
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < ((p.skip & 2) || pair_done ? 0 : BN); c0 += 32) {
 #pragma unroll 1
                 for (int m = 0; m < MT; ++m) {
                     if (!tl.live[m]) continue;
