@@ -463,13 +463,17 @@ def test_module_path_frees_saved_state_without_gc():
             opt.step()
 
         def census():
+            import warnings
+
             n = 0
-            for o in gc.get_objects():
-                try:
-                    if isinstance(o, torch.Tensor) and o.is_cuda:
-                        n += 1
-                except Exception:
-                    pass
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")   # isinstance() on lazily-deprecated module attributes warns
+                for o in gc.get_objects():
+                    try:
+                        if isinstance(o, torch.Tensor) and o.is_cuda:
+                            n += 1
+                    except Exception:
+                        pass
             return n
 
         gc.collect()
