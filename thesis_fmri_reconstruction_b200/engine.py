@@ -70,6 +70,9 @@ class _TrainerBase:
             for t in tensors:
                 self.td.all_reduce(t, op=self.td.ReduceOp.SUM, group=self.dist)
                 t.record_stream(self.comm_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        return ev   # everything reduced so far on the exchange stream (update() may wait for a prefix of the exchanges)
 
     def _wait_comm(self):
         NN.join_side()
@@ -251,7 +254,7 @@ class VaeGanStage1(_TrainerBase):
         # (3) decoder: g_dec = d [lambda * mse - (1 - lambda) * loss_dis] / d decoder over both decoder calls
         self.dec.backward(bd.P, cd1, lam, dimg_mse, -(1.0 - lam), dimg_bce[:B], bd.G, False, True, False)
         self.dec.backward(bd.P, cd2, -(1.0 - lam), dimg_bce[B:], 0.0, None, bd.G, True, True, False)
-        self._allreduce_async([bd.flat_g])
+        self._ev_dec = self._allreduce_async([bd.flat_g])   # loss sums, discriminator and decoder buckets are reduced here
         # (4) encoder: g_enc = d [sum kl + sum mse] / d encoder; the mse term flows x_tilde -> decoder (data gradient) -> z
         dz = self.dec.backward(bd.P, cd1, 1.0, dimg_mse, 0.0, None, None, False, False, True)
         dycat = E(B, 2 * z, dtype=self.adt)
@@ -285,17 +288,31 @@ class VaeGanStage1(_TrainerBase):
     def update(self, B_global):
         """Equilibrium gate (device side) + the three RMSprop updates (train_vgan_stage1.py:396-432), then repack."""
         hp = self.hp
-        self._wait_comm()
+        # Data parallel: the loss sums, the discriminator and the decoder buckets were exchanged during the encoder sweep, so
+        # the gate, their two updates and their repacks run while the last exchange (the encoder's conv part, issued after the
+        # final backward kernel: 0.2 ms exposed at 8 GPUs in profiles/r2_nccl_overlap_N8_B512_per_rank.txt) is still in flight;
+        # only the encoder update waits for it. The three buckets are independent, so the order changes nothing numerically.
+        ev = getattr(self, "_ev_dec", None)
+        staged = self.world > 1 and ev is not None
+        if staged:
+            NN.join_side()
+            torch.cuda.current_stream().wait_event(ev)
+            self._ev_dec = None
+        else:
+            self._wait_comm()
         gates = self.sc[8:10]
         if self.gate_on:
             L.vgan_gate(self.sc, float(B_global), hp["margin"], hp["equilibrium"], gates)
         else:
             gates.fill_(1.0)
-        for pre, g in (("encoder.", None), ("decoder.", gates[1:2]), ("discriminator.", gates[0:1])):
+        nets = {"encoder.": self.enc, "decoder.": self.dec, "discriminator.": self.dis}
+        for pre, g in (("decoder.", gates[1:2]), ("discriminator.", gates[0:1]), ("encoder.", None)):
+            if pre == "encoder." and staged:
+                self._wait_comm()
             b = self.buckets[pre]
             L.multi_tensor_rmsprop([b.flat_p], [b.flat_g], [b.states[0]], self.lr[pre], hp["alpha"], hp["eps"], 0.0,
                                    None, g)
-        self.refresh()
+            nets[pre].refresh(b.P, inplace=True)
 
     def step(self, x, eps, z_p):
         """One full training iteration on device-resident inputs. Returns the device tensor of loss sums."""
